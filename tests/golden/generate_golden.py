@@ -1,0 +1,213 @@
+"""Generate tests/golden/*.json by running the REAL reference (NumPy arm) from /root/reference.
+
+Run once in the build container (the reference does not travel to the GPU box):
+
+    python tests/golden/generate_golden.py
+
+cvxpy / matplotlib are absent here and only used by the reference for its optional pre-check and
+plots, so empty stub modules are injected; every solver is built with
+``check_cvxpy=False``.  Each Newton class is instrumented (wrapping ``backtrack_search``) to record
+the per-step sizes, which pins the line-search decision sequence (quirks Q1-Q4) and not only the
+final optimum.  Inputs come from the seeded generators in ``tests/problems.py``; fixtures store the
+generator call and the reference's outputs.
+"""
+
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("IPM_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+for name in ("cvxpy", "matplotlib", "matplotlib.pyplot"):
+    sys.modules.setdefault(name, types.ModuleType(name))
+sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+sys.path.insert(0, REF)
+
+import problems  # noqa: E402
+import NewtonSolver as _ns  # noqa: E402
+import NewtonSolverInfeasibleStart as _nsi  # noqa: E402
+from LPSolver import LPSolver  # noqa: E402
+from QPSolver import QPSolver  # noqa: E402
+from SOCPSolver import SOCPSolver  # noqa: E402
+from LassoSolver import LassoSolver  # noqa: E402
+import PhaseOne as _p1  # noqa: E402
+
+STEPS = []
+
+
+def _wrap(cls, infeasible):
+    orig = cls.backtrack_search
+
+    def wrapped(self, *a, **k):
+        r = orig(self, *a, **k)
+        step = r[0] if infeasible else r
+        STEPS.append([bool(getattr(self, "phase1_flag", False)), float(step)])
+        return r
+
+    cls.backtrack_search = wrapped
+
+
+_wrap(_ns.NewtonSolver, False)
+_wrap(_nsi.NewtonSolverInfeasibleStart, True)
+
+
+def _flt(x):
+    return None if x is None else float(x)
+
+
+def run_barrier(cls, gen, gen_kwargs, index, settings, name):
+    prob = getattr(problems, gen)(**gen_kwargs)
+    if isinstance(prob, list):
+        prob = prob[index]
+    STEPS.clear()
+    np.random.seed(0)
+    s = cls(**prob, check_cvxpy=False, suppress_print=True, **settings)
+    ran_phase1 = hasattr(s, "phase1_solver") and s.phase1_solver.phase1_fm.s >= 1
+    val = s.solve()
+    rec = dict(
+        name=name, solver=cls.__name__, generator=gen, generator_kwargs=gen_kwargs, index=index, settings=settings,
+        value=float(val), inner_iters=[int(k) for k in s.inner_iters], outer_iters=int(s.outer_iters),
+        phase1_inner_iters=[int(k) for k in s.phase1_solver.inner_iters] if ran_phase1 else None,
+        xstar=[float(v) for v in np.asarray(s.xstar)], optimality_gap=float(s.optimality_gap),
+        phase1_steps=[st for p, st in STEPS if p], main_steps=[st for p, st in STEPS if not p],
+    )
+    print(name, rec["value"], rec["inner_iters"], rec["phase1_inner_iters"])
+    return rec
+
+
+def group_lasso_socp():
+    """demo.ipynb cells 26-28: SOCP form of the group lasso on example_data (27 vars, 8 cones)."""
+    X = np.loadtxt(os.path.join(REF, "example_data/X_train.csv"), delimiter=",")
+    X = np.hstack([np.ones(X.shape[0])[:, None], X])
+    Y = np.loadtxt(os.path.join(REF, "example_data/Y_train.csv"), delimiter=",")
+    groups = [[0], [1], [2], [3, 4, 5, 6, 7], [8, 9, 10, 11, 12, 13], [14, 15], [16], [17], [18]]
+    w = np.sqrt([len(g) for g in groups])[1:]
+    P = np.zeros((27, 27))
+    P[:19, :19] = 1 / X.shape[0] * X.T @ X
+    q = np.zeros(27)
+    q[:19] = -1 / X.shape[0] * Y.T @ X
+    q[19:] = 0.02 * w
+    A, c = [], []
+    for i in range(len(groups) - 1):
+        Ai, ci = np.zeros((27, 27)), np.zeros(27)
+        Ai[groups[i + 1], groups[i + 1]] = 1
+        ci[i + 19] = 1
+        A.append(Ai), c.append(ci)
+    STEPS.clear()
+    np.random.seed(0)
+    s = SOCPSolver(P=P, q=q, A=[a.copy() for a in A], b=None, c=c, d=None, lower_bound=None, upper_bound=None,
+                   check_cvxpy=False, suppress_print=True)
+    x0 = np.array(s.x).copy()
+    val = s.solve()
+    rec = dict(name="socp_group_lasso", P=P.tolist(), q=q.tolist(), groups=groups, x0=x0.tolist(),
+               value=float(val), offset=float(Y.T @ Y / (2 * X.shape[0])), fstar=49.9649387126726,
+               inner_iters=[int(k) for k in s.inner_iters],
+               phase1_inner_iters=[int(k) for k in s.phase1_solver.inner_iters],
+               xstar=[float(v) for v in s.xstar], main_steps=[st for p, st in STEPS if not p],
+               phase1_steps=[st for p, st in STEPS if p])
+    print("socp_group_lasso", val, val + rec["offset"], rec["inner_iters"], rec["phase1_inner_iters"])
+    return rec
+
+
+def lasso_case(name, gen_kwargs, settings):
+    prob = problems.lasso_testsolver(**gen_kwargs)
+    s = LassoSolver(A=prob["A"].copy(), b=prob["b"], reg=prob["reg"], compute_loss=False, adaptive_rho=False,
+                    use_gpu=False, check_cvxpy=False, **settings)
+    X, sol, _, its = s.solve()
+    rec = dict(name=name, generator="lasso_testsolver", generator_kwargs=gen_kwargs, settings=settings,
+               solutions=[float(v) for v in sol], iterations=its if isinstance(its, list) else int(its),
+               X_col0=[float(v) for v in X[:, 0]], X_frob=float(np.linalg.norm(X)),
+               X_abs_sum=float(np.abs(X).sum()))
+    print(name, rec["solutions"][:3], rec["iterations"])
+    return rec
+
+
+def standalone_phase_one():
+    """Known-answer values of AutomatedTestsPhaseOne.py plus functional polytopes (:235-343)."""
+    out = []
+    # gradient / Hessian / objective KATs are restated analytically in tests/test_phase_one_kat.py;
+    # here: functional runs of the real class
+    cases = {
+        "inside": (np.array([[1.0, 0], [0, 1], [-1, 0], [0, -1]]), np.array([1.0, 1, 1, 1]), np.array([0.0, 0.0])),
+        "outside": (np.array([[1.0, 0], [0, 1], [-1, 0], [0, -1]]), np.array([1.0, 1, 1, 1]), np.array([5.0, 5.0])),
+        "unbounded_set": (np.array([[1.0, 0], [0, 1]]), np.array([1.0, 1]), np.array([5.0, 5.0])),
+        "empty_set": (np.array([[1.0, 0], [-1, 0]]), np.array([-1.0, -1]), np.array([0.0, 0.0])),
+    }
+    for nm, (G, h, x0) in cases.items():
+        s = _p1.PhaseOneSolver(G, h, 15, x0=x0.copy())
+        x, sv, warn = s.solve()
+        out.append(dict(name=nm, G=G.tolist(), h=h.tolist(), x0=x0.tolist(), mu=15, x=[float(v) for v in x],
+                        s=float(sv), warn=bool(warn)))
+        print("phase_one", nm, x, sv, warn)
+    np.random.seed(0)
+    m, n = 200, 1000  # AutomatedTestsPhaseOne.py:325-343 shape; scaled down for fixture speed below
+    m, n = 60, 40
+    G = np.random.randn(m, n)
+    xf = np.random.randn(n)
+    h = G @ xf + np.random.rand(m)
+    s = _p1.PhaseOneSolver(G, h, 15)
+    x, sv, warn = s.solve()
+    out.append(dict(name="random_60x40", seed=0, m=m, n=n, mu=15, s=float(sv), warn=bool(warn),
+                    x=[float(v) for v in x], max_violation=float(np.max(G @ x - h))))
+    print("phase_one random", sv, warn, np.max(G @ x - h))
+    return out
+
+
+def main():
+    barrier = []
+    for i in range(3):
+        barrier.append(run_barrier(LPSolver, "lp_testsolver", dict(seed=1, n=100, m=80, k=20, count=3), i,
+                                   problems.LP_TEST_SETTINGS, f"lp_seed1_n100_{i}"))
+    for i in range(2):
+        barrier.append(run_barrier(QPSolver, "qp_testsolver", dict(seed=1, n=100, m=80, k=20, count=2), i,
+                                   problems.QP_TEST_SETTINGS, f"qp_seed1_n100_{i}"))
+    barrier.append(run_barrier(LPSolver, "lp_dense_family", dict(seed=0, n=64), None, {}, "lp_dense_n64_cold"))
+    barrier.append(run_barrier(LPSolver, "lp_dense_family", dict(seed=0, n=64, warm=True), None, {},
+                               "lp_dense_n64_warm"))
+    barrier.append(run_barrier(LPSolver, "lp_dense_family", dict(seed=0, n=256), None, {}, "lp_dense_n256_cold"))
+    barrier.append(run_barrier(LPSolver, "lp_dense_family", dict(seed=0, n=256, warm=True), None, {},
+                               "lp_dense_n256_warm"))
+    barrier.append(run_barrier(LPSolver, "lp_dense_family", dict(seed=7, n=97, m=150), None, {},
+                               "lp_dense_n97_ragged"))
+    barrier.append(run_barrier(QPSolver, "qp_dense_family", dict(seed=0, n=128, p=32, k=16), None, {},
+                               "qp_dense_n128"))
+    barrier.append(run_barrier(QPSolver, "qp_dense_family", dict(seed=0, n=512, p=128, k=64), None, {},
+                               "qp_dense_n512"))
+    barrier.append(run_barrier(LPSolver, "lp_bounds_only", dict(seed=3, n=50), None, {}, "lp_bounds_only_n50"))
+    barrier.append(run_barrier(LPSolver, "lp_bounds_only", dict(seed=3, n=50, p=10), None, {},
+                               "lp_bounds_eq_n50"))
+    barrier.append(run_barrier(SOCPSolver, "socp_family", dict(seed=4, n=48, M=6, k=8), None,
+                               problems.SOCP_TEST_SETTINGS, "socp_n48_warm"))
+    barrier.append(run_barrier(SOCPSolver, "socp_family", dict(seed=4, n=48, M=6, k=8, p=6), None,
+                               problems.SOCP_TEST_SETTINGS, "socp_n48_eq_warm"))
+    barrier.append(run_barrier(SOCPSolver, "socp_family", dict(seed=4, n=48, M=6, k=8, warm=False), None,
+                               problems.SOCP_TEST_SETTINGS, "socp_n48_cold"))
+    barrier.append(run_barrier(SOCPSolver, "socp_family", dict(seed=11, n=96, M=12, k=16), None,
+                               problems.SOCP_TEST_SETTINGS, "socp_n96_warm"))
+    with open(os.path.join(HERE, "barrier_cases.json"), "w") as f:
+        json.dump(barrier, f, indent=1)
+    with open(os.path.join(HERE, "socp_group_lasso.json"), "w") as f:
+        json.dump(group_lasso_socp(), f, indent=1)
+    lasso = [
+        lasso_case("lasso_seed1_n100", dict(seed=1, n=100, m=80, num_problems=30), problems.LASSO_TEST_SETTINGS),
+        lasso_case("lasso_seed1_n100_chunks3", dict(seed=1, n=100, m=80, num_problems=30),
+                   dict(problems.LASSO_TEST_SETTINGS, num_chunks=3)),
+        lasso_case("lasso_seed2_n64_defaults", dict(seed=2, n=64, m=40, num_problems=17),
+                   dict(rho=0.4, max_iters=1000, check_stop=10, add_bias=True)),
+        lasso_case("lasso_seed3_positive", dict(seed=3, n=32, m=30, num_problems=5),
+                   dict(rho=0.4, max_iters=400, check_stop=10, add_bias=True, positive=True, normalize_A=True)),
+    ]
+    with open(os.path.join(HERE, "lasso_cases.json"), "w") as f:
+        json.dump(lasso, f, indent=1)
+    with open(os.path.join(HERE, "phase_one_standalone.json"), "w") as f:
+        json.dump(standalone_phase_one(), f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
