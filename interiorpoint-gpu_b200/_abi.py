@@ -1,0 +1,95 @@
+"""ctypes binding of ``libipm_b200.so`` (the C-ABI declared in ``include/ipm_b200.h``).
+
+The product path has NO CPU fallback: if the library is missing or no sm_100 device is visible,
+``lib()`` / ``require_device()`` raise.  Arguments are raw device pointers (``tensor.data_ptr()``) and
+sizes; every call is asynchronous on the given CUDA stream and returns a status code that is mapped to a
+Python exception here.
+"""
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libipm_b200.so")
+
+_dp = C.c_void_p  # device pointer
+_i = C.c_int
+_d = C.c_double
+_ll = C.c_longlong
+
+# name -> (restype, argtypes).  Keep in sync with include/ipm_b200.h (tests/test_abi.py checks the header).
+SIGNATURES = {
+    "ipm_abi_version": (_i, []),
+    "ipm_device_ok": (_i, []),
+    "ipm_last_cuda_error": (C.c_char_p, []),
+    "ipm_gemm_tn_f64": (_i, [_dp, _i, _dp, _i, _dp, _d, _d, _dp, _i, _i, _i, _i, _i, _dp]),
+    "ipm_gemv_n_f64": (_i, [_dp, _i, _i, _i, _dp, _dp, _d, _d, _dp]),
+    "ipm_gemv_t_ws_doubles": (_ll, [_i, _i, _i]),
+    "ipm_gemv_t_f64": (_i, [_dp, _i, _i, _i, _dp, _i, _i, _dp, _i, _d, _d, _dp, _ll, _dp]),
+    "ipm_dots_f64": (_i, [_i, C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_i), _dp, _dp]),
+    "ipm_axpy_dev_f64": (_i, [_i, _dp, _dp, _dp, _dp]),
+    "ipm_potrf_upper_f64": (_i, [_dp, _i, _i, _dp, _dp]),
+    "ipm_trsm_upper_t_f64": (_i, [_dp, _i, _i, _dp, _i, _i, _dp]),
+    "ipm_trsv_upper_f64": (_i, [_dp, _i, _i, _dp, _i, _dp]),
+    "ipm_lin_barrier_ws_doubles": (_ll, []),
+    "ipm_lin_barrier_eval_f64": (_i, [_i, _i, _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "ipm_lin_grad_f64": (_i, [_i, _d, _dp, _dp, _dp, _dp, _i, _dp, _dp, _dp, _dp, _dp]),
+    "ipm_hess_finish_f64": (_i, [_dp, _i, _i, _dp, _dp, _dp, _d, _dp]),
+    "ipm_scale_copy_upper_f64": (_i, [_dp, _i, _dp, _i, _i, _d, _dp]),
+    "ipm_ls_feas_lin_f64": (_i, [_i, _i, _dp, _dp, _dp, _i, _i, _i, _dp, _i, _dp, _dp, _dp]),
+    "ipm_ls_feas_poly_f64": (_i, [_i, _dp, _dp, _dp, _dp, _i, _dp, _i, _dp]),
+    "ipm_ls_armijo_f64": (_i, [_i, _dp, _dp, _dp, _dp, _i, _dp, _dp, _d, _d, _i, _dp, _dp]),
+    "ipm_ls_residual_f64": (_i, [_i, _i, _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp, _d, _dp, _dp]),
+    "ipm_trial_point_f64": (_i, [_i, _dp, _dp, _dp, _dp, _dp]),
+    "ipm_lincomb3_f64": (_i, [_i, _d, _dp, _d, _dp, _d, _dp, _dp, _dp]),
+}
+
+IPM_OK, IPM_ERR_ARG, IPM_ERR_CUDA, IPM_ERR_NO_DEVICE = 0, -1, -2, -3
+
+_lib = None
+
+
+class IpmError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise IpmError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the B200 engine has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def require_device():
+    rc = lib().ipm_device_ok()
+    if rc != IPM_OK:
+        raise IpmError("no sm_100 (B200) CUDA device visible: the ipm_b200 engine has no CPU fallback")
+
+
+def check(rc, what=""):
+    if rc == IPM_OK:
+        return
+    if rc == IPM_ERR_ARG:
+        raise IpmError(f"{what}: invalid argument")
+    if rc == IPM_ERR_CUDA:
+        raise IpmError(f"{what}: CUDA error: {lib().ipm_last_cuda_error().decode()}")
+    if rc == IPM_ERR_NO_DEVICE:
+        raise IpmError(f"{what}: no sm_100 device / driver entry point")
+    raise IpmError(f"{what}: status {rc}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args), name)

@@ -1,0 +1,71 @@
+// Shared device/host helpers for libipm_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define IPM_OK 0
+#define IPM_ERR_ARG (-1)       // bad argument (size / alignment / null pointer)
+#define IPM_ERR_CUDA (-2)      // a CUDA runtime call failed (see ipm_last_cuda_error)
+#define IPM_ERR_NO_DEVICE (-3) // no sm_100 device / driver entry point missing
+
+extern "C" int ipm_set_cuda_error(cudaError_t e);
+
+#define IPM_CUDA_CHECK(expr)                                   \
+  do {                                                         \
+    cudaError_t _e = (expr);                                   \
+    if (_e != cudaSuccess) return ipm_set_cuda_error(_e);      \
+  } while (0)
+
+#define IPM_LAUNCH_CHECK() IPM_CUDA_CHECK(cudaGetLastError())
+
+namespace ipm {
+
+constexpr int kWarp = 32;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_max_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum in a fixed (deterministic) order; result valid in thread 0. `red` holds >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect `red` from a previous use
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (w == 0) {
+    r = lane < nw ? red[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;
+}
+__device__ __forceinline__ double block_min(double v, double* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_min(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double r = INFINITY;
+  if (w == 0) {
+    r = lane < nw ? red[lane] : INFINITY;
+    r = warp_min(r);
+  }
+  return r;
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace ipm

@@ -1,0 +1,172 @@
+"""Kernel-level parity (GPU): every C-ABI op against float64 NumPy/torch on the same inputs.
+
+Tolerances are FP64 reorder-level: the DMMA contraction sums in a different order than BLAS, so results
+agree to ~1e-13 relative to sum |a||b| (SURVEY 7.4-1 shows the solver needs <= 1e-13)."""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from ipm_b200 import _abi  # noqa: E402
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64).cuda()
+
+
+def padded(a, mult=16):
+    """Row-major device copy with the leading dimension rounded up to `mult` doubles."""
+    r, c = a.shape
+    ld = (c + mult - 1) // mult * mult
+    out = torch.zeros((r, ld), dtype=torch.float64, device="cuda")
+    out[:, :c] = torch.as_tensor(a)
+    return out, ld
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device():
+    _abi.require_device()
+
+
+@pytest.mark.parametrize("M,N,K,use_w,upper", [
+    (128, 128, 64, False, 0), (256, 384, 200, True, 0), (100, 100, 37, True, 1), (513, 300, 513, False, 0),
+    (1000, 1000, 777, True, 1), (8, 8, 4, True, 1), (130, 70, 1, False, 0), (257, 257, 1030, True, 1),
+])
+def test_gemm_tn(M, N, K, use_w, upper):
+    rs = np.random.RandomState(M * 7 + N * 3 + K)
+    A = rs.uniform(-2, 2, (K, M))
+    B = A if upper else rs.uniform(-2, 2, (K, N))
+    w = 10.0 ** rs.uniform(-6, 6, K) if use_w else None
+    D0 = rs.uniform(-1, 1, (M, N))
+    alpha, beta = -1.25, 0.5
+    Ad, lda = padded(A)
+    Bd, ldb = (Ad, lda) if upper else padded(B)
+    Dd, ldd = padded(D0)
+    wd = dev(w) if use_w else None
+    _abi.call("ipm_gemm_tn_f64", Ad.data_ptr(), lda, Bd.data_ptr(), ldb, _abi.ptr(wd), alpha, beta, Dd.data_ptr(), ldd,
+              M, N, K, upper, None)
+    torch.cuda.synchronize()
+    got = Dd[:, :N].cpu().numpy()
+    Aw = A * (w[:, None] if use_w else 1.0)
+    ref = beta * D0 + alpha * (Aw.T @ B)
+    scale = np.abs(Aw).T @ np.abs(B) + np.abs(D0)
+    if upper:
+        iu = np.triu_indices(M)
+        assert np.max(np.abs(got[iu] - ref[iu]) / scale[iu]) < 1e-14
+        il = np.tril_indices(M, -1)
+        np.testing.assert_array_equal(got[il], D0[il])  # strict lower triangle untouched
+    else:
+        assert np.max(np.abs(got - ref) / scale) < 1e-14
+    assert torch.count_nonzero(Dd[:, N:]) == 0  # padding untouched
+
+
+def test_gemm_tn_beta_zero_ignores_nan_output():
+    rs = np.random.RandomState(0)
+    A = rs.randn(50, 40)
+    Ad, lda = padded(A)
+    Dd = torch.full((40, 48), float("nan"), dtype=torch.float64, device="cuda")
+    _abi.call("ipm_gemm_tn_f64", Ad.data_ptr(), lda, Ad.data_ptr(), lda, None, 1.0, 0.0, Dd.data_ptr(), 48, 40, 40, 50,
+              0, None)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(Dd[:, :40].cpu().numpy(), A.T @ A, rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (7, 33), (300, 1000), (1000, 257), (2049, 4096)])
+def test_gemv_n_and_t(rows, cols):
+    rs = np.random.RandomState(rows + cols)
+    Mx = rs.uniform(-2, 2, (rows, cols))
+    x = rs.randn(cols)
+    y0 = rs.randn(rows)
+    Md, ld = padded(Mx)
+    yd = dev(y0)
+    _abi.call("ipm_gemv_n_f64", Md.data_ptr(), ld, rows, cols, dev(x).data_ptr(), yd.data_ptr(), 2.0, -1.0, None)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(yd.cpu().numpy(), 2.0 * (Mx @ x) - y0, rtol=1e-12, atol=1e-12)
+    # transposed, two right-hand sides
+    V = rs.randn(2, rows)
+    Vd = dev(V)
+    Yd = torch.zeros((2, cols), dtype=torch.float64, device="cuda")
+    nws = _abi.lib().ipm_gemv_t_ws_doubles(rows, cols, 2)
+    ws = torch.empty(nws, dtype=torch.float64, device="cuda")
+    _abi.call("ipm_gemv_t_f64", Md.data_ptr(), ld, rows, cols, Vd.data_ptr(), 2, rows, Yd.data_ptr(), cols, 1.0, 0.0,
+              ws.data_ptr(), nws, None)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(Yd.cpu().numpy(), V @ Mx, rtol=1e-12, atol=1e-11)
+
+
+def spd(n, seed, cond_pow=6):
+    rs = np.random.RandomState(seed)
+    C_ = rs.uniform(-2, 2, (2 * n, n))
+    w = 10.0 ** rs.uniform(-cond_pow, cond_pow, 2 * n)
+    return (C_ * w[:, None]).T @ C_ + np.eye(n) * 1e-3
+
+
+@pytest.mark.parametrize("n", [1, 5, 64, 128, 129, 300, 513, 1025])
+def test_potrf_trsv(n):
+    H = spd(n, n)
+    Hd, ld = padded(H)
+    Hd_low_before = torch.tril(Hd[:, :n], -1).clone()
+    info = torch.full((1,), -7, dtype=torch.int32, device="cuda")
+    _abi.call("ipm_potrf_upper_f64", Hd.data_ptr(), ld, n, info.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert int(info.item()) == 0
+    U = torch.triu(Hd[:, :n]).cpu().numpy()
+    assert np.max(np.abs(U.T @ U - H)) / np.max(np.abs(H)) < 1e-13
+    assert torch.equal(torch.tril(Hd[:, :n], -1), Hd_low_before)  # strict lower triangle untouched
+    # solves
+    rs = np.random.RandomState(n)
+    b = rs.randn(n)
+    bd = dev(b)
+    _abi.call("ipm_trsv_upper_f64", Hd.data_ptr(), ld, n, bd.data_ptr(), 1, None)
+    _abi.call("ipm_trsv_upper_f64", Hd.data_ptr(), ld, n, bd.data_ptr(), 0, None)
+    torch.cuda.synchronize()
+    x = bd.cpu().numpy()
+    # backward-stable solve: residual small relative to |H||x| + |b|
+    res = np.abs(H @ x - b) / (np.abs(H) @ np.abs(x) + np.abs(b))
+    assert res.max() < 1e-12
+
+
+def test_potrf_reports_first_bad_pivot():
+    n = 200
+    H = spd(n, 3, cond_pow=1)
+    H[150, 150] = -1.0
+    Hd, ld = padded(H)
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _abi.call("ipm_potrf_upper_f64", Hd.data_ptr(), ld, n, info.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert int(info.item()) == 151  # LAPACK convention: 1-based order of the failing leading minor
+
+
+@pytest.mark.parametrize("n,p", [(64, 10), (300, 129), (513, 64)])
+def test_trsm_upper_t(n, p):
+    H = spd(n, n + 1, cond_pow=2)
+    U = np.linalg.cholesky(H).T
+    rs = np.random.RandomState(p)
+    B = rs.randn(n, p)
+    Ud, ldu = padded(np.triu(U))
+    Bd, ldb = padded(B)
+    _abi.call("ipm_trsm_upper_t_f64", Ud.data_ptr(), ldu, n, Bd.data_ptr(), ldb, p, None)
+    torch.cuda.synchronize()
+    Y = Bd[:, :p].cpu().numpy()
+    res = np.abs(U.T @ Y - B) / (np.abs(U.T) @ np.abs(Y) + np.abs(B))
+    assert res.max() < 1e-12
+
+
+def test_dots_and_axpy():
+    rs = np.random.RandomState(5)
+    a, b, c = rs.randn(1000), rs.randn(1000), rs.randn(77)
+    ad, bd, cd = dev(a), dev(b), dev(c)
+    out = torch.zeros(3, dtype=torch.float64, device="cuda")
+    pa = (C.c_void_p * 3)(ad.data_ptr(), ad.data_ptr(), cd.data_ptr())
+    pb = (C.c_void_p * 3)(bd.data_ptr(), ad.data_ptr(), cd.data_ptr())
+    nn = (C.c_int * 3)(1000, 1000, 77)
+    _abi.call("ipm_dots_f64", 3, pa, pb, nn, out.data_ptr(), None)
+    step = dev(np.array([0.36]))
+    _abi.call("ipm_axpy_dev_f64", 1000, step.data_ptr(), bd.data_ptr(), ad.data_ptr(), None)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(out.cpu().numpy(), [a @ b, a @ a, c @ c], rtol=1e-13)
+    np.testing.assert_array_equal(ad.cpu().numpy(), a + 0.36 * b)  # bit-exact NumPy rounding
