@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 interior-point engine (contract: see DESIGN.md, "Measurement").
+
+Workload (BASELINE.json configs[1]): dense random LP, n = 8192 variables, m = 16384 inequality rows plus box
+bounds, FP64, constructor defaults of the reference's ``LPSolver``; warm start (x0 strictly feasible, so the
+timed region is the main barrier phase).  One bench "step" = one complete ``LPSolver.solve()``.
+
+  metric `newton_steps_per_s` = Newton iterations performed / device time, summed over all ranks.
+  value : problem data already resident in HBM (solver constructed before the timed region; what the reference
+          times, testSolver.py:151-153).
+  e2e   : through the public API from HOST NumPy buffers: constructor (H2D of C, d, c, bounds) + solve() + the
+          device->host read of the solution, all inside the timed region.
+  roofline : the Hessian kernel  H = C' diag(w) C  (ipm_gemm_tn_f64, FP64 DMMA): algorithmic m*n*(n+1) flop per
+          launch / mean launch time from CUDA events recorded around every such launch inside the timed region.
+  cpu_baseline : the CPU oracle (NumPy/SciPy restatement of the reference, oracle/) on this box's host cores on
+          a bounded sample (a fixed number of full-size Newton steps).
+
+N > 1 (torchrun): every rank solves an independent instance of the same LP family (seed + rank) with no
+data-path collective ("weak" scaling; BASELINE north_star: batches of independent LP instances split across
+GPUs with no communication).
+
+`--impl reference` times the reference algorithm on the host CPU (oracle port; the reference itself is pure
+Python/NumPy and does not travel to the GPU box) for the same metric.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+FP64_TENSOR_PEAK_TFLOPS = 37.1  # measured DMMA.8x8x4 issue rate on this pool's B200 (profiles/fp64_peak_r01.json)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=8192)
+    ap.add_argument("--m", type=int, default=None)
+    ap.add_argument("--cpu-newton-steps", type=int, default=2, help="full-size Newton steps in the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def workload(args, rank):
+    import problems
+
+    m = 2 * args.n if args.m is None else args.m
+    prob = problems.lp_dense_family(seed=8192 + rank, n=args.n, m=m, warm=True)
+    return prob, m
+
+
+def cpu_sample(prob, newton_steps):
+    """Bounded CPU sample: `newton_steps` full-size Newton iterations of the oracle (first centering step)."""
+    from oracle import OracleLP
+
+    p = dict(prob)
+    p["x0"] = prob["x0"].copy()
+    o = OracleLP(**p, max_outer_iters=1, max_inner_iters=newton_steps)
+    t0 = time.perf_counter()
+    o.solve()
+    dt = time.perf_counter() - t0
+    return sum(o.inner_iters), dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    prob, m = workload(args, 0)
+    times, steps = [], 0
+    for i in range(args.warmup + args.steps):
+        k, dt = cpu_sample(prob, 1)
+        if i >= args.warmup:
+            times.append(dt)
+            steps += k
+    total = sum(times)
+    val = steps / total
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": "newton_steps_per_s", "value": val, "unit": "Newton steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"dense LP n={args.n} m={m} box+-3, warm start (BASELINE configs[1])",
+                   "sample": "one full-size Newton iteration per step"},
+        "cpu_baseline": {"value": val, "unit": "Newton steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} full-size Newton iterations of the oracle (NumPy/SciPy, BLAS threads = "
+                                   f"{cores})"},
+        "e2e": {"value": val, "unit": "Newton steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from ipm_b200.LPSolver import LPSolver
+
+    prob, m = workload(args, rank)
+    n = args.n
+    host = {k: (torch.as_tensor(v).pin_memory().numpy() if isinstance(v, np.ndarray) else v) for k, v in prob.items()}
+    x0 = prob["x0"].copy()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ resident-data arm
+    solver = LPSolver(**{k: v for k, v in host.items() if k != "x0"}, x0=x0.copy(), check_cvxpy=False,
+                      suppress_print=True)
+    x0_dev = solver.x_dev.clone()
+
+    def one_solve():
+        solver.x_dev.copy_(x0_dev)
+        solver.solve()
+        return sum(solver.inner_iters)
+
+    for _ in range(args.warmup):
+        one_solve()
+    L = solver.launcher
+    L.timed_ops = {"ipm_gemm_tn_f64": []}
+    launches0 = L.kernel_launches()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    newton = 0
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            newton += one_solve()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = L.kernel_launches() - launches0
+    hess = [a.elapsed_time(b) for a, b, tag in L.timed_ops["ipm_gemm_tn_f64"] if tag == "hessian"]
+    L.timed_ops = None
+    value_ref = solver.value
+
+    # ------------------------------------------------------------------ end-to-end arm (host buffers)
+    e2e_ms, e2e_newton, h2d, d2h = None, 0, 0, 0
+    if not args.no_e2e:
+        del solver
+        torch.cuda.empty_cache()
+
+        def e2e_step():
+            s = LPSolver(**{k: v for k, v in host.items() if k != "x0"}, x0=x0.copy(), check_cvxpy=False,
+                         suppress_print=True)
+            s.solve()
+            xs = s.xstar  # device -> host read of the result
+            return sum(s.inner_iters), s.data.h2d_bytes + 8 * n, xs.nbytes + 8
+
+        e2e_step()  # warm-up (allocator)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            k, h2d, d2h = e2e_step()
+            e2e_newton += k
+        f1.record()
+        barrier()
+        e2e_ms = f0.elapsed_time(f1)
+
+    # ------------------------------------------------------------------ reduce over ranks (max time, sum work)
+    stats = torch.tensor([ms, float(newton), e2e_ms or 0.0, float(e2e_newton), float(launches)], dtype=torch.float64,
+                         device="cuda")
+    if world > 1:
+        tmax = stats.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = stats.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, e2e_ms = float(tmax[0]), float(tmax[2])
+        newton, e2e_newton, launches = float(tsum[1]), float(tsum[3]), float(tsum[4])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = newton / (ms * 1e-3)
+    hess_ms = float(np.mean(hess)) if hess else None
+    flops = float(m) * n * (n + 1)
+    achieved = flops / (hess_ms * 1e-3) / 1e12 if hess_ms else None
+    line = {
+        "metric": "newton_steps_per_s", "value": value, "unit": "Newton steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"dense LP n={n} m={m} box+-3, warm start (BASELINE configs[1]); one step = one "
+                               "LPSolver.solve()", "l2": "inputs (C = %.2f GB) larger than L2" % (8e-9 * m * n),
+                   "per_rank": "independent LP instance per GPU, no collective" if world > 1 else "single GPU"},
+        "time_to_solve_s": ms * 1e-3 / args.steps, "newton_steps_per_solve": newton / args.steps / world,
+        "objective": value_ref, "gpu_launches": int(launches), "clocks": clk.summary(),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
+                     "frac": achieved / FP64_TENSOR_PEAK_TFLOPS if achieved else None, "traffic": None,
+                     "kernel": "gemm_tn_kernel<true> (Hessian C'diag(w)C, upper tiles)",
+                     "flop_per_launch": flops, "ms_per_launch": hess_ms, "launches_timed": len(hess),
+                     "peak_source": "FP64 DMMA issue-rate microbenchmark on this pool (tools/fp64_peak.cu, "
+                                    "profiles/fp64_peak_r01.json); MEASURED_PEAKS.json has no FP64 entry"},
+    }
+    if e2e_ms:
+        line["e2e"] = {"value": e2e_newton / (e2e_ms * 1e-3), "unit": "Newton steps/s", "h2d_bytes_per_step": int(h2d),
+                       "d2h_bytes_per_step": int(d2h), "time_to_solve_s": e2e_ms * 1e-3 / args.steps}
+    if not args.no_cpu_baseline and world == 1:
+        k, dt = cpu_sample(prob, args.cpu_newton_steps)
+        line["cpu_baseline"] = {"value": k / dt, "unit": "Newton steps/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"{k} full-size Newton iterations (first centering step) of the oracle, "
+                                          f"{dt:.1f} s"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -22,6 +22,7 @@ SIGNATURES = {
     "ipm_abi_version": (_i, []),
     "ipm_device_ok": (_i, []),
     "ipm_last_cuda_error": (C.c_char_p, []),
+    "ipm_launch_count": (C.c_ulonglong, []),
     "ipm_gemm_tn_f64": (_i, [_dp, _i, _dp, _i, _dp, _d, _d, _dp, _i, _i, _i, _i, _i, _dp]),
     "ipm_gemv_n_f64": (_i, [_dp, _i, _i, _i, _dp, _dp, _d, _d, _dp]),
     "ipm_gemv_t_ws_doubles": (_ll, [_i, _i, _i]),
@@ -32,16 +33,19 @@ SIGNATURES = {
     "ipm_trsm_upper_t_f64": (_i, [_dp, _i, _i, _dp, _i, _i, _dp]),
     "ipm_trsv_upper_f64": (_i, [_dp, _i, _i, _dp, _i, _dp]),
     "ipm_lin_barrier_ws_doubles": (_ll, []),
-    "ipm_lin_barrier_eval_f64": (_i, [_i, _i, _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "ipm_lin_barrier_eval_f64": (_i, [_i, _i, _dp, _dp, _dp, _dp, _dp, _dp, _i, _i, _dp, _dp, _dp, _dp, _dp, _dp,
+                                      _dp]),
     "ipm_lin_grad_f64": (_i, [_i, _d, _dp, _dp, _dp, _dp, _i, _dp, _dp, _dp, _dp, _dp]),
     "ipm_hess_finish_f64": (_i, [_dp, _i, _i, _dp, _dp, _dp, _d, _dp]),
     "ipm_scale_copy_upper_f64": (_i, [_dp, _i, _dp, _i, _i, _d, _dp]),
     "ipm_ls_feas_lin_f64": (_i, [_i, _i, _dp, _dp, _dp, _i, _i, _i, _dp, _i, _dp, _dp, _dp]),
     "ipm_ls_feas_poly_f64": (_i, [_i, _dp, _dp, _dp, _dp, _i, _dp, _i, _dp]),
-    "ipm_ls_armijo_f64": (_i, [_i, _dp, _dp, _dp, _dp, _i, _dp, _dp, _d, _d, _i, _dp, _dp]),
+    "ipm_ls_armijo_f64": (_i, [_i, _dp, _dp, _dp, _dp, _i, _dp, _dp, _dp, _d, _d, _i, _dp, _dp]),
     "ipm_ls_residual_f64": (_i, [_i, _i, _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp, _d, _dp, _dp]),
     "ipm_trial_point_f64": (_i, [_i, _dp, _dp, _dp, _dp, _dp]),
     "ipm_lincomb3_f64": (_i, [_i, _d, _dp, _d, _dp, _d, _dp, _dp, _dp]),
+    "ipm_table_lookup_f64": (_i, [_dp, _i, _dp, _dp, _dp]),
+    "ipm_vec_op_f64": (_i, [_i, _i, _dp, _dp, _dp, _d, _dp]),
 }
 
 IPM_OK, IPM_ERR_ARG, IPM_ERR_CUDA, IPM_ERR_NO_DEVICE = 0, -1, -2, -3

@@ -16,7 +16,13 @@ extern "C" int ipm_set_cuda_error(cudaError_t e);
     if (_e != cudaSuccess) return ipm_set_cuda_error(_e);      \
   } while (0)
 
-#define IPM_LAUNCH_CHECK() IPM_CUDA_CHECK(cudaGetLastError())
+extern "C" void ipm_count_launch(void);
+// one call per kernel launch: checks the launch and bumps the library's launch counter (ipm_launch_count)
+#define IPM_LAUNCH_CHECK()                 \
+  do {                                     \
+    ipm_count_launch();                    \
+    IPM_CUDA_CHECK(cudaGetLastError());    \
+  } while (0)
 
 namespace ipm {
 

@@ -101,15 +101,16 @@ extern "C" int ipm_ls_feas_poly_f64(int count, const double* s0, const double* p
 
 // ------------------------------------------------------------------------------------------------
 // Armijo search of the feasible-start Newton method (single CTA).
-//   scal_in : [0] sum log(s(x)+1e-15)   [1] obj(x)   [2] d obj . dx (linear part)   [3] dx' P dx (0 if none)
-//             [4] g . x
+//   sumlog  : sum log(s(x)+1e-15) at the current point
+//   terms   : [0] obj(x)   [1] d obj . dx (linear part)   [2] dx' P dx (0 if none)   [3] g . x
 //   out     : [0] step  [1] stuck (0/1)  [2] final table index  [3] frozen log-sum  [4] Armijo trials
 // obj(x + a dx) = obj + a*scal[2] + 0.5*a*a*scal[3]   (exact for linear / quadratic objectives)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
 ls_armijo_kernel(int nc, const double* __restrict__ s0, const double* __restrict__ p1,
                  const double* __restrict__ p2, const double* __restrict__ table, int len,
-                 const int* __restrict__ kmax_ptr, const double* __restrict__ scal_in, double t, double alpha,
+                 const int* __restrict__ kmax_ptr, const double* __restrict__ sumlog_ptr,
+                 const double* __restrict__ terms, double t, double alpha,
                  int update_slacks_every, double* __restrict__ out) {
   __shared__ double red[32];
   __shared__ double bcast;
@@ -132,7 +133,7 @@ ls_armijo_kernel(int nc, const double* __restrict__ s0, const double* __restrict
     __syncthreads();
     return r;
   };
-  const double sumlog0 = scal_in[0], obj0 = scal_in[1], dobj = scal_in[2], quad = scal_in[3], gx = scal_in[4];
+  const double sumlog0 = *sumlog_ptr, obj0 = terms[0], dobj = terms[1], quad = terms[2], gx = terms[3];
   const double fx = t * obj0 - sumlog0;
   double a = table[k], a_eval = a;
   double L = logsum(a_eval);
@@ -156,10 +157,11 @@ ls_armijo_kernel(int nc, const double* __restrict__ s0, const double* __restrict
 }
 
 extern "C" int ipm_ls_armijo_f64(int nc, const double* s0, const double* p1, const double* p2, const double* table,
-                                 int len, const int* kmax, const double* scal_in, double t, double alpha,
-                                 int update_slacks_every, double* out, void* stream) {
-  if (nc < 0 || !table || len < 2 || !kmax || !scal_in || !out || (nc > 0 && (!s0 || !p1))) return IPM_ERR_ARG;
-  ls_armijo_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nc, s0, p1, p2, table, len, kmax, scal_in, t, alpha,
+                                 int len, const int* kmax, const double* sumlog, const double* terms, double t,
+                                 double alpha, int update_slacks_every, double* out, void* stream) {
+  if (nc < 0 || !table || len < 2 || !kmax || !sumlog || !terms || !out || (nc > 0 && (!s0 || !p1)))
+    return IPM_ERR_ARG;
+  ls_armijo_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nc, s0, p1, p2, table, len, kmax, sumlog, terms, t, alpha,
                                                         update_slacks_every, out);
   IPM_LAUNCH_CHECK();
   return IPM_OK;
@@ -275,6 +277,42 @@ extern "C" int ipm_lincomb3_f64(int n, double ca, const double* a, double cb, co
   int blocks = ceil_div(n, 256);
   if (blocks > 1184) blocks = 1184;
   lincomb3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(n, ca, a, cb, b, cc, c, out);
+  IPM_LAUNCH_CHECK();
+  return IPM_OK;
+}
+
+// out[0] = table[min(*kmax, len - 1)]  (step chosen by the feasibility back-off, kept on the device)
+__global__ void table_lookup_kernel(const double* __restrict__ table, int len, const int* __restrict__ kmax,
+                                    double* __restrict__ out) {
+  int k = *kmax;
+  out[0] = table[k < len - 1 ? k : len - 1];
+}
+
+extern "C" int ipm_table_lookup_f64(const double* table, int len, const int* kmax, double* out, void* stream) {
+  if (!table || len < 2 || !kmax || !out) return IPM_ERR_ARG;
+  table_lookup_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(table, len, kmax, out);
+  IPM_LAUNCH_CHECK();
+  return IPM_OK;
+}
+
+// element-wise helpers: op 0: out = alpha*a*b   op 1: out = alpha*a/b   op 2: out = alpha/a
+__global__ void vec_op_kernel(int op, int n, const double* __restrict__ a, const double* __restrict__ b,
+                              double* __restrict__ out, double alpha) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double v;
+    if (op == 0) v = alpha * (a[i] * b[i]);
+    else if (op == 1) v = alpha * (a[i] / b[i]);
+    else v = alpha / a[i];
+    out[i] = v;
+  }
+}
+
+extern "C" int ipm_vec_op_f64(int op, int n, const double* a, const double* b, double* out, double alpha,
+                              void* stream) {
+  if (op < 0 || op > 2 || n <= 0 || !a || !out || (op < 2 && !b)) return IPM_ERR_ARG;
+  int blocks = ceil_div(n, 256);
+  if (blocks > 1184) blocks = 1184;
+  vec_op_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(op, n, a, b, out, alpha);
   IPM_LAUNCH_CHECK();
   return IPM_OK;
 }

@@ -17,3 +17,8 @@ extern "C" int ipm_device_ok(void) {
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   return major == 10 ? IPM_OK : IPM_ERR_NO_DEVICE;
 }
+
+// Number of kernels this library has launched in this process (bench.py reports the delta over the timed region).
+static unsigned long long g_launches = 0;
+extern "C" void ipm_count_launch(void) { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+extern "C" unsigned long long ipm_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }

@@ -1,0 +1,544 @@
+"""Device-resident Newton / barrier engine for the linear-inequality family (LP, QP and their phase-I).
+
+Host side of the hot path: Python + torch tensors for memory, every numerical op is a call into
+``libipm_b200.so`` (hand-written sm_100a CUDA, see ``csrc/``).  One Newton iteration is a fixed sequence of
+asynchronous launches on one stream; the host reads back a handful of scalars ONCE per iteration (step size,
+stuck flag, g.dx, potrf info) to take the reference's control-flow decisions (NewtonSolver.py:129-133).
+
+Mirrors, on the device, ``FunctionManagerLP/QP/Phase1`` (FunctionManager.py:197-831) and
+``NewtonSolverCholesky`` / ``NewtonSolverCholeskyInfeasibleStart`` (+ diagonal variants)
+(NewtonSolver.py:250-341,403-420; NewtonSolverInfeasibleStart.py:356-538,757-809).
+"""
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+try:
+    from . import _abi
+except ImportError:  # flat-module use (directory on sys.path, like the reference)
+    import _abi
+
+STUCK = 1e-13
+F64 = torch.float64
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def step_table(beta):
+    """The reference's step sequence 1, beta, beta*beta, ... (repeated multiplication, NewtonSolver.py:175,195)
+    up to and including the first entry below 1e-13."""
+    if not (0.0 < beta < 1.0):
+        raise ValueError("beta must lie in (0, 1)")
+    tab = [1.0]
+    a = 1
+    while True:
+        a *= beta
+        tab.append(float(a))
+        if a < STUCK:
+            break
+    return tab
+
+
+class Launcher:
+    """Counts launches of our own kernels (bench.py reports it) and owns the stream."""
+
+    def __init__(self, device):
+        self.device = device
+        self.calls = 0
+        self._base = _abi.lib().ipm_launch_count()
+        self.timed_ops = None  # {"op name": [(start_event, end_event, tag), ...]} when bench.py profiles live
+        self.tag = None
+
+    def kernel_launches(self):
+        """Kernels launched by libipm_b200 since this launcher was created (process-wide counter)."""
+        return int(_abi.lib().ipm_launch_count() - self._base)
+
+    def __call__(self, name, *args):
+        self.calls += 1
+        rec = self.timed_ops.get(name) if self.timed_ops is not None else None
+        if rec is None:
+            _abi.call(name, *args, None)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _abi.call(name, *args, None)
+        e1.record()
+        rec.append((e0, e1, self.tag))
+
+
+def to_dev_matrix(a, device):
+    """Host (or device) 2-D array -> device FP64 row-major with ld rounded up to 16 doubles (TMA needs a 16-byte
+    row stride; the padding columns are zero)."""
+    t = torch.as_tensor(a)
+    r, c = t.shape
+    ld = _round_up(max(c, 1), 16)
+    out = torch.zeros((r, ld), dtype=F64, device=device)
+    out[:, :c].copy_(t, non_blocking=True)
+    return out, ld
+
+
+def to_dev_vector(a, device, n=None):
+    if a is None:
+        return None
+    t = torch.as_tensor(np.asarray(a, dtype=np.float64))
+    if t.ndim == 0:
+        t = t.repeat(n)
+    return t.to(device=device, dtype=F64).contiguous()
+
+
+class LinearProblemData:
+    """Problem data resident in HBM.  C: m x n inequality rows, A: p x n equality rows (also kept transposed,
+    n x p, because every contraction kernel wants the contracted index as the row index), P: n x n."""
+
+    def __init__(self, n, device, c=None, P=None, q=None, C=None, d=None, lb=None, ub=None, A=None, b=None):
+        self.n, self.device = n, device
+        self.m = 0 if C is None else C.shape[0]
+        self.p = 0 if A is None else A.shape[0]
+        self.C, self.ldc = (None, 0) if C is None else to_dev_matrix(C, device)
+        self.d = to_dev_vector(d, device)
+        self.lb = to_dev_vector(lb, device, n)
+        self.ub = to_dev_vector(ub, device, n)
+        self.is_qp = P is not None
+        self.P, self.ldp = (None, 0) if P is None else to_dev_matrix(P, device)
+        self.q = to_dev_vector(q, device)
+        if not self.is_qp:
+            self.c = to_dev_vector(np.ones(n) if c is None else c, device)
+        self.A, self.lda = (None, 0) if A is None else to_dev_matrix(A, device)
+        self.At, self.ldat = (None, 0) if A is None else to_dev_matrix(torch.as_tensor(A).T, device)
+        self.b = to_dev_vector(b, device)
+        self.n_slacks = self.m + (n if ub is not None else 0) + (n if lb is not None else 0)
+        self.h2d_bytes = sum(t.numel() * 8 for t in (self.C, self.d, self.lb, self.ub, self.P, self.q, self.A,
+                                                     self.At, self.b) if t is not None)
+
+
+class NewtonWorkspace:
+    """All per-iteration buffers, allocated once (nz = n for the main phase, n + 1 for phase-I)."""
+
+    def __init__(self, data, nz):
+        dev, n, m, p = data.device, data.n, data.m, data.p
+        z = lambda *s: torch.zeros(*s, dtype=F64, device=dev)  # noqa: E731
+        self.nz = nz
+        self.ldh = _round_up(nz, 16)
+        self.H = z(nz, self.ldh)
+        self.g, self.dz, self.trial, self.gtrial = z(nz), z(nz), z(nz), z(nz)
+        ms = max(data.n_slacks, 1)
+        self.slacks, self.inv, self.p1 = z(ms), z(ms), z(ms)
+        self.slacks_t, self.inv_t = z(ms), z(ms)
+        self.w, self.Cx, self.Cdx = z(max(m, 1)), z(max(m, 1)), z(max(m, 1))
+        self.w_t = z(max(m, 1))
+        self.hdiag, self.hxs, self.lin, self.hq, self.Pdx = z(n), z(n), z(n), z(n), z(n)
+        self.hdiag_t = z(n)
+        self.CtV = z(2, n)
+        self.CtV_in = z(2, max(m, 1))
+        self.red = z(8)
+        self.red_t = z(8)
+        self.terms = z(8)  # [obj0, dobj, quad, g.z, g.dz, ...]
+        self.ls_out = z(8)
+        self.consts = torch.tensor([1.0, 0.0], dtype=F64, device=dev)
+        self.kmax = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.info = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.ev_ws = z(_abi.lib().ipm_lin_barrier_ws_doubles())
+        nws = max(_abi.lib().ipm_gemv_t_ws_doubles(max(m, 1), n, 2),
+                  _abi.lib().ipm_gemv_t_ws_doubles(max(p, 1), n, 2),
+                  _abi.lib().ipm_gemv_t_ws_doubles(n, max(p, 1), 2))
+        self.gt_ws, self.gt_ws_n = z(nws), nws
+        if p:
+            self.ldy = _round_up(p, 16)
+            self.Y = z(n, self.ldy)      # U^{-T} A^T
+            self.lds = _round_up(p, 16)
+            self.S = z(p, self.lds)      # Schur complement
+            self.v, self.dv, self.wv = z(p), z(p), z(p)
+            self.Axb, self.Adx, self.rhs_p = z(p), z(p), z(p)
+            self.ATv, self.ATdv, self.yv = z(n), z(n), z(n)
+            self.r0d, self.u0, self.u1 = z(n), z(n), z(n)
+            self.hinv = z(n)
+        # pinned host mirror for the once-per-iteration readback
+        self.host = torch.zeros(24, dtype=F64).pin_memory()
+        self.host_info = torch.zeros(2, dtype=torch.int32).pin_memory()
+
+
+class LinearNewton:
+    """Damped Newton centering for the LP / QP barrier (``phase1=False``) or its phase-I problem
+    (``phase1=True``; iterate z = (x, s)).  Equality constraints (``data.A``) select the infeasible-start
+    method with block elimination."""
+
+    def __init__(self, data, phase1=False, max_iters=50, epsilon=1e-5, alpha=0.2, beta=0.6, phase1_tol=0.1,
+                 use_psd_condition=False, update_slacks_every=0, diagonal=False, launcher=None):
+        self.d = data
+        self.phase1 = phase1
+        self.nz = data.n + (1 if phase1 else 0)
+        self.max_iters, self.eps, self.alpha, self.beta = max_iters, epsilon, alpha, beta
+        self.phase1_tol = phase1_tol
+        self.use_psd_condition = use_psd_condition
+        self.update_slacks_every = update_slacks_every
+        self.diagonal = diagonal
+        self.equality = (data.A is not None) and not phase1
+        if self.equality and update_slacks_every > 0:
+            raise NotImplementedError("update_slacks_every > 0 is not supported by the device-side residual search")
+        self.L = launcher or Launcher(data.device)
+        self.ws = NewtonWorkspace(data, self.nz)
+        tab = step_table(beta)
+        self.table = torch.tensor(tab, dtype=F64, device=data.device)
+        self.table_len = len(tab)
+        self.t = 1.0
+        self.use_backup = False  # sticky, like the reference (NewtonSolver.py:319)
+        self.shift = 0.0
+        self.newton_steps = 0
+        self.trace = None
+
+    # ---------------------------------------------------------------- barrier pieces
+    def set_t(self, t):
+        self.t = float(t)
+
+    def _eval(self, z, slacks, inv, w, hdiag, red):
+        d, ws, L = self.d, self.ws, self.L
+        n, m = d.n, d.m
+        if m:
+            L("ipm_gemv_n_f64", d.C.data_ptr(), d.ldc, m, n, z.data_ptr(), ws.Cx.data_ptr(), 1.0, 0.0)
+        s_ptr = z.data_ptr() + 8 * n if self.phase1 else None
+        L("ipm_lin_barrier_eval_f64", m, n, _abi.ptr(ws.Cx) if m else None, _abi.ptr(d.d), z.data_ptr(),
+          _abi.ptr(d.ub), _abi.ptr(d.lb), s_ptr, int(self.phase1), int(self.phase1 or self.diagonal), slacks.data_ptr(), inv.data_ptr(), w.data_ptr(),
+          hdiag.data_ptr(), red.data_ptr(), ws.ev_ws.data_ptr())
+
+    def _bound_inv_ptrs(self, inv):
+        d = self.d
+        off = d.m
+        ub_p = lb_p = None
+        if d.ub is not None:
+            ub_p = inv.data_ptr() + 8 * off
+            off += d.n
+        if d.lb is not None:
+            lb_p = inv.data_ptr() + 8 * off
+        return ub_p, lb_p
+
+    def _lin_term(self, z):
+        """lin = c (LP) or P x + q (QP): the objective gradient without t."""
+        d, ws, L = self.d, self.ws, self.L
+        if self.phase1:
+            return None
+        if not d.is_qp:
+            return d.c
+        if d.q is not None:
+            ws.lin.copy_(d.q)
+            beta = 1.0
+        else:
+            beta = 0.0
+        L("ipm_gemv_n_f64", d.P.data_ptr(), d.ldp, d.n, d.n, z.data_ptr(), ws.lin.data_ptr(), 1.0, beta)
+        return ws.lin
+
+    def _gradient(self, t, lin, inv, w, red, g, want_border):
+        """g from reciprocal slacks (FunctionManager.py:232-265, 509-545, 741-781)."""
+        d, ws, L = self.d, self.ws, self.L
+        n, m = d.n, d.m
+        nv = 2 if (self.phase1 and want_border) else 1
+        if m:
+            if nv == 2:  # V = [inv_ineq ; w] as two rows of one buffer
+                ws.CtV_in[0].copy_(inv[:m])
+                ws.CtV_in[1].copy_(w[:m])
+                vptr, ldv = ws.CtV_in.data_ptr(), m
+            else:
+                vptr, ldv = inv.data_ptr(), m
+            L("ipm_gemv_t_f64", d.C.data_ptr(), d.ldc, m, n, vptr, nv, ldv, ws.CtV.data_ptr(), n, 1.0, 0.0,
+              ws.gt_ws.data_ptr(), ws.gt_ws_n)
+        ub_p, lb_p = self._bound_inv_ptrs(inv)
+        L("ipm_lin_grad_f64", n, t, _abi.ptr(lin), ws.CtV.data_ptr() if m else None, ub_p, lb_p, int(self.phase1),
+          red.data_ptr() + 16, (ws.CtV.data_ptr() + 8 * n) if (m and nv == 2) else None, g.data_ptr(),
+          ws.hxs.data_ptr())
+
+    def _hessian(self, t):
+        """H (upper) = [t P +] C' diag(w) C + diag(hdiag) [+ phase-I border] (FunctionManager.py:267-326,
+        547-611, 783-827)."""
+        d, ws, L = self.d, self.ws, self.L
+        n, m = d.n, d.m
+        beta = 0.0
+        if d.is_qp and not self.phase1:
+            L("ipm_scale_copy_upper_f64", ws.H.data_ptr(), ws.ldh, d.P.data_ptr(), d.ldp, n, t)
+            beta = 1.0
+        elif m == 0:
+            L("ipm_scale_copy_upper_f64", ws.H.data_ptr(), ws.ldh, None, 0, n, 0.0)
+        if m:
+            L.tag = "hessian"
+            L("ipm_gemm_tn_f64", d.C.data_ptr(), d.ldc, d.C.data_ptr(), d.ldc, ws.w.data_ptr(), 1.0, beta,
+              ws.H.data_ptr(), ws.ldh, n, n, m, 1)
+            L.tag = None
+        shift = self.shift + (1e-9 if self.use_psd_condition else 0.0)
+        L("ipm_hess_finish_f64", ws.H.data_ptr(), ws.ldh, n, ws.hdiag.data_ptr(),
+          ws.hxs.data_ptr() if self.phase1 else None, (ws.red.data_ptr() + 24) if self.phase1 else None, shift)
+
+    def _chol_solve_vec(self, vec):
+        """vec <- H^{-1} vec using the factor in ws.H."""
+        ws, L = self.ws, self.L
+        L("ipm_trsv_upper_f64", ws.H.data_ptr(), ws.ldh, self.nz, vec.data_ptr(), 1)
+        L("ipm_trsv_upper_f64", ws.H.data_ptr(), ws.ldh, self.nz, vec.data_ptr(), 0)
+
+    def _dots(self, pairs, out_offset=0):
+        k = len(pairs)
+        pa = (C.c_void_p * k)(*[a.data_ptr() if hasattr(a, "data_ptr") else a for a, _, _ in pairs])
+        pb = (C.c_void_p * k)(*[b.data_ptr() if hasattr(b, "data_ptr") else b for _, b, _ in pairs])
+        nn = (C.c_int * k)(*[c for _, _, c in pairs])
+        self.L("ipm_dots_f64", k, pa, pb, nn, self.ws.terms.data_ptr() + 8 * out_offset)
+
+    # ---------------------------------------------------------------- scalar queries used by the outer loops
+    def _read_terms(self, k):
+        ws = self.ws
+        ws.host[:k].copy_(ws.terms[:k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return [float(v) for v in ws.host[:k]]
+
+    def dot(self, a, b):
+        self._dots([(a, b, a.numel())])
+        return self._read_terms(1)[0]
+
+    def min_slack(self, z):
+        """Smallest slack at z (used for the phase-I start s0 = 1 - min slack, FunctionManager.py:390-393)."""
+        ws = self.ws
+        self._eval(z, ws.slacks, ws.inv, ws.w, ws.hdiag, ws.red)
+        ws.host[:1].copy_(ws.red[1:2], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(ws.host[0])
+
+    def slacks_at(self, x):
+        ws = self.ws
+        self._eval(x, ws.slacks, ws.inv, ws.w, ws.hdiag, ws.red)
+        return ws.slacks[: self.d.n_slacks].clone()
+
+    def equality_residual(self, x):
+        """||A x - b||_2 (LPSolver.py:600-602)."""
+        d, ws = self.d, self.ws
+        ws.Axb.copy_(d.b)
+        self.L("ipm_gemv_n_f64", d.A.data_ptr(), d.lda, d.p, d.n, x.data_ptr(), ws.Axb.data_ptr(), 1.0, -1.0)
+        return float(np.sqrt(self.dot(ws.Axb, ws.Axb)))
+
+    def qp_objective(self, x):
+        """1/2 x'Px + q'x (FunctionManager.py:683-704)."""
+        d, ws = self.d, self.ws
+        self.L("ipm_gemv_n_f64", d.P.data_ptr(), d.ldp, d.n, d.n, x.data_ptr(), ws.Pdx.data_ptr(), 1.0, 0.0)
+        pairs = [(x, ws.Pdx, d.n)] + ([(d.q, x, d.n)] if d.q is not None else [])
+        self._dots(pairs)
+        vals = self._read_terms(len(pairs))
+        return 0.5 * vals[0] + (vals[1] if d.q is not None else 0.0)
+
+    # ---------------------------------------------------------------- feasible-start iteration
+    def _objective_pairs(self, z, lin):
+        """dot pairs producing [obj(x), d obj.dx, dx'P dx] -- the exact polynomial of obj along the ray."""
+        d, ws = self.d, self.ws
+        n = d.n
+        one, zero = ws.consts.data_ptr(), ws.consts.data_ptr() + 8
+        if self.phase1:  # obj = s (FunctionManager.py:472-482)
+            return [(z.data_ptr() + 8 * n, one, 1), (ws.dz.data_ptr() + 8 * n, one, 1), (zero, zero, 1)]
+        if not d.is_qp:
+            return [(d.c, z, n), (d.c, ws.dz, n), (zero, zero, 1)]
+        # obj = x.(0.5 P x + q);  hq = lin - 0.5 P x = 0.5 P x + q
+        self.L("ipm_gemv_n_f64", d.P.data_ptr(), d.ldp, n, n, ws.dz.data_ptr(), ws.Pdx.data_ptr(), 1.0, 0.0)
+        self.L("ipm_lincomb3_f64", n, 0.5, lin.data_ptr(), 0.5 if d.q is not None else 0.0, _abi.ptr(d.q), 0.0,
+               None, ws.hq.data_ptr())
+        return [(ws.hq, z, n), (lin, ws.dz, n), (ws.dz, ws.Pdx, n)]
+
+    def _feasibility(self, z):
+        d, ws, L = self.d, self.ws, self.L
+        n, m = d.n, d.m
+        if m:
+            L("ipm_gemv_n_f64", d.C.data_ptr(), d.ldc, m, n, ws.dz.data_ptr(), ws.Cdx.data_ptr(), 1.0, 0.0)
+        L("ipm_ls_feas_lin_f64", m, n, ws.slacks.data_ptr(), ws.Cdx.data_ptr() if m else None, ws.dz.data_ptr(),
+          int(d.ub is not None), int(d.lb is not None), int(self.phase1), self.table.data_ptr(), self.table_len,
+          ws.p1.data_ptr(), ws.kmax.data_ptr())
+
+    def _iterate_feasible(self, z):
+        d, ws, L = self.d, self.ws, self.L
+        t = self.t
+        self._eval(z, ws.slacks, ws.inv, ws.w, ws.hdiag, ws.red)
+        lin = self._lin_term(z)
+        self._gradient(t, lin, ws.inv, ws.w, ws.red, ws.g, want_border=True)
+        if self.diagonal:
+            # bounds-only LP: H is diagonal, dx = -g / h (NewtonSolver.py:415-420)
+            L("ipm_vec_op_f64", 1, d.n, ws.g.data_ptr(), ws.hdiag.data_ptr(), ws.dz.data_ptr(), -1.0)
+        else:
+            self._hessian(t)
+            L("ipm_potrf_upper_f64", ws.H.data_ptr(), ws.ldh, self.nz, ws.info.data_ptr())
+            L("ipm_lincomb3_f64", self.nz, -1.0, ws.g.data_ptr(), 0.0, None, 0.0, None, ws.dz.data_ptr())
+            self._chol_solve_vec(ws.dz)
+        self._feasibility(z)
+        pairs = self._objective_pairs(z, lin) + [(ws.g, z, self.nz), (ws.g, ws.dz, self.nz)]
+        self._dots(pairs)
+        L("ipm_ls_armijo_f64", d.n_slacks, ws.slacks.data_ptr(), ws.p1.data_ptr(), None, self.table.data_ptr(),
+          self.table_len, ws.kmax.data_ptr(), ws.red.data_ptr(), ws.terms.data_ptr(), t, self.alpha,
+          self.update_slacks_every, ws.ls_out.data_ptr())
+        L("ipm_axpy_dev_f64", self.nz, ws.ls_out.data_ptr(), ws.dz.data_ptr(), z.data_ptr())
+        # one readback per Newton iteration
+        ws.host[:5].copy_(ws.ls_out[:5], non_blocking=True)
+        ws.host[5:10].copy_(ws.terms[:5], non_blocking=True)
+        ws.host[10:11].copy_(z[self.nz - 1:self.nz], non_blocking=True)
+        ws.host_info.copy_(ws.info, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h = ws.host
+        return dict(step=float(h[0]), stuck=h[1] != 0, g_dz=float(h[9]), z_last=float(h[10]),
+                    info=int(ws.host_info[0]))
+
+    def solve(self, z):
+        """Centering at the current t.  ``z`` is updated in place on the device.  Returns
+        (iters, decrement_or_residual, success) like NewtonSolver.solve / NewtonSolverInfeasibleStart.solve."""
+        if self.equality:
+            return self._solve_infeasible(z)
+        nd = None
+        it = 0
+        for it in range(self.max_iters):
+            zsave = z.clone() if not self.diagonal else None
+            r = self._iterate_feasible(z)
+            if r["info"] != 0 and not self.diagonal:
+                r = self._retry_regularised(z, zsave)
+            self.newton_steps += 1
+            nd = -r["g_dz"] / 2
+            if self.trace is not None:
+                self.trace.append((r["step"], nd))
+            if self.phase1 and r["z_last"] < -self.phase1_tol:  # NewtonSolver.py:105-107
+                return it + 1, None, True
+            if r["step"] < STUCK:
+                return it + 1, nd, False
+            elif nd < self.eps:
+                return it + 1, nd, True
+        return it + 1, nd, False
+
+    def _retry_regularised(self, z, zsave):
+        """Cholesky hit a non-positive pivot.  The reference switches (sticky) to an SVD least-squares solve
+        (NewtonSolver.py:314-341); the device engine re-factorises H + shift*I with a growing shift instead
+        (documented deviation: this path is only reached on numerically singular Hessians)."""
+        self.use_backup = True
+        base = float(torch.diagonal(self.ws.H[:, : self.nz]).abs().mean()) if self.shift == 0.0 else self.shift
+        shift = max(self.shift, 1e-14 * max(base, 1e-300))
+        for _ in range(40):
+            self.shift = shift
+            z.copy_(zsave)
+            r = self._iterate_feasible(z)
+            if r["info"] == 0:
+                return r
+            shift *= 100.0
+        raise np.linalg.LinAlgError("Hessian is not positive definite even after regularisation")
+
+    # ---------------------------------------------------------------- infeasible-start (equality constrained)
+    def _direction_infeasible(self, z, lin):
+        """Block elimination (NewtonSolverInfeasibleStart.py:386-490):
+        H = U'U;  Y = U^{-T} A';  S = Y'Y;  y = H^{-1} g;  w = S^{-1}(Ax - b - A y);  dx = -H^{-1}(g + A'w)."""
+        d, ws, L = self.d, self.ws, self.L
+        n, p, t = d.n, d.p, self.t
+        # b2 = A x - b
+        ws.Axb.copy_(d.b)
+        L("ipm_gemv_n_f64", d.A.data_ptr(), d.lda, p, n, z.data_ptr(), ws.Axb.data_ptr(), 1.0, -1.0)
+        if self.diagonal:
+            # S = A diag(1/h) A'  (NewtonSolverInfeasibleStart.py:774-809)
+            L("ipm_vec_op_f64", 2, n, ws.hdiag.data_ptr(), None, ws.hinv.data_ptr(), 1.0)
+            L("ipm_gemm_tn_f64", d.At.data_ptr(), d.ldat, d.At.data_ptr(), d.ldat, ws.hinv.data_ptr(), 1.0, 0.0,
+              ws.S.data_ptr(), ws.lds, p, p, n, 1)
+            L("ipm_vec_op_f64", 0, n, ws.hinv.data_ptr(), ws.g.data_ptr(), ws.yv.data_ptr(), 1.0)
+        else:
+            self._hessian(t)
+            L("ipm_potrf_upper_f64", ws.H.data_ptr(), ws.ldh, n, ws.info.data_ptr())
+            ws.Y[:, :p].copy_(d.At[:, :p])
+            L("ipm_trsm_upper_t_f64", ws.H.data_ptr(), ws.ldh, n, ws.Y.data_ptr(), ws.ldy, p)
+            L("ipm_gemm_tn_f64", ws.Y.data_ptr(), ws.ldy, ws.Y.data_ptr(), ws.ldy, None, 1.0, 0.0, ws.S.data_ptr(),
+              ws.lds, p, p, n, 1)
+            ws.yv.copy_(ws.g)
+            self._chol_solve_vec(ws.yv)
+        if self.shift:
+            L("ipm_hess_finish_f64", ws.S.data_ptr(), ws.lds, p, None, None, None, self.shift)
+        L("ipm_potrf_upper_f64", ws.S.data_ptr(), ws.lds, p, ws.info.data_ptr() + 4)
+        # rhs = b2 - A y ; w = S^{-1} rhs
+        ws.rhs_p.copy_(ws.Axb)
+        L("ipm_gemv_n_f64", d.A.data_ptr(), d.lda, p, n, ws.yv.data_ptr(), ws.rhs_p.data_ptr(), -1.0, 1.0)
+        ws.wv.copy_(ws.rhs_p)
+        L("ipm_trsv_upper_f64", ws.S.data_ptr(), ws.lds, p, ws.wv.data_ptr(), 1)
+        L("ipm_trsv_upper_f64", ws.S.data_ptr(), ws.lds, p, ws.wv.data_ptr(), 0)
+        # dx = -H^{-1}(g + A'w)
+        ws.dz.copy_(ws.g)
+        L("ipm_gemv_t_f64", d.A.data_ptr(), d.lda, p, n, ws.wv.data_ptr(), 1, p, ws.dz.data_ptr(), n, 1.0, 1.0,
+          ws.gt_ws.data_ptr(), ws.gt_ws_n)
+        if self.diagonal:
+            L("ipm_vec_op_f64", 0, n, ws.hinv.data_ptr(), ws.dz.data_ptr(), ws.dz.data_ptr(), -1.0)
+        else:
+            self._chol_solve_vec(ws.dz)
+            L("ipm_lincomb3_f64", n, -1.0, ws.dz.data_ptr(), 0.0, None, 0.0, None, ws.dz.data_ptr())
+        # dv = w - v
+        L("ipm_lincomb3_f64", p, 1.0, ws.wv.data_ptr(), -1.0, ws.v.data_ptr(), 0.0, None, ws.dv.data_ptr())
+
+    def _iterate_infeasible(self, z):
+        d, ws, L = self.d, self.ws, self.L
+        n, p, t = d.n, d.p, self.t
+        self._eval(z, ws.slacks, ws.inv, ws.w, ws.hdiag, ws.red)
+        lin = self._lin_term(z)
+        self._gradient(t, lin, ws.inv, ws.w, ws.red, ws.g, want_border=False)
+        self._direction_infeasible(z, lin)
+        # feasibility back-off, then the barrier part of the gradient at the first feasible trial (frozen, Q4)
+        self._feasibility(z)
+        L("ipm_table_lookup_f64", self.table.data_ptr(), self.table_len, ws.kmax.data_ptr(),
+          ws.ls_out.data_ptr() + 48)  # a_k -> ls_out[6]
+        L("ipm_trial_point_f64", n, ws.ls_out.data_ptr() + 48, z.data_ptr(), ws.dz.data_ptr(), ws.trial.data_ptr())
+        self._eval(ws.trial, ws.slacks_t, ws.inv_t, ws.w_t, ws.hdiag_t, ws.red_t)
+        self._gradient(0.0, None, ws.inv_t, ws.w_t, ws.red_t, ws.gtrial, want_border=False)  # barrier part only
+        # cached products (NewtonSolverInfeasibleStart.py:196-205)
+        L("ipm_gemv_t_f64", d.A.data_ptr(), d.lda, p, n, ws.v.data_ptr(), 1, p, ws.ATv.data_ptr(), n, 1.0, 0.0,
+          ws.gt_ws.data_ptr(), ws.gt_ws_n)
+        L("ipm_gemv_t_f64", d.A.data_ptr(), d.lda, p, n, ws.dv.data_ptr(), 1, p, ws.ATdv.data_ptr(), n, 1.0, 0.0,
+          ws.gt_ws.data_ptr(), ws.gt_ws_n)
+        L("ipm_gemv_n_f64", d.A.data_ptr(), d.lda, p, n, ws.dz.data_ptr(), ws.Adx.data_ptr(), 1.0, 0.0)
+        # r0 dual part = g + A'v
+        L("ipm_lincomb3_f64", n, 1.0, ws.g.data_ptr(), 1.0, ws.ATv.data_ptr(), 0.0, None, ws.r0d.data_ptr())
+        # u0 = t*lin + gbar + A'v ;  u1 = t*P dx + A'dv
+        L("ipm_lincomb3_f64", n, t, lin.data_ptr(), 1.0, ws.gtrial.data_ptr(), 1.0, ws.ATv.data_ptr(),
+          ws.u0.data_ptr())
+        if d.is_qp:
+            L("ipm_gemv_n_f64", d.P.data_ptr(), d.ldp, n, n, ws.dz.data_ptr(), ws.Pdx.data_ptr(), 1.0, 0.0)
+            L("ipm_lincomb3_f64", n, t, ws.Pdx.data_ptr(), 1.0, ws.ATdv.data_ptr(), 0.0, None, ws.u1.data_ptr())
+        else:
+            L("ipm_lincomb3_f64", n, 1.0, ws.ATdv.data_ptr(), 0.0, None, 0.0, None, ws.u1.data_ptr())
+        L("ipm_ls_residual_f64", n, p, ws.r0d.data_ptr(), ws.u0.data_ptr(), ws.u1.data_ptr(), ws.Axb.data_ptr(),
+          ws.Adx.data_ptr(), self.table.data_ptr(), self.table_len, ws.kmax.data_ptr(), self.alpha,
+          ws.ls_out.data_ptr())
+        L("ipm_axpy_dev_f64", n, ws.ls_out.data_ptr(), ws.dz.data_ptr(), z.data_ptr())
+        L("ipm_axpy_dev_f64", p, ws.ls_out.data_ptr(), ws.dv.data_ptr(), ws.v.data_ptr())
+        ws.host[:5].copy_(ws.ls_out[:5], non_blocking=True)
+        ws.host_info.copy_(ws.info, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h = ws.host
+        return dict(step=float(h[0]), stuck=int(h[1]), r0=float(h[3]), rnorm=float(h[4]),
+                    info=int(ws.host_info[0]) or int(ws.host_info[1]))
+
+    def reset_dual(self):
+        self.ws.v.zero_()
+
+    def _solve_infeasible(self, z):
+        rn = None
+        it = 0
+        for it in range(self.max_iters):
+            zsave, vsave = z.clone(), self.ws.v.clone()
+            r = self._iterate_infeasible(z)
+            if r["info"] != 0:
+                r = self._retry_regularised_infeasible(z, zsave, vsave)
+            self.newton_steps += 1
+            rn = None if r["stuck"] == 2 else r["rnorm"]
+            if self.trace is not None:
+                self.trace.append((r["step"], rn))
+            if r["step"] < STUCK:
+                return it + 1, rn, False
+            elif rn < self.eps:
+                return it + 1, rn, True
+        return it + 1, rn, False
+
+    def _retry_regularised_infeasible(self, z, zsave, vsave):
+        """Reference: sticky switch to LU solves (NewtonSolverInfeasibleStart.py:491-538).  Device engine:
+        regularised re-factorisation (same documented deviation as the feasible-start path)."""
+        self.use_backup = True
+        ws = self.ws
+        base = float(ws.hdiag.abs().mean()) if self.shift == 0.0 else self.shift
+        shift = max(self.shift, 1e-14 * max(base, 1e-300))
+        for _ in range(40):
+            self.shift = shift
+            z.copy_(zsave)
+            ws.v.copy_(vsave)
+            r = self._iterate_infeasible(z)
+            if r["info"] == 0:
+                return r
+            shift *= 100.0
+        raise np.linalg.LinAlgError("KKT system is not solvable even after regularisation")
