@@ -31,7 +31,7 @@ SIGNATURES = {
     "ipm_axpy_dev_f64": (_i, [_i, _dp, _dp, _dp, _dp]),
     "ipm_potrf_upper_f64": (_i, [_dp, _i, _i, _dp, _dp]),
     "ipm_trsm_upper_t_f64": (_i, [_dp, _i, _i, _dp, _i, _i, _dp]),
-    "ipm_trsv_upper_f64": (_i, [_dp, _i, _i, _dp, _i, _dp]),
+    "ipm_trsv_upper_f64": (_i, [_dp, _i, _i, _dp, _i, _dp, _dp]),
     "ipm_lin_barrier_ws_doubles": (_ll, []),
     "ipm_lin_barrier_eval_f64": (_i, [_i, _i, _dp, _dp, _dp, _dp, _dp, _dp, _i, _i, _dp, _dp, _dp, _dp, _dp, _dp,
                                       _dp]),

@@ -4,8 +4,9 @@
 // contraction as the Hessian itself (k = row index of the panel, see gemm_tn_core.cuh):
 //     trailing update   A22 -= U12^T U12        -> ipm_gemm_tn_f64(A = B = U12, alpha = -1, beta = 1, upper)
 //     TRSM update       B2  -= U12^T Y1         -> ipm_gemm_tn_f64(A = U12, B = Y1)
-// so the DMMA/TMA core does n^3/3 of the n^3/3 flops; the per-panel pieces below (128x128 diagonal
-// factor, 128-row triangular panel solve) are the serial O(n^2 NB) remainder.
+// so the DMMA/TMA core does the n^3/3 flops; the per-panel pieces below (128x128 diagonal factor, 128-row
+// triangular panel solve) are the serial O(n^2 NB) remainder.  Two-level blocking: the trailing update uses
+// K = 256 (two 128-row panels) so that each output tile is read/written half as often.
 #include "common.cuh"
 
 using namespace ipm;
@@ -13,39 +14,73 @@ using namespace ipm;
 extern "C" int ipm_gemm_tn_f64(const double* A, int lda, const double* B, int ldb, const double* w, double alpha,
                                double beta, double* D, int ldd, int M, int N, int K, int upper, void* stream);
 
-constexpr int NB = 128;  // panel height == GEMM tile
+constexpr int NB = 128;    // panel height == GEMM tile
+constexpr int NBO = 256;   // outer block (K of the trailing update)
 
 // ------------------------------------------------------------------------------------------------
-// Diagonal block: unblocked right-looking Cholesky of an nb x nb (nb <= 128) upper block held in smem.
-// info (1-based global index of the first non-positive pivot) is written once; 0 means success.
+// Diagonal block: right-looking Cholesky of an nb x nb (nb <= 128) upper block, REGISTER resident.
+// 16 warps; thread (warp w, lane t) owns rows w + 16a (a < 8) and columns t + 32b (b < 4).  Per column j the
+// owning warp scales the pivot row (rsqrt, no division on the chain) and publishes it through a
+// double-buffered 128-entry shared vector -- one barrier per column; everyone then applies the rank-1 update
+// to its registers.  info (1-based global index of the first non-positive pivot) is written once.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512, 1) potf2_kernel(double* __restrict__ A, long long ld, int nb, int k0,
                                                        int* __restrict__ info) {
-  extern __shared__ double S[];  // nb x LDS_
-  const int LDS_ = NB;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  for (int r = warp; r < nb; r += nwarps)
-    for (int c = r + lane; c < nb; c += 32) S[r * LDS_ + c] = A[(long long)r * ld + c];
-  __syncthreads();
-  for (int j = 0; j < nb; ++j) {
-    if (tid == 0) {
-      const double d = S[j * LDS_ + j];
-      if (!(d > 0.0) && atomicCAS(info, 0, k0 + j + 1) == 0) { /* first failure recorded */ }
-      S[j * LDS_ + j] = sqrt(d);
+  __shared__ double urow[2][NB];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double own[8][4];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int r = warp + 16 * a, c = lane + 32 * b;
+      own[a][b] = (r < nb && c < nb && c >= r) ? A[(long long)r * ld + c] : 0.0;
     }
-    __syncthreads();
-    const double dinv = 1.0 / S[j * LDS_ + j];
-    for (int c = j + 1 + tid; c < nb; c += blockDim.x) S[j * LDS_ + c] *= dinv;
-    __syncthreads();
-    for (int r = j + 1 + warp; r < nb; r += nwarps) {
-      const double ujr = S[j * LDS_ + r];
-      for (int c = r + lane; c < nb; c += 32) S[r * LDS_ + c] = fma(-ujr, S[j * LDS_ + c], S[r * LDS_ + c]);
+  // column j = 16*ja + jw: row j lives in own[ja][*] of warp jw, its pivot in own[ja][ja >> 1] of lane j & 31.
+  // ja is unrolled so every register-array index is a compile-time constant (no local-memory spill).
+#pragma unroll
+  for (int ja = 0; ja < 8; ++ja) {
+    for (int jw = 0; jw < 16; ++jw) {
+      const int j = 16 * ja + jw;
+      if (j >= nb) break;  // uniform
+      double* ur = urow[j & 1];
+      if (warp == jw) {
+        const double d = __shfl_sync(0xffffffffu, own[ja][ja >> 1], j & 31);
+        if (lane == 0 && !(d > 0.0)) atomicCAS(info, 0, k0 + j + 1);
+        const double dinv = rsqrt(d);
+        const double ujj = d * dinv;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int c = lane + 32 * b;
+          const double v = (c == j) ? ujj : (c > j ? own[ja][b] * dinv : 0.0);
+          ur[c] = v;
+          if (c >= j) own[ja][b] = v;
+        }
+      }
+      __syncthreads();
+      double uc[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) uc[b] = ur[lane + 32 * b];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        const int r = warp + 16 * a;
+        if (a >= ja && r > j && r < nb) {  // warp-uniform; rows above the pivot are final
+          const double ujr = ur[r];
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+            if (lane + 32 * b >= r) own[a][b] = fma(-ujr, uc[b], own[a][b]);
+        }
+      }
+      // urow is double buffered: the next column writes the other half, so one barrier per column suffices
     }
-    // the next pivot S[j+1][j+1] is final after this update; the barrier at the top of the next step orders it
-    __syncthreads();
   }
-  for (int r = warp; r < nb; r += nwarps)
-    for (int c = r + lane; c < nb; c += 32) A[(long long)r * ld + c] = S[r * LDS_ + c];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int r = warp + 16 * a, c = lane + 32 * b;
+      if (r < nb && c < nb && c >= r) A[(long long)r * ld + c] = own[a][b];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -65,13 +100,38 @@ __global__ void __launch_bounds__(256, 1) trsm_panel_kernel(const double* __rest
   const int c = tid & (TP_COLS - 1), tr = tid >> 6;  // 4 row phases
   const int col0 = blockIdx.x * TP_COLS;
   const int ncl = min(TP_COLS, ncols - col0);
-  for (int idx = tid; idx < nb * NB; idx += blockDim.x) {
-    const int r = idx / NB, cc = idx - r * NB;
-    Us[idx] = (cc >= r && cc < nb) ? U11[(long long)r * ldu + cc] : 0.0;
+  const bool vecU = (nb == NB) && !(ldu & 1) && !(((uintptr_t)U11) & 15);
+  const bool vecP = (nb == NB) && (ncl == TP_COLS) && !(ldp & 1) && !(((uintptr_t)(P + col0)) & 15);
+  if (vecU) {
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) {
+      const int idx = tid + 256 * q;  // double2 index
+      const int r = idx >> 6, cc = (idx & 63) * 2;
+      double2 v = make_double2(0.0, 0.0);
+      if (cc + 1 >= r) v = *reinterpret_cast<const double2*>(U11 + (long long)r * ldu + cc);
+      Us[r * NB + cc] = cc >= r ? v.x : 0.0;
+      Us[r * NB + cc + 1] = v.y;
+    }
+  } else {
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+      const int r = idx >> 7, cc = idx & 127;
+      Us[idx] = (r < nb && cc >= r && cc < nb) ? U11[(long long)r * ldu + cc] : 0.0;
+    }
   }
-  for (int idx = tid; idx < nb * TP_COLS; idx += blockDim.x) {
-    const int r = idx / TP_COLS, cc = idx - r * TP_COLS;
-    Ps[idx] = cc < ncl ? P[(long long)r * ldp + col0 + cc] : 0.0;
+  if (vecP) {
+#pragma unroll 8
+    for (int q = 0; q < 16; ++q) {
+      const int idx = tid + 256 * q;  // double2 index: row = idx / 32, col2 = idx % 32
+      const int r = idx >> 5, cc = (idx & 31) * 2;
+      const double2 v = *reinterpret_cast<const double2*>(P + (long long)r * ldp + col0 + cc);
+      Ps[r * TP_COLS + cc] = v.x;
+      Ps[r * TP_COLS + cc + 1] = v.y;
+    }
+  } else {
+    for (int idx = tid; idx < NB * TP_COLS; idx += 256) {
+      const int r = idx >> 6, cc = idx & 63;
+      Ps[idx] = (r < nb && cc < ncl) ? P[(long long)r * ldp + col0 + cc] : 0.0;
+    }
   }
   __syncthreads();
   for (int b0 = 0; b0 < nb; b0 += 32) {
@@ -81,10 +141,17 @@ __global__ void __launch_bounds__(256, 1) trsm_panel_kernel(const double* __rest
 #pragma unroll
       for (int r = 0; r < 32; ++r) {
         if (r < bl) {
-          double v = Ps[(b0 + r) * TP_COLS + c];
+          // four partial sums shorten the dependent FMA chain
+          double v0 = Ps[(b0 + r) * TP_COLS + c], v1 = 0.0, v2 = 0.0, v3 = 0.0;
 #pragma unroll
-          for (int l = 0; l < r; ++l) v = fma(-Us[(b0 + l) * NB + b0 + r], x[l], v);
-          x[r] = v / Us[(b0 + r) * NB + b0 + r];
+          for (int l = 0; l < r; ++l) {
+            const double u = Us[(b0 + l) * NB + b0 + r];
+            if ((l & 3) == 0) v0 = fma(-u, x[l], v0);
+            else if ((l & 3) == 1) v1 = fma(-u, x[l], v1);
+            else if ((l & 3) == 2) v2 = fma(-u, x[l], v2);
+            else v3 = fma(-u, x[l], v3);
+          }
+          x[r] = ((v0 + v1) + (v2 + v3)) / Us[(b0 + r) * NB + b0 + r];
           Ps[(b0 + r) * TP_COLS + c] = x[r];
         }
       }
@@ -95,6 +162,7 @@ __global__ void __launch_bounds__(256, 1) trsm_panel_kernel(const double* __rest
       double acc[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[q] = (rb + q < nb) ? Ps[(rb + q) * TP_COLS + c] : 0.0;
+#pragma unroll 8
       for (int l = 0; l < bl; ++l) {
         const double xl = Ps[(b0 + l) * TP_COLS + c];
         const double* urow = Us + (b0 + l) * NB + rb;
@@ -107,9 +175,19 @@ __global__ void __launch_bounds__(256, 1) trsm_panel_kernel(const double* __rest
     }
     __syncthreads();
   }
-  for (int idx = tid; idx < nb * TP_COLS; idx += blockDim.x) {
-    const int r = idx / TP_COLS, cc = idx - r * TP_COLS;
-    if (cc < ncl) P[(long long)r * ldp + col0 + cc] = Ps[idx];
+  if (vecP) {
+#pragma unroll 8
+    for (int q = 0; q < 16; ++q) {
+      const int idx = tid + 256 * q;
+      const int r = idx >> 5, cc = (idx & 31) * 2;
+      *reinterpret_cast<double2*>(P + (long long)r * ldp + col0 + cc) =
+          make_double2(Ps[r * TP_COLS + cc], Ps[r * TP_COLS + cc + 1]);
+    }
+  } else {
+    for (int idx = tid; idx < NB * TP_COLS; idx += 256) {
+      const int r = idx >> 6, cc = idx & 63;
+      if (r < nb && cc < ncl) P[(long long)r * ldp + col0 + cc] = Ps[idx];
+    }
   }
 }
 
@@ -117,9 +195,38 @@ static int launch_trsm_panel(const double* U11, long long ldu, int nb, double* P
                              cudaStream_t st) {
   if (ncols <= 0) return IPM_OK;
   const int smem = (NB * NB + NB * TP_COLS) * 8;
-  IPM_CUDA_CHECK(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  static bool attr_set = false;
+  if (!attr_set) {
+    IPM_CUDA_CHECK(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
   trsm_panel_kernel<<<ceil_div(ncols, TP_COLS), 256, smem, st>>>(U11, ldu, nb, P, ldp, ncols);
   IPM_LAUNCH_CHECK();
+  return IPM_OK;
+}
+
+// Library-owned side stream + events for the look-ahead (one set per device, created on first use).
+struct SideStream {
+  cudaStream_t stream;
+  cudaEvent_t fork, join, chain, u2;
+  bool ready;
+};
+static SideStream g_side[16];
+
+static int get_side_stream(SideStream** out) {
+  int dev = 0;
+  IPM_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 16) return IPM_ERR_ARG;
+  SideStream* s = &g_side[dev];
+  if (!s->ready) {
+    IPM_CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    IPM_CUDA_CHECK(cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming));
+    IPM_CUDA_CHECK(cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming));
+    IPM_CUDA_CHECK(cudaEventCreateWithFlags(&s->chain, cudaEventDisableTiming));
+    IPM_CUDA_CHECK(cudaEventCreateWithFlags(&s->u2, cudaEventDisableTiming));
+    s->ready = true;
+  }
+  *out = s;
   return IPM_OK;
 }
 
@@ -127,26 +234,77 @@ static int launch_trsm_panel(const double* U11, long long ldu, int nb, double* P
 // ipm_potrf_upper_f64: in-place blocked right-looking Cholesky, H = U^T U (upper triangle of H in/out; the
 // strict lower triangle is never read or written).  *info_dev = 0 on success, else the 1-based index of the
 // first non-positive pivot (LAPACK dpotrf convention); it is written on the device, never synchronised here.
+//
+// for each outer block of 256 rows:   [ potf2(128) ; trsm of its 128-row panel ; K=128 update of the second
+// 128-row band ]  [ potf2(128) ; trsm of the second panel ]  then ONE K=256 DMMA update of the trailing matrix.
 // ------------------------------------------------------------------------------------------------
 extern "C" int ipm_potrf_upper_f64(double* H, int ld, int n, int* info_dev, void* stream) {
   if (!H || !info_dev || n < 0 || ld < n || (ld & 1)) return IPM_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   IPM_CUDA_CHECK(cudaMemsetAsync(info_dev, 0, sizeof(int), st));
-  IPM_CUDA_CHECK(cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NB * NB * 8));
-  for (int k0 = 0; k0 < n; k0 += NB) {
-    const int nb = n - k0 < NB ? n - k0 : NB;
-    double* Akk = H + (long long)k0 * ld + k0;
-    potf2_kernel<<<1, 512, NB * NB * 8, st>>>(Akk, ld, nb, k0, info_dev);
-    IPM_LAUNCH_CHECK();
-    const int rest = n - k0 - nb;
-    if (rest > 0) {
-      double* A12 = Akk + nb;
-      int rc = launch_trsm_panel(Akk, ld, nb, A12, ld, rest, st);
+  // Look-ahead: the serial panel chain of outer block o+1 (two potf2 + two panel solves, single-CTA latency
+  // bound) runs on a side stream concurrently with the bulk trailing update of block o on the caller's stream.
+  //   side : chain(0), U1(0), chain(1), [wait U2(0)] U1(1), chain(2), ...
+  //   main :            [wait chain(0)] U2(0), [wait chain(1)] U2(1), ...
+  // U1(o) = update of the NEXT block's 256 rows (all the next chain needs); U2(o) = rows below them.
+  SideStream* ss = nullptr;
+  const bool lookahead = n > 2 * NBO;
+  if (lookahead) {
+    int rc = get_side_stream(&ss);
+    if (rc) return rc;
+    IPM_CUDA_CHECK(cudaEventRecord(ss->fork, st));
+    IPM_CUDA_CHECK(cudaStreamWaitEvent(ss->stream, ss->fork, 0));
+  }
+  cudaStream_t cs = lookahead ? ss->stream : st;  // stream of the panel chain
+  bool have_u2 = false;
+  for (int o0 = 0; o0 < n; o0 += NBO) {
+    const int oend = o0 + NBO < n ? o0 + NBO : n;
+    for (int k0 = o0; k0 < oend; k0 += NB) {
+      const int nb = n - k0 < NB ? n - k0 : NB;
+      double* Akk = H + (long long)k0 * ld + k0;
+      potf2_kernel<<<1, 512, 0, cs>>>(Akk, ld, nb, k0, info_dev);
+      IPM_LAUNCH_CHECK();
+      const int rest = n - k0 - nb;
+      if (rest <= 0) continue;
+      double* A12 = Akk + nb;  // nb x rest row panel
+      int rc = launch_trsm_panel(Akk, ld, nb, A12, ld, rest, cs);
       if (rc) return rc;
-      double* A22 = H + (long long)(k0 + nb) * ld + (k0 + nb);
-      rc = ipm_gemm_tn_f64(A12, ld, A12, ld, nullptr, -1.0, 1.0, A22, ld, rest, rest, nb, 1, stream);
-      if (rc) return rc;
+      const int band = oend - (k0 + nb);  // rows of this outer block still to be factored
+      if (band > 0) {
+        // A[k0+nb : oend, k0+nb : n] -= U12[:, :band]^T U12      (band x rest, K = nb; store col >= row only)
+        double* Aband = H + (long long)(k0 + nb) * ld + (k0 + nb);
+        rc = ipm_gemm_tn_f64(A12, ld, A12, ld, nullptr, -1.0, 1.0, Aband, ld, band, rest, nb, 2, (void*)cs);
+        if (rc) return rc;
+      }
     }
+    const int rest = n - oend;
+    if (rest <= 0) break;
+    const int K = oend - o0;
+    const double* Uo = H + (long long)o0 * ld + oend;  // K x rest panel rows of this outer block
+    double* A22 = H + (long long)oend * ld + oend;
+    if (!lookahead) {
+      int rc = ipm_gemm_tn_f64(Uo, ld, Uo, ld, nullptr, -1.0, 1.0, A22, ld, rest, rest, K, 1, stream);
+      if (rc) return rc;
+      continue;
+    }
+    IPM_CUDA_CHECK(cudaEventRecord(ss->chain, cs));
+    const int band2 = rest < NBO ? rest : NBO;
+    if (have_u2) IPM_CUDA_CHECK(cudaStreamWaitEvent(cs, ss->u2, 0));  // U1(o) rewrites rows that U2(o-1) wrote
+    int rc = ipm_gemm_tn_f64(Uo, ld, Uo, ld, nullptr, -1.0, 1.0, A22, ld, band2, rest, K, 2, (void*)cs);  // U1(o)
+    if (rc) return rc;
+    const int rest2 = rest - band2;
+    if (rest2 > 0) {
+      IPM_CUDA_CHECK(cudaStreamWaitEvent(st, ss->chain, 0));
+      rc = ipm_gemm_tn_f64(Uo + band2, ld, Uo + band2, ld, nullptr, -1.0, 1.0,
+                           A22 + (long long)band2 * ld + band2, ld, rest2, rest2, K, 1, stream);  // U2(o)
+      if (rc) return rc;
+      IPM_CUDA_CHECK(cudaEventRecord(ss->u2, st));
+      have_u2 = true;
+    }
+  }
+  if (lookahead) {
+    IPM_CUDA_CHECK(cudaEventRecord(ss->join, cs));
+    IPM_CUDA_CHECK(cudaStreamWaitEvent(st, ss->join, 0));
   }
   return IPM_OK;
 }
@@ -158,16 +316,25 @@ extern "C" int ipm_potrf_upper_f64(double* H, int ld, int n, int* info_dev, void
 extern "C" int ipm_trsm_upper_t_f64(const double* U, int ldu, int n, double* B, int ldb, int p, void* stream) {
   if (!U || !B || n < 0 || p < 0 || ldu < n || ldb < p || (ldu & 1) || (ldb & 1)) return IPM_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  for (int k0 = 0; k0 < n && p > 0; k0 += NB) {
-    const int nb = n - k0 < NB ? n - k0 : NB;
-    const double* Ukk = U + (long long)k0 * ldu + k0;
-    double* Bk = B + (long long)k0 * ldb;
-    int rc = launch_trsm_panel(Ukk, ldu, nb, Bk, ldb, p, st);
-    if (rc) return rc;
-    const int rest = n - k0 - nb;
-    if (rest > 0) {
-      rc = ipm_gemm_tn_f64(Ukk + nb, ldu, Bk, ldb, nullptr, -1.0, 1.0, B + (long long)(k0 + nb) * ldb, ldb, rest, p,
-                           nb, 0, stream);
+  for (int o0 = 0; o0 < n && p > 0; o0 += NBO) {
+    const int oend = o0 + NBO < n ? o0 + NBO : n;
+    for (int k0 = o0; k0 < oend; k0 += NB) {
+      const int nb = n - k0 < NB ? n - k0 : NB;
+      const double* Ukk = U + (long long)k0 * ldu + k0;
+      double* Bk = B + (long long)k0 * ldb;
+      int rc = launch_trsm_panel(Ukk, ldu, nb, Bk, ldb, p, st);
+      if (rc) return rc;
+      const int band = oend - (k0 + nb);
+      if (band > 0) {  // rows of the same outer block: B[k0+nb : oend] -= U[k0:k0+nb, k0+nb:oend]^T Y_k
+        rc = ipm_gemm_tn_f64(Ukk + nb, ldu, Bk, ldb, nullptr, -1.0, 1.0, B + (long long)(k0 + nb) * ldb, ldb, band, p,
+                             nb, 0, stream);
+        if (rc) return rc;
+      }
+    }
+    const int rest = n - oend;
+    if (rest > 0) {  // all rows below the outer block, K = 256
+      int rc = ipm_gemm_tn_f64(U + (long long)o0 * ldu + oend, ldu, B + (long long)o0 * ldb, ldb, nullptr, -1.0, 1.0,
+                               B + (long long)oend * ldb, ldb, rest, p, oend - o0, 0, stream);
       if (rc) return rc;
     }
   }
@@ -175,126 +342,177 @@ extern "C" int ipm_trsm_upper_t_f64(const double* U, int ldu, int n, double* B, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Vector triangular solves (HBM-bound: U is read once).  Right-looking in 128-wide strips:
+// Vector triangular solves (HBM-bound: U is read once).  Right-looking in 128-wide strips, ONE kernel per
+// strip: every CTA re-solves the 128x128 diagonal block in shared memory (4 warp-level 32x32 substitutions
+// with shuffles -- cheaper than a second launch plus a grid-wide dependency), CTA 0 publishes the strip's
+// solution, and each CTA applies the strip to its slice of the remaining right-hand side.
 //   trans = 1:  solve U^T y = b  (top -> bottom)      trans = 0:  solve U x = b  (bottom -> top)
+// `work` is the right-hand side (updated in place), `out` receives the solution (must not alias work).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 1) trsv_diag_kernel(const double* __restrict__ Ukk, long long ld, int nb,
-                                                           double* __restrict__ b, int trans) {
-  extern __shared__ double S[];  // nb x (NB + 1)
-  __shared__ double xs[NB];
-  const int LDS_ = NB + 1;
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < nb * NB; idx += blockDim.x) {
-    const int r = idx / NB, c = idx - r * NB;
-    if (c < nb) S[r * LDS_ + c] = c >= r ? Ukk[(long long)r * ld + c] : 0.0;
-  }
-  if (tid < nb) xs[tid] = b[tid];
-  __syncthreads();
-  if (trans) {
-    // forward: y_r = (b_r - sum_{l<r} U[l][r] y_l) / U[r][r]; right-looking update of the later entries
-    for (int r = 0; r < nb; ++r) {
-      if (tid == r) xs[r] = xs[r] / S[r * LDS_ + r];
-      __syncthreads();
-      if (tid > r && tid < nb) xs[tid] = fma(-S[r * LDS_ + tid], xs[r], xs[tid]);
-      __syncthreads();
+constexpr int TS_LD = NB + 1;
+
+__device__ __forceinline__ void trsv_block_solve(double* __restrict__ S, double* __restrict__ xs, int nb, int trans) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nsb = (nb + 31) >> 5;
+  for (int s = 0; s < nsb; ++s) {
+    const int sb = trans ? s : nsb - 1 - s;
+    const int base = sb * 32;
+    const int bl = min(32, nb - base);
+    if (warp == 0) {
+      const bool act = lane < bl;
+      double v = act ? xs[base + lane] : 0.0;
+      // reciprocal of the pivot once per lane: keeps the division off the 32-step dependent chain
+      const double rdg = act ? 1.0 / S[(base + lane) * TS_LD + base + lane] : 1.0;
+      if (trans) {
+        for (int l = 0; l < bl; ++l) {
+          const double yl = __shfl_sync(0xffffffffu, v * rdg, l);
+          if (lane == l) v = yl;
+          else if (lane > l && act) v = fma(-S[(base + l) * TS_LD + base + lane], yl, v);
+        }
+      } else {
+        for (int l = bl - 1; l >= 0; --l) {
+          const double xl = __shfl_sync(0xffffffffu, v * rdg, l);
+          if (lane == l) v = xl;
+          else if (lane < l) v = fma(-S[(base + lane) * TS_LD + base + l], xl, v);
+        }
+      }
+      if (act) xs[base + lane] = v;
     }
-  } else {
-    for (int r = nb - 1; r >= 0; --r) {
-      if (tid == r) xs[r] = xs[r] / S[r * LDS_ + r];
-      __syncthreads();
-      if (tid < r) xs[tid] = fma(-S[tid * LDS_ + r], xs[r], xs[tid]);
-      __syncthreads();
+    __syncthreads();
+    // apply the solved sub-block to the entries of this 128-block still to be solved
+    if (trans) {
+      const int cidx = tid;
+      if (cidx >= base + bl && cidx < nb) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int l = 0; l + 1 < bl; l += 2) {
+          a0 = fma(S[(base + l) * TS_LD + cidx], xs[base + l], a0);
+          a1 = fma(S[(base + l + 1) * TS_LD + cidx], xs[base + l + 1], a1);
+        }
+        if (bl & 1) a0 = fma(S[(base + bl - 1) * TS_LD + cidx], xs[base + bl - 1], a0);
+        xs[cidx] -= a0 + a1;
+      }
+    } else {
+      const int ridx = tid;
+      if (ridx < base) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int l = 0; l + 1 < bl; l += 2) {
+          a0 = fma(S[ridx * TS_LD + base + l], xs[base + l], a0);
+          a1 = fma(S[ridx * TS_LD + base + l + 1], xs[base + l + 1], a1);
+        }
+        if (bl & 1) a0 = fma(S[ridx * TS_LD + base + bl - 1], xs[base + bl - 1], a0);
+        xs[ridx] -= a0 + a1;
+      }
     }
+    __syncthreads();
   }
-  if (tid < nb) b[tid] = xs[tid];
 }
 
-// b[j] -= sum_{i<nb} U[i][j] * y[i]   for j in [0, ncols): rows i are the strip just solved.
-__global__ void __launch_bounds__(128) trsv_update_fwd_kernel(const double* __restrict__ Us, long long ld, int nb,
-                                                              const double* __restrict__ y, double* __restrict__ b,
-                                                              int ncols) {
-  __shared__ double ys[NB];
-  for (int i = threadIdx.x; i < NB; i += blockDim.x) ys[i] = i < nb ? y[i] : 0.0;
-  __syncthreads();
-  const int j = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
-  if (j >= ncols) return;
-  const bool pair = j + 1 < ncols;
-  const bool vec = pair && !(ld & 1) && !(((uintptr_t)(Us + j)) & 15);
-  double a0 = 0.0, a1 = 0.0;
+__global__ void __launch_bounds__(128, 1)
+trsv_strip_kernel(const double* __restrict__ U, long long ld, int n, int k0, int nb, double* __restrict__ work,
+                  double* __restrict__ out, int trans) {
+  extern __shared__ double S[];  // NB x TS_LD
+  __shared__ double xs[NB];
+  __shared__ double part[4][64];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* Ukk = U + (long long)k0 * ld + k0;
+  const bool vec = (nb == NB) && !(ld & 1) && !(((uintptr_t)Ukk) & 15);
   if (vec) {
-    int i = 0;
-    for (; i + 7 < nb; i += 8) {
-      double2 m[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) m[q] = *reinterpret_cast<const double2*>(Us + (long long)(i + q) * ld + j);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) { a0 = fma(m[q].x, ys[i + q], a0); a1 = fma(m[q].y, ys[i + q], a1); }
-    }
-    for (; i < nb; ++i) {
-      double2 m = *reinterpret_cast<const double2*>(Us + (long long)i * ld + j);
-      a0 = fma(m.x, ys[i], a0); a1 = fma(m.y, ys[i], a1);
+#pragma unroll 16
+    for (int q = 0; q < 64; ++q) {
+      const int idx = tid + 128 * q;  // double2 index
+      const int r = idx >> 6, c = (idx & 63) * 2;
+      if (c + 1 >= r) {
+        const double2 v = *reinterpret_cast<const double2*>(Ukk + (long long)r * ld + c);
+        S[r * TS_LD + c] = v.x;
+        S[r * TS_LD + c + 1] = v.y;
+      }
     }
   } else {
-    for (int i = 0; i < nb; ++i) {
-      a0 = fma(Us[(long long)i * ld + j], ys[i], a0);
-      if (pair) a1 = fma(Us[(long long)i * ld + j + 1], ys[i], a1);
+    for (int idx = tid; idx < nb * NB; idx += 128) {
+      const int r = idx >> 7, c = idx & 127;
+      if (c < nb && c >= r) S[r * TS_LD + c] = Ukk[(long long)r * ld + c];
     }
   }
-  b[j] -= a0;
-  if (pair) b[j + 1] -= a1;
-}
-
-// b[i] -= sum_{j<nb} U[i][j] * x[j]   for rows i in [0, nrows): one warp per row, strip columns contiguous.
-__global__ void __launch_bounds__(256) trsv_update_bwd_kernel(const double* __restrict__ Us, long long ld, int nb,
-                                                              const double* __restrict__ x, double* __restrict__ b,
-                                                              int nrows) {
-  __shared__ double xs[NB];
-  for (int i = threadIdx.x; i < NB; i += blockDim.x) xs[i] = i < nb ? x[i] : 0.0;
+  if (tid < nb) xs[tid] = work[k0 + tid];
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int r = warp_global; r < nrows; r += nwarps) {
-    const double* row = Us + (long long)r * ld;
-    double acc = 0.0;
-    for (int j = lane; j < nb; j += 32) acc = fma(row[j], xs[j], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) b[r] -= acc;
+  trsv_block_solve(S, xs, nb, trans);
+  if (blockIdx.x == 0 && tid < nb) out[k0 + tid] = xs[tid];
+  if (trans) {
+    // work[j] -= sum_i U[k0+i][j] * y_i   for this CTA's 64 columns j > k0+nb-1; warps split the 128 rows
+    const int rest = n - k0 - nb;
+    const int j0 = blockIdx.x * 64;
+    if (j0 >= rest) return;
+    const double* Us = Ukk + nb + j0;
+    const int j = 2 * lane;
+    double a0 = 0.0, a1 = 0.0;
+    const bool pair = j0 + j + 1 < rest, one = j0 + j < rest;
+    const bool v2 = pair && !(ld & 1) && !(((uintptr_t)Us) & 15);
+    const int i0 = warp * 32, i1 = min(nb, i0 + 32);
+    if (v2) {
+#pragma unroll 16
+      for (int i = i0; i < i1; ++i) {
+        const double2 m = *reinterpret_cast<const double2*>(Us + (long long)i * ld + j);
+        a0 = fma(m.x, xs[i], a0);
+        a1 = fma(m.y, xs[i], a1);
+      }
+    } else if (one) {
+      for (int i = i0; i < i1; ++i) {
+        a0 = fma(Us[(long long)i * ld + j], xs[i], a0);
+        if (pair) a1 = fma(Us[(long long)i * ld + j + 1], xs[i], a1);
+      }
+    }
+    part[warp][j] = a0;
+    part[warp][j + 1] = a1;
+    __syncthreads();
+    if (tid < 64 && j0 + tid < rest)
+      work[k0 + nb + j0 + tid] -= (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+  } else {
+    // work[i] -= sum_j U[i][k0+j] * x_j   for this CTA's 64 rows i < k0; one warp per row, 16 rows per warp
+    const int r0 = blockIdx.x * 64;
+    if (r0 >= k0) return;
+    const bool v2 = (nb == NB) && !(ld & 1) && !(((uintptr_t)(U + k0)) & 15);
+    for (int rr = warp; rr < 64; rr += 4) {
+      const int i = r0 + rr;
+      if (i >= k0) break;
+      const double* row = U + (long long)i * ld + k0;
+      double a = 0.0;
+      if (v2) {
+        const double2 m0 = *reinterpret_cast<const double2*>(row + 2 * lane);
+        const double2 m1 = *reinterpret_cast<const double2*>(row + 64 + 2 * lane);
+        a = fma(m0.x, xs[2 * lane], a);
+        a = fma(m0.y, xs[2 * lane + 1], a);
+        a = fma(m1.x, xs[64 + 2 * lane], a);
+        a = fma(m1.y, xs[64 + 2 * lane + 1], a);
+      } else {
+        for (int jj = lane; jj < nb; jj += 32) a = fma(row[jj], xs[jj], a);
+      }
+      a = warp_sum(a);
+      if (lane == 0) work[i] -= a;
+    }
   }
 }
 
-extern "C" int ipm_trsv_upper_f64(const double* U, int ld, int n, double* b, int trans, void* stream) {
-  if (!U || !b || n < 0 || ld < n) return IPM_ERR_ARG;
+// b is overwritten with the solution; ws holds n doubles of scratch.
+extern "C" int ipm_trsv_upper_f64(const double* U, int ld, int n, double* b, int trans, double* ws, void* stream) {
+  if (!U || !b || !ws || n < 0 || ld < n) return IPM_ERR_ARG;
+  if (n == 0) return IPM_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int smem = NB * (NB + 1) * 8;
-  IPM_CUDA_CHECK(cudaFuncSetAttribute(trsv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  if (trans) {
-    for (int k0 = 0; k0 < n; k0 += NB) {
-      const int nb = n - k0 < NB ? n - k0 : NB;
-      const double* Ukk = U + (long long)k0 * ld + k0;
-      trsv_diag_kernel<<<1, 128, smem, st>>>(Ukk, ld, nb, b + k0, 1);
-      IPM_LAUNCH_CHECK();
-      const int rest = n - k0 - nb;
-      if (rest > 0) {
-        trsv_update_fwd_kernel<<<ceil_div(rest, 256), 128, 0, st>>>(Ukk + nb, ld, nb, b + k0, b + k0 + nb, rest);
-        IPM_LAUNCH_CHECK();
-      }
-    }
-  } else {
-    const int nblk = ceil_div(n, NB);
-    for (int kb = nblk - 1; kb >= 0; --kb) {
-      const int k0 = kb * NB;
-      const int nb = n - k0 < NB ? n - k0 : NB;
-      const double* Ukk = U + (long long)k0 * ld + k0;
-      trsv_diag_kernel<<<1, 128, smem, st>>>(Ukk, ld, nb, b + k0, 0);
-      IPM_LAUNCH_CHECK();
-      if (k0 > 0) {
-        int blocks = ceil_div(k0, 8);
-        if (blocks > 148 * 4) blocks = 148 * 4;
-        trsv_update_bwd_kernel<<<blocks, 256, 0, st>>>(U + k0, ld, nb, b + k0, b, k0);
-        IPM_LAUNCH_CHECK();
-      }
-    }
+  const int smem = NB * TS_LD * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    IPM_CUDA_CHECK(cudaFuncSetAttribute(trsv_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
   }
+  const int nblk = ceil_div(n, NB);
+  for (int s = 0; s < nblk; ++s) {
+    const int kb = trans ? s : nblk - 1 - s;
+    const int k0 = kb * NB;
+    const int nb = n - k0 < NB ? n - k0 : NB;
+    const int todo = trans ? n - k0 - nb : k0;
+    const int grid = todo > 0 ? ceil_div(todo, 64) : 1;
+    trsv_strip_kernel<<<grid, 128, smem, st>>>(U, ld, n, k0, nb, b, ws, trans);
+    IPM_LAUNCH_CHECK();
+  }
+  IPM_CUDA_CHECK(cudaMemcpyAsync(b, ws, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
   return IPM_OK;
 }

@@ -10,16 +10,57 @@ struct PlainEpilogue {
   long long ldd;
   int M, N;
   double alpha, beta;
-  int upper;
-  __device__ __forceinline__ void put(int row, int col, double v) const {
-    if (row >= M || col >= N) return;
-    if (upper && col < row) return;
-    double* p = D + (long long)row * ldd + col;
-    *p = (beta == 0.0) ? alpha * v : fma(alpha, v, beta * *p);
-  }
-  __device__ __forceinline__ void operator()(int row, int col, double v0, double v1) const {
-    put(row, col, v0);
-    put(row, col + 1, v1);
+  int tri;  // != 0: store only col >= row (upper triangle of the output block)
+
+  __device__ __forceinline__ void tile(const double (&acc)[8][4][2], int m_base, int n_base, int g8, int l4) const {
+    const bool vec_ok = ((ldd & 1) == 0) && ((((uintptr_t)D) & 15) == 0);
+    // fast path: the warp tile is fully inside the matrix, fully on/above the diagonal, 16-byte aligned
+    const bool interior = vec_ok && (m_base + 64 <= M) && (n_base + 32 <= N) && (!tri || n_base >= m_base + 63);
+    if (interior) {
+#pragma unroll
+      for (int ib = 0; ib < 8; ib += 2) {
+        double2 old[2][4];
+        if (beta != 0.0) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int jn = 0; jn < 4; ++jn)
+              old[i][jn] = *reinterpret_cast<const double2*>(D + (long long)(m_base + (ib + i) * 8 + g8) * ldd +
+                                                             n_base + jn * 8 + 2 * l4);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int jn = 0; jn < 4; ++jn) {
+            double2 v;
+            if (beta != 0.0) {
+              v.x = fma(alpha, acc[ib + i][jn][0], beta * old[i][jn].x);
+              v.y = fma(alpha, acc[ib + i][jn][1], beta * old[i][jn].y);
+            } else {
+              v.x = alpha * acc[ib + i][jn][0];
+              v.y = alpha * acc[ib + i][jn][1];
+            }
+            *reinterpret_cast<double2*>(D + (long long)(m_base + (ib + i) * 8 + g8) * ldd + n_base + jn * 8 +
+                                        2 * l4) = v;
+          }
+      }
+      return;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = m_base + i * 8 + g8;
+#pragma unroll
+      for (int jn = 0; jn < 4; ++jn) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = n_base + jn * 8 + 2 * l4 + e;
+          if (row < M && col < N && !(tri && col < row)) {
+            double* p = D + (long long)row * ldd + col;
+            *p = (beta == 0.0) ? alpha * acc[i][jn][e] : fma(alpha, acc[i][jn][e], beta * *p);
+          }
+        }
+      }
+    }
   }
 };
 
@@ -30,7 +71,8 @@ using namespace ipm;
 extern "C" int ipm_gemm_tn_f64(const double* A, int lda, const double* B, int ldb, const double* w, double alpha,
                                double beta, double* D, int ldd, int M, int N, int K, int upper, void* stream) {
   if (!A || !B || !D || M <= 0 || N <= 0 || K < 0 || lda < M || ldb < N || ldd < N) return IPM_ERR_ARG;
-  if (upper && M != N) return IPM_ERR_ARG;
+  if (upper == 1 && M != N) return IPM_ERR_ARG;
+  if (upper < 0 || upper > 2) return IPM_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap tmA, tmB;
   int rc = make_operand_map(&tmA, A, lda, K, M);
@@ -38,16 +80,17 @@ extern "C" int ipm_gemm_tn_f64(const double* A, int lda, const double* B, int ld
   rc = make_operand_map(&tmB, B, ldb, K, N);
   if (rc) return rc;
   const int tm = ceil_div(M, gemm::BM), tn = ceil_div(N, gemm::BN);
-  const int tiles = upper ? tn * (tn + 1) / 2 : tm * tn;
+  const int tri_tiles = upper == 1;  // upper == 2: all tiles, but still store only col >= row
+  const int tiles = tri_tiles ? tn * (tn + 1) / 2 : tm * tn;
   PlainEpilogue epi{D, ldd, M, N, alpha, beta, upper};
   if (w) {
     auto kern = gemm::gemm_tn_kernel<true, PlainEpilogue>;
     IPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
-    kern<<<tiles, gemm::THREADS, gemm::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, w, upper, epi);
+    kern<<<tiles, gemm::THREADS, gemm::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, w, tri_tiles, epi);
   } else {
     auto kern = gemm::gemm_tn_kernel<false, PlainEpilogue>;
     IPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
-    kern<<<tiles, gemm::THREADS, gemm::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, nullptr, upper, epi);
+    kern<<<tiles, gemm::THREADS, gemm::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, nullptr, tri_tiles, epi);
   }
   IPM_LAUNCH_CHECK();
   return IPM_OK;

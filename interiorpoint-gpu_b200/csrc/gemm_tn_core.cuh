@@ -88,8 +88,8 @@ __device__ __forceinline__ void decode_tile(int lin, int tiles_m, int tiles_n, b
   tj = t + (lin - (t * T - t * (t - 1) / 2));
 }
 
-// Epilogue concept:  void operator()(int row, int col, double v0, double v1) const
-//   v0 -> (row, col), v1 -> (row, col + 1); the functor does its own bounds checks.
+// Epilogue concept:  void tile(const double (&acc)[8][4][2], int m_base, int n_base, int g8, int l4) const
+//   called once per consumer warp with its 64x32 accumulator tile; the functor does its own bounds checks.
 template <bool HAS_W, class Epilogue>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
@@ -193,15 +193,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   // ---------------- epilogue ----------------
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = m0 + wm * 64 + i * 8 + g8;
-#pragma unroll
-    for (int jn = 0; jn < 4; ++jn) {
-      const int col = n0 + wn * 32 + jn * 8 + 2 * l4;
-      epi(row, col, acc[i][jn][0], acc[i][jn][1]);
-    }
-  }
+  // The functor sees the warp's whole 64x32 accumulator tile so it can batch its global loads:
+  //   acc[i][jn][e] -> row = m_base + i*8 + g8,  col = n_base + jn*8 + 2*l4 + e
+  epi.tile(acc, m0 + wm * 64, n0 + wn * 32, g8, l4);
 }
 
 }  // namespace gemm

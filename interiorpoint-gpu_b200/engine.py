@@ -135,6 +135,7 @@ class NewtonWorkspace:
         self.CtV = z(2, n)
         self.CtV_in = z(2, max(m, 1))
         self.red = z(8)
+        self.tr_ws = z(max(nz, p, 1))
         self.red_t = z(8)
         self.terms = z(8)  # [obj0, dobj, quad, g.z, g.dz, ...]
         self.ls_out = z(8)
@@ -272,8 +273,8 @@ class LinearNewton:
     def _chol_solve_vec(self, vec):
         """vec <- H^{-1} vec using the factor in ws.H."""
         ws, L = self.ws, self.L
-        L("ipm_trsv_upper_f64", ws.H.data_ptr(), ws.ldh, self.nz, vec.data_ptr(), 1)
-        L("ipm_trsv_upper_f64", ws.H.data_ptr(), ws.ldh, self.nz, vec.data_ptr(), 0)
+        L("ipm_trsv_upper_f64", ws.H.data_ptr(), ws.ldh, self.nz, vec.data_ptr(), 1, ws.tr_ws.data_ptr())
+        L("ipm_trsv_upper_f64", ws.H.data_ptr(), ws.ldh, self.nz, vec.data_ptr(), 0, ws.tr_ws.data_ptr())
 
     def _dots(self, pairs, out_offset=0):
         k = len(pairs)
@@ -449,8 +450,8 @@ class LinearNewton:
         ws.rhs_p.copy_(ws.Axb)
         L("ipm_gemv_n_f64", d.A.data_ptr(), d.lda, p, n, ws.yv.data_ptr(), ws.rhs_p.data_ptr(), -1.0, 1.0)
         ws.wv.copy_(ws.rhs_p)
-        L("ipm_trsv_upper_f64", ws.S.data_ptr(), ws.lds, p, ws.wv.data_ptr(), 1)
-        L("ipm_trsv_upper_f64", ws.S.data_ptr(), ws.lds, p, ws.wv.data_ptr(), 0)
+        L("ipm_trsv_upper_f64", ws.S.data_ptr(), ws.lds, p, ws.wv.data_ptr(), 1, ws.tr_ws.data_ptr())
+        L("ipm_trsv_upper_f64", ws.S.data_ptr(), ws.lds, p, ws.wv.data_ptr(), 0, ws.tr_ws.data_ptr())
         # dx = -H^{-1}(g + A'w)
         ws.dz.copy_(ws.g)
         L("ipm_gemv_t_f64", d.A.data_ptr(), d.lda, p, n, ws.wv.data_ptr(), 1, p, ws.dz.data_ptr(), n, 1.0, 1.0,

@@ -121,8 +121,9 @@ def test_potrf_trsv(n):
     rs = np.random.RandomState(n)
     b = rs.randn(n)
     bd = dev(b)
-    _abi.call("ipm_trsv_upper_f64", Hd.data_ptr(), ld, n, bd.data_ptr(), 1, None)
-    _abi.call("ipm_trsv_upper_f64", Hd.data_ptr(), ld, n, bd.data_ptr(), 0, None)
+    tws = torch.zeros(n, dtype=torch.float64, device="cuda")
+    _abi.call("ipm_trsv_upper_f64", Hd.data_ptr(), ld, n, bd.data_ptr(), 1, tws.data_ptr(), None)
+    _abi.call("ipm_trsv_upper_f64", Hd.data_ptr(), ld, n, bd.data_ptr(), 0, tws.data_ptr(), None)
     torch.cuda.synchronize()
     x = bd.cpu().numpy()
     # backward-stable solve: residual small relative to |H||x| + |b|

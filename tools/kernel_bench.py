@@ -69,8 +69,9 @@ res["potrf_ms"] = (t[0] - tcopy[0], t[1] - tcopy[1])
 res["potrf_tflops"] = n ** 3 / 3 / ((t[1] - tcopy[1]) * 1e-3) / 1e12
 res["potrf_info"] = int(info.item())
 b = torch.rand(n, dtype=torch.float64, device="cuda", generator=g)
-t = timeit(lambda: (_abi.call("ipm_trsv_upper_f64", Hf.data_ptr(), n, n, b.data_ptr(), 1, None),
-                    _abi.call("ipm_trsv_upper_f64", Hf.data_ptr(), n, n, b.data_ptr(), 0, None)))
+tws = torch.zeros(n, dtype=torch.float64, device="cuda")
+t = timeit(lambda: (_abi.call("ipm_trsv_upper_f64", Hf.data_ptr(), n, n, b.data_ptr(), 1, tws.data_ptr(), None),
+                    _abi.call("ipm_trsv_upper_f64", Hf.data_ptr(), n, n, b.data_ptr(), 0, tws.data_ptr(), None)))
 res["trsv2_ms"] = t
 t = timeit(lambda: _abi.call("ipm_gemv_n_f64", C_.data_ptr(), n, m, n, x.data_ptr(), y.data_ptr(), 1.0, 0.0, None))
 res["gemv_n_ms"] = t
