@@ -33,15 +33,23 @@ SIGNATURES = {
     "ipm_trsm_upper_t_f64": (_i, [_dp, _i, _i, _dp, _i, _i, _dp]),
     "ipm_trsv_upper_f64": (_i, [_dp, _i, _i, _dp, _i, _dp, _dp]),
     "ipm_lin_barrier_ws_doubles": (_ll, []),
-    "ipm_lin_barrier_eval_f64": (_i, [_i, _i, _dp, _dp, _dp, _dp, _dp, _dp, _i, _i, _dp, _dp, _dp, _dp, _dp, _dp,
+    "ipm_lin_barrier_eval_f64": (_i, [_i, _i, _dp, _dp, _dp, _dp, _dp, _dp, _i, _d, _dp, _dp, _dp, _dp, _dp, _dp,
                                       _dp]),
+    "ipm_lasso_partials_doubles": (_ll, [_i, _i]),
+    "ipm_lasso_admm_step_f64": (_i, [_dp, _i, _i, _i, _dp, _dp, _d, _dp, _dp, _dp, _dp, _i, _i, _i, _i, _dp, _dp,
+                                     _dp]),
+    "ipm_lasso_objective_f64": (_i, [_dp, _i, _i, _dp, _i, _i, _i, _dp, _i, _i, _dp, _dp]),
+    "ipm_scale_shift_f64": (_i, [_dp, _i, _dp, _i, _i, _i, _d, _d, _dp]),
+    "ipm_cone_eval_f64": (_i, [_i, _dp, _i, _dp, _dp, _dp, _d, _i, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "ipm_cone_grad_rows_f64": (_i, [_i, _i, _dp, _dp, _i, _dp, _i, _dp, _dp, _dp, _i, _dp]),
+    "ipm_cone_ls_coeffs_f64": (_i, [_i, _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp, _dp, _dp]),
     "ipm_lin_grad_f64": (_i, [_i, _d, _dp, _dp, _dp, _dp, _i, _dp, _dp, _dp, _dp, _dp]),
     "ipm_hess_finish_f64": (_i, [_dp, _i, _i, _dp, _dp, _dp, _d, _dp]),
     "ipm_scale_copy_upper_f64": (_i, [_dp, _i, _dp, _i, _i, _d, _dp]),
     "ipm_ls_feas_lin_f64": (_i, [_i, _i, _dp, _dp, _dp, _i, _i, _i, _dp, _i, _dp, _dp, _dp]),
     "ipm_ls_feas_poly_f64": (_i, [_i, _dp, _dp, _dp, _dp, _i, _dp, _i, _dp]),
-    "ipm_ls_armijo_f64": (_i, [_i, _dp, _dp, _dp, _dp, _i, _dp, _dp, _dp, _d, _d, _i, _dp, _dp]),
-    "ipm_ls_residual_f64": (_i, [_i, _i, _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp, _d, _dp, _dp]),
+    "ipm_ls_armijo_f64": (_i, [_i, _dp, _dp, _dp, _dp, _i, _dp, _dp, _dp, _d, _d, _i, _dp, _dp, _dp, _dp]),
+    "ipm_ls_residual_f64": (_i, [_i, _i, _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp, _d, _dp, _dp, _dp]),
     "ipm_trial_point_f64": (_i, [_i, _dp, _dp, _dp, _dp, _dp]),
     "ipm_lincomb3_f64": (_i, [_i, _d, _dp, _d, _dp, _d, _dp, _dp, _dp]),
     "ipm_table_lookup_f64": (_i, [_dp, _i, _dp, _dp, _dp]),

@@ -20,7 +20,7 @@ struct EvalRed {
 __global__ void __launch_bounds__(EV_THREADS)
 lin_barrier_eval_kernel(int m, int n, const double* __restrict__ Cx, const double* __restrict__ d,
                         const double* __restrict__ x, const double* __restrict__ ub, const double* __restrict__ lb,
-                        const double* __restrict__ s_ptr, int phase1, int hd_guard, double* __restrict__ slacks,
+                        const double* __restrict__ s_ptr, int phase1, double hd_guard, double* __restrict__ slacks,
                         double* __restrict__ inv, double* __restrict__ w, double* __restrict__ hdiag,
                         double* __restrict__ red_out, double* __restrict__ part, unsigned* __restrict__ counter) {
   __shared__ double red[32];
@@ -50,7 +50,7 @@ lin_barrier_eval_kernel(int m, int n, const double* __restrict__ Cx, const doubl
         const double iv = 1.0 / (sl + LOG_GUARD);
         slacks[lb_off + j] = sl;
         inv[lb_off + j] = iv;
-        hd += hd_guard ? iv * iv : 1.0 / (sl * sl);
+        hd += (hd_guard == 1e-15) ? iv * iv : 1.0 / ((sl + hd_guard) * (sl + hd_guard));
         sumlog += log(sl + LOG_GUARD);
         mins = fmin(mins, sl);
         suminv += iv;
@@ -62,7 +62,7 @@ lin_barrier_eval_kernel(int m, int n, const double* __restrict__ Cx, const doubl
         const double iv = 1.0 / (sl + LOG_GUARD);
         slacks[ub_off + j] = sl;
         inv[ub_off + j] = iv;
-        hd += hd_guard ? iv * iv : 1.0 / (sl * sl);
+        hd += (hd_guard == 1e-15) ? iv * iv : 1.0 / ((sl + hd_guard) * (sl + hd_guard));
         sumlog += log(sl + LOG_GUARD);
         mins = fmin(mins, sl);
         suminv += iv;
@@ -100,11 +100,11 @@ lin_barrier_eval_kernel(int m, int n, const double* __restrict__ Cx, const doubl
 extern "C" long long ipm_lin_barrier_ws_doubles(void) { return 5 * 296 + 2; }
 
 // slack layout: [m inequality rows | n upper-bound rows (if ub) | n lower-bound rows (if lb)]
-// hdiag_guarded: diagonal terms 1/(s+1e-15)^2 (phase-I and the diagonal-Hessian LP, FunctionManager.py:283-292,
+// hdiag_guard g: diagonal terms 1/(s+g)^2 -- g = 1e-15 for phase-I and the diagonal-Hessian LP (FunctionManager.py:283-292,
 // 561-587) instead of 1/s^2 (dense main phase, FunctionManager.py:320-322)
 extern "C" int ipm_lin_barrier_eval_f64(int m, int n, const double* Cx, const double* d, const double* x,
                                         const double* ub, const double* lb, const double* s_ptr, int phase1,
-                                        int hdiag_guarded, double* slacks, double* inv, double* w, double* hdiag, double* red_out,
+                                        double hdiag_guard, double* slacks, double* inv, double* w, double* hdiag, double* red_out,
                                         double* ws, void* stream) {
   if (m < 0 || n <= 0 || !x || !slacks || !inv || !hdiag || !red_out || !ws) return IPM_ERR_ARG;
   if (m > 0 && (!Cx || !d || !w)) return IPM_ERR_ARG;
@@ -112,7 +112,7 @@ extern "C" int ipm_lin_barrier_eval_f64(int m, int n, const double* Cx, const do
   if (blocks > 296) blocks = 296;
   unsigned* counter = reinterpret_cast<unsigned*>(ws + 5 * 296);
   lin_barrier_eval_kernel<<<blocks, EV_THREADS, 0, (cudaStream_t)stream>>>(m, n, Cx, d, x, ub, lb, s_ptr, phase1,
-                                                                          hdiag_guarded, slacks, inv, w, hdiag, red_out, ws,
+                                                                          hdiag_guard, slacks, inv, w, hdiag, red_out, ws,
                                                                           counter);
   IPM_LAUNCH_CHECK();
   return IPM_OK;

@@ -103,15 +103,21 @@ extern "C" int ipm_ls_feas_poly_f64(int count, const double* s0, const double* p
 // Armijo search of the feasible-start Newton method (single CTA).
 //   sumlog  : sum log(s(x)+1e-15) at the current point
 //   terms   : [0] obj(x)   [1] d obj . dx (linear part)   [2] dx' P dx (0 if none)   [3] g . x
-//   out     : [0] step  [1] stuck (0/1)  [2] final table index  [3] frozen log-sum  [4] Armijo trials
-// obj(x + a dx) = obj + a*scal[2] + 0.5*a*a*scal[3]   (exact for linear / quadratic objectives)
+//   out     : [0] step  [1] stuck (0/1; 3 = trial point infeasible, raise kmax and retry)  [2] final table index
+//             [3] frozen log-sum  [4] Armijo trials
+// obj(x + a dx) = obj + a*terms[1] + 0.5*a*a*terms[2]   (exact for linear / quadratic objectives)
+// L_direct / nneg (optional, second-order cones): the barrier log-sum and the count of negative slacks EVALUATED
+// AT the trial point x + table[kmax]*dx by a full barrier evaluation.  Cone slacks rhs^2 - |lhs|^2 cancel
+// catastrophically near the boundary, so the frozen term must come from the same formula the next iteration will
+// use (that is what the reference does, NewtonSolver.py:172-183); the polynomial only proposes kmax.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
 ls_armijo_kernel(int nc, const double* __restrict__ s0, const double* __restrict__ p1,
                  const double* __restrict__ p2, const double* __restrict__ table, int len,
                  const int* __restrict__ kmax_ptr, const double* __restrict__ sumlog_ptr,
                  const double* __restrict__ terms, double t, double alpha,
-                 int update_slacks_every, double* __restrict__ out) {
+                 int update_slacks_every, const double* __restrict__ L_direct,
+                 const double* __restrict__ nneg, double* __restrict__ out) {
   __shared__ double red[32];
   __shared__ double bcast;
   const int kstuck = len - 1;
@@ -119,6 +125,12 @@ ls_armijo_kernel(int nc, const double* __restrict__ s0, const double* __restrict
   if (k >= kstuck) {  // feasibility back-off ran out of steps (NewtonSolver.py:176-181)
     if (threadIdx.x == 0) {
       out[0] = table[kstuck]; out[1] = 1.0; out[2] = (double)kstuck; out[3] = NAN; out[4] = 0.0;
+    }
+    return;
+  }
+  if (nneg && *nneg > 0.0) {  // the proposed step leaves the domain when evaluated directly
+    if (threadIdx.x == 0) {
+      out[0] = table[k]; out[1] = 3.0; out[2] = (double)k; out[3] = NAN; out[4] = 0.0;
     }
     return;
   }
@@ -136,7 +148,7 @@ ls_armijo_kernel(int nc, const double* __restrict__ s0, const double* __restrict
   const double sumlog0 = *sumlog_ptr, obj0 = terms[0], dobj = terms[1], quad = terms[2], gx = terms[3];
   const double fx = t * obj0 - sumlog0;
   double a = table[k], a_eval = a;
-  double L = logsum(a_eval);
+  double L = L_direct ? *L_direct : logsum(a_eval);
   const double L_first = L;
   int attempt = 0, stuck = 0;
   while (true) {
@@ -158,11 +170,12 @@ ls_armijo_kernel(int nc, const double* __restrict__ s0, const double* __restrict
 
 extern "C" int ipm_ls_armijo_f64(int nc, const double* s0, const double* p1, const double* p2, const double* table,
                                  int len, const int* kmax, const double* sumlog, const double* terms, double t,
-                                 double alpha, int update_slacks_every, double* out, void* stream) {
+                                 double alpha, int update_slacks_every, const double* L_direct,
+                                 const double* nneg, double* out, void* stream) {
   if (nc < 0 || !table || len < 2 || !kmax || !sumlog || !terms || !out || (nc > 0 && (!s0 || !p1)))
     return IPM_ERR_ARG;
   ls_armijo_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nc, s0, p1, p2, table, len, kmax, sumlog, terms, t, alpha,
-                                                        update_slacks_every, out);
+                                                        update_slacks_every, L_direct, nneg, out);
   IPM_LAUNCH_CHECK();
   return IPM_OK;
 }
@@ -172,14 +185,15 @@ extern "C" int ipm_ls_armijo_f64(int nc, const double* s0, const double* p1, con
 //   r(a) = || [ u0 + a*u1 ; q0 + a*q1 ] ||     u: dual part (n),  q: primal part (p)
 //   r0   = || [ g + A'v ; A x - b ] || = || [ r0d ; q0 ] ||
 //   while r(a) > (1 - alpha*a) * r0:  a <- next table entry (stop when it drops below 1e-13)
-//   out : [0] step  [1] stuck (0/1/2: 2 = stuck already in the feasibility back-off)  [2] index
+//   out : [0] step  [1] stuck (0/1/2: 2 = stuck already in the feasibility back-off; 3 = trial point infeasible
+//         when evaluated directly (nneg > 0): raise kmax and retry)  [2] index
 //         [3] r0  [4] r(a) of the last evaluated trial
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
 ls_residual_kernel(int n, int p, const double* __restrict__ r0d, const double* __restrict__ u0,
                    const double* __restrict__ u1, const double* __restrict__ q0, const double* __restrict__ q1,
                    const double* __restrict__ table, int len, const int* __restrict__ kmax_ptr, double alpha,
-                   double* __restrict__ out) {
+                   const double* __restrict__ nneg, double* __restrict__ out) {
   __shared__ double red[32];
   __shared__ double bcast;
   const int kstuck = len - 1;
@@ -187,6 +201,12 @@ ls_residual_kernel(int n, int p, const double* __restrict__ r0d, const double* _
   if (k >= kstuck) {
     if (threadIdx.x == 0) {
       out[0] = table[kstuck]; out[1] = 2.0; out[2] = (double)kstuck; out[3] = NAN; out[4] = NAN;
+    }
+    return;
+  }
+  if (nneg && *nneg > 0.0) {
+    if (threadIdx.x == 0) {
+      out[0] = table[k]; out[1] = 3.0; out[2] = (double)k; out[3] = NAN; out[4] = NAN;
     }
     return;
   }
@@ -230,10 +250,11 @@ ls_residual_kernel(int n, int p, const double* __restrict__ r0d, const double* _
 
 extern "C" int ipm_ls_residual_f64(int n, int p, const double* r0d, const double* u0, const double* u1,
                                    const double* q0, const double* q1, const double* table, int len,
-                                   const int* kmax, double alpha, double* out, void* stream) {
+                                   const int* kmax, double alpha, const double* nneg, double* out, void* stream) {
   if (n <= 0 || p < 0 || !r0d || !u0 || !u1 || !table || len < 2 || !kmax || !out || (p > 0 && (!q0 || !q1)))
     return IPM_ERR_ARG;
-  ls_residual_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, p, r0d, u0, u1, q0, q1, table, len, kmax, alpha, out);
+  ls_residual_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, p, r0d, u0, u1, q0, q1, table, len, kmax, alpha, nneg,
+                                                          out);
   IPM_LAUNCH_CHECK();
   return IPM_OK;
 }

@@ -11,6 +11,7 @@ Mirrors, on the device, ``FunctionManagerLP/QP/Phase1`` (FunctionManager.py:197-
 """
 
 import ctypes as C
+from types import SimpleNamespace
 
 import numpy as np
 import torch
@@ -125,7 +126,7 @@ class NewtonWorkspace:
         self.ldh = _round_up(nz, 16)
         self.H = z(nz, self.ldh)
         self.g, self.dz, self.trial, self.gtrial = z(nz), z(nz), z(nz), z(nz)
-        ms = max(data.n_slacks, 1)
+        ms = max(data.n_slacks + getattr(data, "n_tail", 0), 1)
         self.slacks, self.inv, self.p1 = z(ms), z(ms), z(ms)
         self.slacks_t, self.inv_t = z(ms), z(ms)
         self.w, self.Cx, self.Cdx = z(max(m, 1)), z(max(m, 1)), z(max(m, 1))
@@ -157,6 +158,8 @@ class NewtonWorkspace:
             self.ATv, self.ATdv, self.yv = z(n), z(n), z(n)
             self.r0d, self.u0, self.u1 = z(n), z(n), z(n)
             self.hinv = z(n)
+        self.cur = SimpleNamespace(slacks=self.slacks, inv=self.inv, w=self.w, hdiag=self.hdiag, red=self.red)
+        self.tri = SimpleNamespace(slacks=self.slacks_t, inv=self.inv_t, w=self.w_t, hdiag=self.hdiag_t, red=self.red_t)
         # pinned host mirror for the once-per-iteration readback
         self.host = torch.zeros(24, dtype=F64).pin_memory()
         self.host_info = torch.zeros(2, dtype=torch.int32).pin_memory()
@@ -187,6 +190,7 @@ class LinearNewton:
         self.table_len = len(tab)
         self.t = 1.0
         self.use_backup = False  # sticky, like the reference (NewtonSolver.py:319)
+        self.direct_trial = False  # cones: re-evaluate the barrier AT the proposed trial point
         self.shift = 0.0
         self.newton_steps = 0
         self.trace = None
@@ -195,14 +199,18 @@ class LinearNewton:
     def set_t(self, t):
         self.t = float(t)
 
-    def _eval(self, z, slacks, inv, w, hdiag, red):
+    def _eval(self, z, slot):
+        """Slacks, reciprocals, SYRK weights, diagonal terms and scalar reductions at z into `slot`
+        (ws.cur for the iterate, ws.tri for a line-search trial point)."""
         d, ws, L = self.d, self.ws, self.L
+        slacks, inv, w, hdiag, red = slot.slacks, slot.inv, slot.w, slot.hdiag, slot.red
         n, m = d.n, d.m
         if m:
             L("ipm_gemv_n_f64", d.C.data_ptr(), d.ldc, m, n, z.data_ptr(), ws.Cx.data_ptr(), 1.0, 0.0)
         s_ptr = z.data_ptr() + 8 * n if self.phase1 else None
         L("ipm_lin_barrier_eval_f64", m, n, _abi.ptr(ws.Cx) if m else None, _abi.ptr(d.d), z.data_ptr(),
-          _abi.ptr(d.ub), _abi.ptr(d.lb), s_ptr, int(self.phase1), int(self.phase1 or self.diagonal), slacks.data_ptr(), inv.data_ptr(), w.data_ptr(),
+          _abi.ptr(d.ub), _abi.ptr(d.lb), s_ptr, int(self.phase1),
+          1e-15 if (self.phase1 or self.diagonal) else 0.0, slacks.data_ptr(), inv.data_ptr(), w.data_ptr(),
           hdiag.data_ptr(), red.data_ptr(), ws.ev_ws.data_ptr())
 
     def _bound_inv_ptrs(self, inv):
@@ -231,9 +239,10 @@ class LinearNewton:
         L("ipm_gemv_n_f64", d.P.data_ptr(), d.ldp, d.n, d.n, z.data_ptr(), ws.lin.data_ptr(), 1.0, beta)
         return ws.lin
 
-    def _gradient(self, t, lin, inv, w, red, g, want_border):
+    def _gradient(self, t, lin, slot, g, want_border):
         """g from reciprocal slacks (FunctionManager.py:232-265, 509-545, 741-781)."""
         d, ws, L = self.d, self.ws, self.L
+        inv, w, red = slot.inv, slot.w, slot.red
         n, m = d.n, d.m
         nv = 2 if (self.phase1 and want_border) else 1
         if m:
@@ -270,6 +279,10 @@ class LinearNewton:
         L("ipm_hess_finish_f64", ws.H.data_ptr(), ws.ldh, n, ws.hdiag.data_ptr(),
           ws.hxs.data_ptr() if self.phase1 else None, (ws.red.data_ptr() + 24) if self.phase1 else None, shift)
 
+    def _p2_ptr(self):
+        """Quadratic line-search coefficients (second-order cones only)."""
+        return None
+
     def _chol_solve_vec(self, vec):
         """vec <- H^{-1} vec using the factor in ws.H."""
         ws, L = self.ws, self.L
@@ -297,14 +310,14 @@ class LinearNewton:
     def min_slack(self, z):
         """Smallest slack at z (used for the phase-I start s0 = 1 - min slack, FunctionManager.py:390-393)."""
         ws = self.ws
-        self._eval(z, ws.slacks, ws.inv, ws.w, ws.hdiag, ws.red)
+        self._eval(z, ws.cur)
         ws.host[:1].copy_(ws.red[1:2], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(ws.host[0])
 
     def slacks_at(self, x):
         ws = self.ws
-        self._eval(x, ws.slacks, ws.inv, ws.w, ws.hdiag, ws.red)
+        self._eval(x, ws.cur)
         return ws.slacks[: self.d.n_slacks].clone()
 
     def equality_residual(self, x):
@@ -351,9 +364,9 @@ class LinearNewton:
     def _iterate_feasible(self, z):
         d, ws, L = self.d, self.ws, self.L
         t = self.t
-        self._eval(z, ws.slacks, ws.inv, ws.w, ws.hdiag, ws.red)
+        self._eval(z, ws.cur)
         lin = self._lin_term(z)
-        self._gradient(t, lin, ws.inv, ws.w, ws.red, ws.g, want_border=True)
+        self._gradient(t, lin, ws.cur, ws.g, want_border=True)
         if self.diagonal:
             # bounds-only LP: H is diagonal, dx = -g / h (NewtonSolver.py:415-420)
             L("ipm_vec_op_f64", 1, d.n, ws.g.data_ptr(), ws.hdiag.data_ptr(), ws.dz.data_ptr(), -1.0)
@@ -365,19 +378,32 @@ class LinearNewton:
         self._feasibility(z)
         pairs = self._objective_pairs(z, lin) + [(ws.g, z, self.nz), (ws.g, ws.dz, self.nz)]
         self._dots(pairs)
-        L("ipm_ls_armijo_f64", d.n_slacks, ws.slacks.data_ptr(), ws.p1.data_ptr(), None, self.table.data_ptr(),
-          self.table_len, ws.kmax.data_ptr(), ws.red.data_ptr(), ws.terms.data_ptr(), t, self.alpha,
-          self.update_slacks_every, ws.ls_out.data_ptr())
+        while True:
+            L_direct, nneg = self._verify_trial(z)
+            L("ipm_ls_armijo_f64", d.n_slacks, ws.slacks.data_ptr(), ws.p1.data_ptr(), self._p2_ptr(),
+              self.table.data_ptr(), self.table_len, ws.kmax.data_ptr(), ws.red.data_ptr(), ws.terms.data_ptr(), t,
+              self.alpha, self.update_slacks_every, L_direct, nneg, ws.ls_out.data_ptr())
+            # one readback per Newton iteration (the axpy below is skipped by the kernel-side flag only on retry)
+            ws.host[:5].copy_(ws.ls_out[:5], non_blocking=True)
+            ws.host[5:10].copy_(ws.terms[:5], non_blocking=True)
+            ws.host_info.copy_(ws.info, non_blocking=True)
+            if L_direct is None:
+                break
+            torch.cuda.current_stream().synchronize()
+            if float(ws.host[1]) != 3.0:
+                break
+            ws.kmax.add_(1)  # rare: the polynomial proposal is infeasible when evaluated directly -> next step
         L("ipm_axpy_dev_f64", self.nz, ws.ls_out.data_ptr(), ws.dz.data_ptr(), z.data_ptr())
-        # one readback per Newton iteration
-        ws.host[:5].copy_(ws.ls_out[:5], non_blocking=True)
-        ws.host[5:10].copy_(ws.terms[:5], non_blocking=True)
         ws.host[10:11].copy_(z[self.nz - 1:self.nz], non_blocking=True)
-        ws.host_info.copy_(ws.info, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         h = ws.host
         return dict(step=float(h[0]), stuck=h[1] != 0, g_dz=float(h[9]), z_last=float(h[10]),
                     info=int(ws.host_info[0]))
+
+    def _verify_trial(self, z):
+        """Hook for barriers whose slacks must be re-evaluated AT the proposed trial point (second-order cones).
+        Returns device pointers (frozen log-sum, #negative slacks) or (None, None)."""
+        return None, None
 
     def solve(self, z):
         """Centering at the current t.  ``z`` is updated in place on the device.  Returns
@@ -408,8 +434,17 @@ class LinearNewton:
         (NewtonSolver.py:314-341); the device engine re-factorises H + shift*I with a growing shift instead
         (documented deviation: this path is only reached on numerically singular Hessians)."""
         self.use_backup = True
-        base = float(torch.diagonal(self.ws.H[:, : self.nz]).abs().mean()) if self.shift == 0.0 else self.shift
-        shift = max(self.shift, 1e-14 * max(base, 1e-300))
+        if self.shift == 0.0:
+            # scale of the shift from a fresh (unfactored) Hessian: the failed potrf left NaNs in ws.H
+            z.copy_(zsave)
+            self._eval(z, self.ws.cur)
+            self._gradient(self.t, self._lin_term(z), self.ws.cur, self.ws.g, want_border=True)
+            self._hessian(self.t)
+            diag = torch.diagonal(self.ws.H[:, : self.nz])
+            base = float(diag[torch.isfinite(diag)].abs().mean())
+        else:
+            base = self.shift
+        shift = max(self.shift, 1e-14 * (base if base > 0 else 1.0))
         for _ in range(40):
             self.shift = shift
             z.copy_(zsave)
@@ -467,40 +502,49 @@ class LinearNewton:
     def _iterate_infeasible(self, z):
         d, ws, L = self.d, self.ws, self.L
         n, p, t = d.n, d.p, self.t
-        self._eval(z, ws.slacks, ws.inv, ws.w, ws.hdiag, ws.red)
+        self._eval(z, ws.cur)
         lin = self._lin_term(z)
-        self._gradient(t, lin, ws.inv, ws.w, ws.red, ws.g, want_border=False)
+        self._gradient(t, lin, ws.cur, ws.g, want_border=False)
         self._direction_infeasible(z, lin)
         # feasibility back-off, then the barrier part of the gradient at the first feasible trial (frozen, Q4)
         self._feasibility(z)
-        L("ipm_table_lookup_f64", self.table.data_ptr(), self.table_len, ws.kmax.data_ptr(),
-          ws.ls_out.data_ptr() + 48)  # a_k -> ls_out[6]
-        L("ipm_trial_point_f64", n, ws.ls_out.data_ptr() + 48, z.data_ptr(), ws.dz.data_ptr(), ws.trial.data_ptr())
-        self._eval(ws.trial, ws.slacks_t, ws.inv_t, ws.w_t, ws.hdiag_t, ws.red_t)
-        self._gradient(0.0, None, ws.inv_t, ws.w_t, ws.red_t, ws.gtrial, want_border=False)  # barrier part only
         # cached products (NewtonSolverInfeasibleStart.py:196-205)
         L("ipm_gemv_t_f64", d.A.data_ptr(), d.lda, p, n, ws.v.data_ptr(), 1, p, ws.ATv.data_ptr(), n, 1.0, 0.0,
           ws.gt_ws.data_ptr(), ws.gt_ws_n)
         L("ipm_gemv_t_f64", d.A.data_ptr(), d.lda, p, n, ws.dv.data_ptr(), 1, p, ws.ATdv.data_ptr(), n, 1.0, 0.0,
           ws.gt_ws.data_ptr(), ws.gt_ws_n)
         L("ipm_gemv_n_f64", d.A.data_ptr(), d.lda, p, n, ws.dz.data_ptr(), ws.Adx.data_ptr(), 1.0, 0.0)
-        # r0 dual part = g + A'v
+        # r0 dual part = g + A'v ;  u1 = t*P dx + A'dv
         L("ipm_lincomb3_f64", n, 1.0, ws.g.data_ptr(), 1.0, ws.ATv.data_ptr(), 0.0, None, ws.r0d.data_ptr())
-        # u0 = t*lin + gbar + A'v ;  u1 = t*P dx + A'dv
-        L("ipm_lincomb3_f64", n, t, lin.data_ptr(), 1.0, ws.gtrial.data_ptr(), 1.0, ws.ATv.data_ptr(),
-          ws.u0.data_ptr())
         if d.is_qp:
             L("ipm_gemv_n_f64", d.P.data_ptr(), d.ldp, n, n, ws.dz.data_ptr(), ws.Pdx.data_ptr(), 1.0, 0.0)
             L("ipm_lincomb3_f64", n, t, ws.Pdx.data_ptr(), 1.0, ws.ATdv.data_ptr(), 0.0, None, ws.u1.data_ptr())
         else:
             L("ipm_lincomb3_f64", n, 1.0, ws.ATdv.data_ptr(), 0.0, None, 0.0, None, ws.u1.data_ptr())
-        L("ipm_ls_residual_f64", n, p, ws.r0d.data_ptr(), ws.u0.data_ptr(), ws.u1.data_ptr(), ws.Axb.data_ptr(),
-          ws.Adx.data_ptr(), self.table.data_ptr(), self.table_len, ws.kmax.data_ptr(), self.alpha,
-          ws.ls_out.data_ptr())
+        while True:
+            L("ipm_table_lookup_f64", self.table.data_ptr(), self.table_len, ws.kmax.data_ptr(),
+              ws.ls_out.data_ptr() + 48)  # a_k -> ls_out[6]
+            L("ipm_trial_point_f64", n, ws.ls_out.data_ptr() + 48, z.data_ptr(), ws.dz.data_ptr(),
+              ws.trial.data_ptr())
+            self._eval(ws.trial, ws.tri)
+            self._gradient(0.0, None, ws.tri, ws.gtrial, want_border=False)  # barrier part only
+            # u0 = t*lin + gbar + A'v
+            L("ipm_lincomb3_f64", n, t, lin.data_ptr(), 1.0, ws.gtrial.data_ptr(), 1.0, ws.ATv.data_ptr(),
+              ws.u0.data_ptr())
+            nneg = (ws.red_t.data_ptr() + 32) if self.direct_trial else None
+            L("ipm_ls_residual_f64", n, p, ws.r0d.data_ptr(), ws.u0.data_ptr(), ws.u1.data_ptr(), ws.Axb.data_ptr(),
+              ws.Adx.data_ptr(), self.table.data_ptr(), self.table_len, ws.kmax.data_ptr(), self.alpha, nneg,
+              ws.ls_out.data_ptr())
+            ws.host[:5].copy_(ws.ls_out[:5], non_blocking=True)
+            ws.host_info.copy_(ws.info, non_blocking=True)
+            if not self.direct_trial:
+                break
+            torch.cuda.current_stream().synchronize()
+            if float(ws.host[1]) != 3.0:
+                break
+            ws.kmax.add_(1)
         L("ipm_axpy_dev_f64", n, ws.ls_out.data_ptr(), ws.dz.data_ptr(), z.data_ptr())
         L("ipm_axpy_dev_f64", p, ws.ls_out.data_ptr(), ws.dv.data_ptr(), ws.v.data_ptr())
-        ws.host[:5].copy_(ws.ls_out[:5], non_blocking=True)
-        ws.host_info.copy_(ws.info, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         h = ws.host
         return dict(step=float(h[0]), stuck=int(h[1]), r0=float(h[3]), rnorm=float(h[4]),
@@ -532,8 +576,12 @@ class LinearNewton:
         regularised re-factorisation (same documented deviation as the feasible-start path)."""
         self.use_backup = True
         ws = self.ws
-        base = float(ws.hdiag.abs().mean()) if self.shift == 0.0 else self.shift
-        shift = max(self.shift, 1e-14 * max(base, 1e-300))
+        if self.shift == 0.0:
+            hd = ws.hdiag[torch.isfinite(ws.hdiag)]
+            base = float(hd.abs().mean()) if hd.numel() else 1.0
+        else:
+            base = self.shift
+        shift = max(self.shift, 1e-14 * (base if base > 0 else 1.0))
         for _ in range(40):
             self.shift = shift
             z.copy_(zsave)
