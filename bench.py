@@ -94,6 +94,24 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def hessian_dram_traffic(n, m):
+    """DRAM bytes (read + write) per launch of the Hessian kernel from the committed `ncu --set full` capture
+    (profiles/syrk_hessian_ncu_r01.csv, taken at the default cfg-2 shape); None for any other shape."""
+    if (n, m) != (8192, 16384):
+        return None
+    try:
+        import csv
+
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "syrk_hessian_ncu_r01.csv"))))
+        h, units, first = rows[0], rows[1], rows[2]
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        rd = float(first[h.index("dram__bytes_read.sum")]) * scale[units[h.index("dram__bytes_read.sum")]]
+        wr = float(first[h.index("dram__bytes_write.sum")]) * scale[units[h.index("dram__bytes_write.sum")]]
+        return rd + wr
+    except Exception:
+        return None
+
+
 def workload(args, rank):
     import problems
 
@@ -253,7 +271,8 @@ def main():
         "time_to_solve_s": ms * 1e-3 / args.steps, "newton_steps_per_solve": newton / args.steps / world,
         "objective": value_ref, "gpu_launches": int(launches), "clocks": clk.summary(),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
-                     "frac": achieved / FP64_TENSOR_PEAK_TFLOPS if achieved else None, "traffic": None,
+                     "frac": achieved / FP64_TENSOR_PEAK_TFLOPS if achieved else None,
+                     "traffic": hessian_dram_traffic(n, m), "algorithmic_bytes": 8.0 * (m * n + n * (n + 1) / 2),
                      "kernel": "gemm_tn_kernel<true> (Hessian C'diag(w)C, upper tiles)",
                      "flop_per_launch": flops, "ms_per_launch": hess_ms, "launches_timed": len(hess),
                      "peak_source": "FP64 DMMA issue-rate microbenchmark on this pool (tools/fp64_peak.cu, "

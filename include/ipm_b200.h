@@ -1,0 +1,160 @@
+/* ipm_b200.h -- C ABI of libipm_b200.so: the B200 (sm_100a) hot path of a log-barrier interior-point engine
+ * and a batched ADMM Lasso, drop-in behind the Python API of fdeguire03/InteriorPoint-GPU.
+ *
+ * The reference has NO native boundary: its "GPU arm" is CuPy calls selected by `if self.use_gpu:` inside the
+ * Python classes (e.g. FunctionManager.py:122-125, NewtonSolver.py:285-313).  Each entry point below names the
+ * reference call sites (file:line, relative to the reference repo) whose arithmetic it replaces; the host-side
+ * binding is ctypes (interiorpoint-gpu_b200/_abi.py), see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to FP64 data unless stated otherwise; matrices are row-major with an
+ *     explicit leading dimension in ELEMENTS.  Operands of ipm_gemm_tn_f64 (and everything built on it) need a
+ *     16-byte aligned base and an even leading dimension (TMA row stride); the engine pads ld to 16 doubles.
+ *   - symmetric matrices: only the UPPER triangle (col >= row) is read / written.  Cholesky is H = U^T U.
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream); nothing here
+ *     synchronises, allocates device memory, or throws.  Workspace comes from the caller (*_ws_doubles()).
+ *   - return value: IPM_OK, or a negative status.  Numerical failure is NOT a status: ipm_potrf_upper_f64 writes
+ *     LAPACK-style `info` to device memory, the line searches write a `stuck` flag (the reference signals these
+ *     with LinAlgError / success_flag=False, NewtonSolver.py:130-131,314-330).
+ */
+#ifndef IPM_B200_H
+#define IPM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPM_OK 0
+#define IPM_ERR_ARG (-1)       /* invalid size / alignment / null pointer */
+#define IPM_ERR_CUDA (-2)      /* CUDA runtime error, text via ipm_last_cuda_error() */
+#define IPM_ERR_NO_DEVICE (-3) /* no sm_100 device or driver entry point */
+
+/* ---- library status ------------------------------------------------------------------------------------ */
+int ipm_abi_version(void);
+int ipm_device_ok(void);                       /* IPM_OK iff the current device is compute capability 10.x */
+const char* ipm_last_cuda_error(void);
+unsigned long long ipm_launch_count(void);     /* kernels launched by this library in this process */
+
+/* ---- dense contraction core (TMA + FP64 DMMA) ----------------------------------------------------------- */
+/* D = beta*D + alpha * A^T diag(w) B.   A: K x M (lda), B: K x N (ldb), w: K or NULL, D: M x N (ldd).
+ * upper = 0: all of D;  1: M == N, only tiles/elements with col >= row (SYRK);  2: all tiles, elements col >= row.
+ * Replaces cp.matmul(C.T, (inv_s**2)[:,None]*C)  FunctionManager.py:301-312, 564-576, 801-813 (Hessian),
+ * the per-cone Hessian loop FunctionManager.py:1119-1144, 1396-1422, cp.matmul(A, A11_inv_AT)
+ * NewtonSolverInfeasibleStart.py:426,474,780,796 (Schur) and Qinv @ (u - alpha) LassoSolver.py:245-249. */
+int ipm_gemm_tn_f64(const double* A, int lda, const double* B, int ldb, const double* w, double alpha, double beta,
+                    double* D, int ldd, int M, int N, int K, int upper, void* stream);
+
+/* ---- HBM-streaming level-1/2 ---------------------------------------------------------------------------- */
+/* y = alpha * M x + beta * y   (M: rows x cols).  np.matmul(C, x) FunctionManager.py:123-125, 432-434, 939-941;
+ * np.matmul(P, x) :694-699, 759-761; A @ x NewtonSolverInfeasibleStart.py:199-205. */
+int ipm_gemv_n_f64(const double* M, int ld, int rows, int cols, const double* x, double* y, double alpha, double beta,
+                   void* stream);
+/* Y[v] = alpha * M^T V[v] + beta * Y[v],  v < nv <= 2 (deterministic two-stage column sums).
+ * np.matmul(C.T, inv_slacks) FunctionManager.py:256-262, 527-529, 568-570; A.T @ v
+ * NewtonSolverInfeasibleStart.py:197-203. */
+long long ipm_gemv_t_ws_doubles(int rows, int cols, int nv);
+int ipm_gemv_t_f64(const double* M, int ld, int rows, int cols, const double* V, int nv, int ldv, double* Y, int ldy,
+                   double alpha, double beta, double* ws, long long ws_doubles, void* stream);
+/* out[k] = a[k] . b[k], k < npairs <= 8; a, b, n are HOST arrays of device pointers / lengths.
+ * gradf.dot(x), gradf.dot(xstep) NewtonSolver.py:129,168; c.dot(x) FunctionManager.py:159. */
+int ipm_dots_f64(int npairs, const double* const* a, const double* const* b, const int* n, double* out, void* stream);
+/* y += (*a_dev) * x with the scalar on the device.  x += step_size * xstep NewtonSolver.py:103. */
+int ipm_axpy_dev_f64(int n, const double* a_dev, const double* x, double* y, void* stream);
+/* out = x + (*a_dev) * dx.  next_x = x + step_size * xstep NewtonSolver.py:167,182. */
+int ipm_trial_point_f64(int n, const double* a_dev, const double* x, const double* dx, double* out, void* stream);
+/* out = ca*a + cb*b + cc*c (b, c may be NULL). */
+int ipm_lincomb3_f64(int n, double ca, const double* a, double cb, const double* b, double cc, const double* c,
+                     double* out, void* stream);
+/* op 0: out = alpha*a*b;  1: out = alpha*a/b;  2: out = alpha/a.   -H_inv * gradf NewtonSolver.py:417-418. */
+int ipm_vec_op_f64(int op, int n, const double* a, const double* b, double* out, double alpha, void* stream);
+/* out[i][j] = s*in[i][j] (+ dshift on the diagonal).  Qinv_cache *= -m*rho LassoSolver.py:218. */
+int ipm_scale_shift_f64(const double* in, int ldi, double* out, int ldo, int rows, int cols, double s, double dshift,
+                        void* stream);
+
+/* ---- factorisation and triangular solves ---------------------------------------------------------------- */
+/* In-place H = U^T U on the upper triangle; *info_dev (device int) = 0 or the 1-based index of the first
+ * non-positive pivot.  scipy.linalg.cho_factor / cp.linalg.cholesky NewtonSolver.py:286,303;
+ * NewtonSolverInfeasibleStart.py:398,426,455,473,780,795; LassoSolver.py:160,178. */
+int ipm_potrf_upper_f64(double* H, int ld, int n, int* info_dev, void* stream);
+/* b <- U^{-T} b (trans = 1) or U^{-1} b (trans = 0); ws: n doubles.  cho_solve / solve_triangular
+ * NewtonSolver.py:287-313. */
+int ipm_trsv_upper_f64(const double* U, int ld, int n, double* b, int trans, double* ws, void* stream);
+/* B <- U^{-T} B, B: n x p.  cho_solve(L1, A.T) NewtonSolverInfeasibleStart.py:399-411,460-465;
+ * cho_solve(L, I) LassoSolver.py:163-188. */
+int ipm_trsm_upper_t_f64(const double* U, int ldu, int n, double* B, int ldb, int p, void* stream);
+
+/* ---- barrier evaluation: linear inequalities (LP / QP / phase-I) ---------------------------------------- */
+/* Slacks [m rows | ub | lb], reciprocals, SYRK weights w = inv^2, bound diagonal, reductions
+ * red_out[5] = {sum log(s+1e-15), min s, sum inv, sum inv^2, #(s<0)}.  s_ptr: phase-I slack variable (device) or
+ * NULL.  hdiag_guard g: diagonal 1/(s+g)^2.  update_slacks_fxn FunctionManager.py:118-149, 429-449;
+ * newton_objective :208-230, 484-507; inv_slacks :243-247. */
+long long ipm_lin_barrier_ws_doubles(void);
+int ipm_lin_barrier_eval_f64(int m, int n, const double* Cx, const double* d, const double* x, const double* ub,
+                             const double* lb, const double* s_ptr, int phase1, double hdiag_guard, double* slacks,
+                             double* inv, double* w, double* hdiag, double* red_out, double* ws, void* stream);
+/* g = t*lin - inv_lb + inv_ub + CtInv (main) or the phase-I gradient / Hessian border.
+ * gradient FunctionManager.py:232-265, 509-545, 741-781; hess_xs :568-587. */
+int ipm_lin_grad_f64(int n, double t, const double* lin, const double* CtInv, const double* inv_ub,
+                     const double* inv_lb, int phase1, const double* suminv, const double* CtW, double* g, double* hxs,
+                     void* stream);
+/* H[i][i] += hdiag[i] + shift; optional border column H[i][n] = border[i], H[n][n] = *hss + shift.
+ * FunctionManager.py:314-322, 589-607; add_psd_conditioning NewtonSolver.py:269-275. */
+int ipm_hess_finish_f64(double* H, int ld, int n, const double* hdiag, const double* border, const double* hss,
+                        double shift, void* stream);
+/* H(upper) = t * P(upper) (P NULL: zero).  self.hess = self.t * self.P FunctionManager.py:797, 1117. */
+int ipm_scale_copy_upper_f64(double* H, int ldh, const double* P, int ldp, int n, double t, void* stream);
+
+/* ---- barrier evaluation: second-order cones ------------------------------------------------------------- */
+/* Cone slacks s_i = rhs_i^2 - |lhs_i|^2 (+ *s_ptr), SYRK weights, coefficients of the per-cone gradient rows and
+ * the reductions (merged with red_bounds[5] from the bound part).  FunctionManager.py:933-994, 1258-1262. */
+int ipm_cone_eval_f64(int M, const int* cone_off, int ktot, const double* lhs, const double* rhs, const double* s_ptr,
+                      double guard, int tail_off, double* slacks, double* inv_c, double* wts, double* coefA,
+                      double* coefC, double* plog, double* pinv, const double* red_bounds, double* red_out,
+                      void* stream);
+/* G[i] = sum_{r in cone i} coefA[r] A[r] + coefC[i] c_i = 2/(s_i+eps) (A_i' lhs_i - c_i rhs_i).
+ * FunctionManager.py:1076-1093, 1124-1137, 1341-1358, 1401-1413. */
+int ipm_cone_grad_rows_f64(int M, int n, const int* cone_off, const double* A, int lda, const double* Cc, int ldc,
+                           const double* coefA, const double* coefC, double* G, int ldg, void* stream);
+/* Quadratic of every cone slack (and linear of every cone rhs) along x + a*dx. */
+int ipm_cone_ls_coeffs_f64(int M, const int* cone_off, const double* lhs, const double* rhs, const double* dlhs,
+                           const double* drhs, const double* ds_ptr, int tail_off, double* p1, double* p2,
+                           void* stream);
+
+/* ---- line searches (device side; `table` = 1, beta, beta^2, ... down to the first entry < 1e-13) --------- */
+/* Feasibility back-off: *kmax = first table index keeping every slack >= 0.  NewtonSolver.py:170-183;
+ * NewtonSolverInfeasibleStart.py:179-193. */
+int ipm_ls_feas_lin_f64(int m, int n, const double* slacks, const double* Cdx, const double* dz, int has_ub,
+                        int has_lb, int phase1, const double* table, int len, double* p1_out, int* kmax,
+                        void* stream);
+int ipm_ls_feas_poly_f64(int count, const double* s0, const double* p1, const double* p2, const double* table,
+                         int len, int* kmax, int reset, void* stream);
+/* Armijo loop with the reference's semantics (slope g.x, frozen barrier term, lagging trial point).
+ * out[5] = {step, stuck, index, frozen log-sum, trials}.  NewtonSolver.py:185-206.  textbook != 0: the plain Armijo
+ * rule of the stand-alone phase-I (slope g.dx = terms[4], barrier re-evaluated per trial; PhaseOne.py:187-218). */
+int ipm_ls_armijo_f64(int nc, const double* s0, const double* p1, const double* p2, const double* table, int len,
+                      const int* kmax, const double* sumlog, const double* terms, double t, double alpha,
+                      int update_slacks_every, const double* L_direct, const double* nneg, int textbook, double* out,
+                      void* stream);
+/* Residual-norm search of the infeasible-start method.  out[5] = {step, stuck, index, r0, r(step)}.
+ * NewtonSolverInfeasibleStart.py:207-273. */
+int ipm_ls_residual_f64(int n, int p, const double* r0d, const double* u0, const double* u1, const double* q0,
+                        const double* q1, const double* table, int len, const int* kmax, double alpha,
+                        const double* nneg, double* out, void* stream);
+int ipm_table_lookup_f64(const double* table, int len, const int* kmax, double* out, void* stream);
+
+/* ---- batched ADMM Lasso ---------------------------------------------------------------------------------- */
+/* One ADMM iteration for K problems: x = bA + Q~ z; alpha+ = prox(x + u, eta); u+ = u + x - alpha+;
+ * z_out = u+ - alpha+; on request the four squared norms of the stop test.  LassoSolver.py:245-253, 273-298,
+ * 517-543. */
+long long ipm_lasso_partials_doubles(int n, int K);
+int ipm_lasso_admm_step_f64(const double* Qt, int ldq, int n, int K, const double* bA, const double* eta, double rho,
+                            double* alpha, double* u, const double* z_in, double* z_out, int ld, int add_bias,
+                            int positive, int want_norms, double* partials, double* norms_out, void* stream);
+/* f_c = 1/(2m)|R[:,c]|^2 + reg_c * |alpha[1:,c]|_1 with R = A alpha - b.  LassoSolver.py:314-325. */
+int ipm_lasso_objective_f64(const double* R, int ldr, int m, const double* alpha, int lda, int n, int K,
+                            const double* reg, int add_bias, int positive, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPM_B200_H */

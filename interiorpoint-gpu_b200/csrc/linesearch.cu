@@ -117,7 +117,7 @@ ls_armijo_kernel(int nc, const double* __restrict__ s0, const double* __restrict
                  const int* __restrict__ kmax_ptr, const double* __restrict__ sumlog_ptr,
                  const double* __restrict__ terms, double t, double alpha,
                  int update_slacks_every, const double* __restrict__ L_direct,
-                 const double* __restrict__ nneg, double* __restrict__ out) {
+                 const double* __restrict__ nneg, int textbook, double* __restrict__ out) {
   __shared__ double red[32];
   __shared__ double bcast;
   const int kstuck = len - 1;
@@ -145,7 +145,9 @@ ls_armijo_kernel(int nc, const double* __restrict__ s0, const double* __restrict
     __syncthreads();
     return r;
   };
-  const double sumlog0 = *sumlog_ptr, obj0 = terms[0], dobj = terms[1], quad = terms[2], gx = terms[3];
+  // textbook != 0 (stand-alone PhaseOne.py:187-218): slope g.dx, barrier term re-evaluated at every trial, no lag
+  const double sumlog0 = *sumlog_ptr, obj0 = terms[0], dobj = terms[1], quad = terms[2];
+  const double gx = textbook ? terms[4] : terms[3];
   const double fx = t * obj0 - sumlog0;
   double a = table[k], a_eval = a;
   double L = L_direct ? *L_direct : logsum(a_eval);
@@ -161,7 +163,12 @@ ls_armijo_kernel(int nc, const double* __restrict__ s0, const double* __restrict
     a_eval = a;               // the point evaluated next lags the step by one beta (Q3)
     ++k;
     a = table[k];
-    if (update_slacks_every > 0 && (attempt % update_slacks_every == update_slacks_every - 1)) L = logsum(a_eval);
+    if (textbook) {
+      a_eval = a;
+      L = logsum(a_eval);
+    } else if (update_slacks_every > 0 && (attempt % update_slacks_every == update_slacks_every - 1)) {
+      L = logsum(a_eval);
+    }
   }
   if (threadIdx.x == 0) {
     out[0] = a; out[1] = (double)stuck; out[2] = (double)k; out[3] = L_first; out[4] = (double)attempt;
@@ -171,11 +178,11 @@ ls_armijo_kernel(int nc, const double* __restrict__ s0, const double* __restrict
 extern "C" int ipm_ls_armijo_f64(int nc, const double* s0, const double* p1, const double* p2, const double* table,
                                  int len, const int* kmax, const double* sumlog, const double* terms, double t,
                                  double alpha, int update_slacks_every, const double* L_direct,
-                                 const double* nneg, double* out, void* stream) {
+                                 const double* nneg, int textbook, double* out, void* stream) {
   if (nc < 0 || !table || len < 2 || !kmax || !sumlog || !terms || !out || (nc > 0 && (!s0 || !p1)))
     return IPM_ERR_ARG;
   ls_armijo_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nc, s0, p1, p2, table, len, kmax, sumlog, terms, t, alpha,
-                                                        update_slacks_every, L_direct, nneg, out);
+                                                        update_slacks_every, L_direct, nneg, textbook, out);
   IPM_LAUNCH_CHECK();
   return IPM_OK;
 }

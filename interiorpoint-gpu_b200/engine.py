@@ -382,7 +382,7 @@ class LinearNewton:
             L_direct, nneg = self._verify_trial(z)
             L("ipm_ls_armijo_f64", d.n_slacks, ws.slacks.data_ptr(), ws.p1.data_ptr(), self._p2_ptr(),
               self.table.data_ptr(), self.table_len, ws.kmax.data_ptr(), ws.red.data_ptr(), ws.terms.data_ptr(), t,
-              self.alpha, self.update_slacks_every, L_direct, nneg, ws.ls_out.data_ptr())
+              self.alpha, self.update_slacks_every, L_direct, nneg, 0, ws.ls_out.data_ptr())
             # one readback per Newton iteration (the axpy below is skipped by the kernel-side flag only on retry)
             ws.host[:5].copy_(ws.ls_out[:5], non_blocking=True)
             ws.host[5:10].copy_(ws.terms[:5], non_blocking=True)

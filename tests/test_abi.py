@@ -1,0 +1,94 @@
+"""CPU-side checks of the C-ABI boundary: the library builds for sm_100a, loads without a GPU, exports every
+symbol include/ipm_b200.h declares, the ctypes table agrees with the header, and the product path fails loudly
+(no CPU fallback) when no B200 is visible."""
+
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ipm_b200.h")
+
+
+def header_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(ipm_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    return out
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+
+    g.build()
+    from ipm_b200 import _abi
+
+    return _abi.lib()
+
+
+def test_header_symbols_are_exported(lib):
+    fns = header_functions()
+    assert len(fns) >= 30
+    for name in fns:
+        assert hasattr(lib, name), f"{name} declared in include/ipm_b200.h but not exported"
+
+
+def test_ctypes_table_matches_header(lib):
+    from ipm_b200 import _abi
+
+    fns = header_functions()
+    assert set(_abi.SIGNATURES) == set(fns)
+    for name, (_, argtypes) in _abi.SIGNATURES.items():
+        assert len(argtypes) == fns[name], f"{name}: ctypes has {len(argtypes)} args, header {fns[name]}"
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+
+    from ipm_b200 import _abi
+
+    out = subprocess.run(["cuobjdump", "-lelf", _abi.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_blackwell_evidence_in_sass():
+    """TMA (UTMALDG) and FP64 tensor (DMMA) instructions are what the hot kernels are made of."""
+    import subprocess
+
+    from ipm_b200 import _abi
+
+    sass = subprocess.run(["cuobjdump", "-sass", _abi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTMALDG" in sass and "DMMA" in sass and "SYNCS" in sass
+
+
+def test_no_device_is_loud(lib):
+    import torch
+
+    from ipm_b200 import _abi
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    assert lib.ipm_device_ok() == _abi.IPM_ERR_NO_DEVICE
+    with pytest.raises(_abi.IpmError):
+        _abi.require_device()
+    import numpy as np
+
+    from ipm_b200.LPSolver import LPSolver
+
+    with pytest.raises(_abi.IpmError):  # the drop-in class must not silently fall back to NumPy
+        LPSolver(c=np.ones(3), C=np.eye(3), d=np.ones(3), check_cvxpy=False, suppress_print=True)
+
+
+def test_product_path_never_imports_oracle():
+    pkg = os.path.join(ROOT, "interiorpoint-gpu_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
