@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--cpu-newton-steps", type=int, default=2, help="full-size Newton steps in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--lasso-k", type=int, default=4096, help="Lasso batch size (0 disables the Lasso section)")
     return ap.parse_args()
 
 
@@ -131,6 +132,54 @@ def cpu_sample(prob, newton_steps):
     o.solve()
     dt = time.perf_counter() - t0
     return sum(o.inner_iters), dt
+
+
+def lasso_workload(K):
+    """BASELINE configs[4]: A 2048x512 (+bias), K problems, generator of testSolver.py:1096-1104 (seed 5)."""
+    n, rows = 512, 2048
+    rs = np.random.RandomState(5)
+    A = rs.rand(rows, n)
+    nnz = int(n * K / 4)
+    x_true = np.zeros((n, K))
+    x_true[np.unravel_index(rs.randint(0, n * K, nnz), (n, K))] = rs.uniform(0, 50, nnz)
+    reg = 0.05 + 0.01 * rs.randn(K)
+    b = A @ x_true + rs.randn(rows, K)
+    return A, b, reg
+
+
+def lasso_section(K, rank, world):
+    """Second headline metric (Lasso solves/s): the batch is split by strided columns across ranks (the
+    reference's num_chunks semantics), no communication.  Settings of the reference's GPU arm
+    (testSolver.py:1142-1159: eps 1e-6, max_iters 5000)."""
+    import torch
+
+    from ipm_b200 import dist as D
+    from ipm_b200.LassoSolver import LassoSolver
+
+    A, b, reg = lasso_workload(K)
+    cols = D.strided_columns(K, rank, world)
+    kw = dict(rho=0.4, check_stop=10, add_bias=True, check_cvxpy=False, eps_abs=1e-6, eps_rel=1e-6, max_iters=5000)
+    s = LassoSolver(A, b[:, cols], reg[cols], **kw)
+    s.solve()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = s.L.kernel_launches()
+    e0.record()
+    _, sol, _, its = s.solve()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = s.L.kernel_launches() - l0
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    s2 = LassoSolver(A, b[:, cols], reg[cols], **kw)
+    X2, _, _, _ = s2.solve()
+    f1.record()
+    torch.cuda.synchronize()
+    ms_e2e = f0.elapsed_time(f1)
+    n1 = A.shape[1] + 1
+    return dict(ms=ms, ms_e2e=ms_e2e, iters=int(its), k_local=len(cols), launches=launches,
+                flop=2.0 * n1 * n1 * len(cols) * its, h2d=s2.h2d_bytes, d2h=int(X2.nbytes))
 
 
 def run_reference(args):
@@ -242,6 +291,19 @@ def main():
         barrier()
         e2e_ms = f0.elapsed_time(f1)
 
+    # ------------------------------------------------------------------ Lasso batch (second headline metric)
+    lasso = None
+    if args.lasso_k > 0:
+        torch.cuda.empty_cache()
+        barrier()
+        lasso = lasso_section(args.lasso_k, rank, world)
+        lt = torch.tensor([lasso["ms"], lasso["ms_e2e"]], dtype=torch.float64, device="cuda")
+        ls = torch.tensor([lasso["flop"], float(lasso["launches"])], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(lt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ls, op=dist.ReduceOp.SUM)
+        lasso.update(ms=float(lt[0]), ms_e2e=float(lt[1]), flop=float(ls[0]), launches=int(ls[1]))
+
     # ------------------------------------------------------------------ reduce over ranks (max time, sum work)
     stats = torch.tensor([ms, float(newton), e2e_ms or 0.0, float(e2e_newton), float(launches)], dtype=torch.float64,
                          device="cuda")
@@ -281,6 +343,18 @@ def main():
     if e2e_ms:
         line["e2e"] = {"value": e2e_newton / (e2e_ms * 1e-3), "unit": "Newton steps/s", "h2d_bytes_per_step": int(h2d),
                        "d2h_bytes_per_step": int(d2h), "time_to_solve_s": e2e_ms * 1e-3 / args.steps}
+    if lasso is not None:
+        K = args.lasso_k
+        line["lasso"] = {
+            "metric": "lasso_solves_per_s", "workload": f"LassoSolver ADMM, A 2048x512 + bias, K={K} problems, eps 1e-6 "
+            "(BASELINE configs[4]); strided column split across ranks, no collective",
+            "value": K / (lasso["ms"] * 1e-3), "e2e_value": K / (lasso["ms_e2e"] * 1e-3), "unit": "solves/s",
+            "admm_iterations": lasso["iters"], "ms_per_iteration": lasso["ms"] / lasso["iters"],
+            "gpu_launches": lasso["launches"], "h2d_bytes": lasso["h2d"], "d2h_bytes": lasso["d2h"],
+            "roofline": {"bound": "tensor", "achieved": lasso["flop"] / (lasso["ms"] * 1e-3) / 1e12 / world,
+                         "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s per GPU",
+                         "frac": lasso["flop"] / (lasso["ms"] * 1e-3) / 1e12 / world / FP64_TENSOR_PEAK_TFLOPS,
+                         "note": "2 n^2 K flop per ADMM iteration over the whole solve() incl. stop checks"}}
     if not args.no_cpu_baseline and world == 1:
         k, dt = cpu_sample(prob, args.cpu_newton_steps)
         line["cpu_baseline"] = {"value": k / dt, "unit": "Newton steps/s", "cores": os.cpu_count(), "kind": "port",

@@ -58,6 +58,8 @@ class LassoSolver:
         self.X = np.zeros((self.n, self.num_samples))
         self.feasible, self.cvxpy_vals, self.cvxpy_sols = None, None, None
         self.h2d_bytes = (A.size + b.size + reg.size) * 8
+        # one chunk: everything is precomputed and resident before solve() (LassoSolver.py:193-222)
+        self._prep = self._prepare(np.arange(self.num_samples)) if self.num_chunks == 1 else None
 
     # ------------------------------------------------------------------------------------------------
     def _gemm(self, A, lda, B, ldb, D, ldd, M, N, K, alpha=1.0, beta=0.0, upper=0):
@@ -86,9 +88,10 @@ class LassoSolver:
         if int(info.item()) != 0:
             raise np.linalg.LinAlgError("A'A + m*rho*I is not positive definite")
 
-    def _run(self, cols):
-        """ADMM on the column subset ``cols`` (one chunk).  Returns (alpha device [n x K], objective [K], iters)."""
-        dev, n, m, L = self.device, self.n, self.m, self.L
+    def _prepare(self, cols):
+        """Host->device transfer of the chunk's b / reg and the cached products A'b, Q A'b (LassoSolver.py:193-216
+        for one chunk -- done once in the constructor, like the reference -- and :352-390 per chunk)."""
+        dev, n, m = self.device, self.n, self.m
         b = np.ascontiguousarray(self.b_host[:, cols])
         reg = np.ascontiguousarray(self.reg_host[cols])
         K = b.shape[1]
@@ -97,9 +100,20 @@ class LassoSolver:
         reg_dev = torch.as_tensor(reg).to(dev)
         eta = reg_dev / self.rho
         z = lambda: torch.zeros((n, ld), dtype=F64, device=dev)  # noqa: E731
-        Atb, bA, alpha, u, z0, z1 = z(), z(), z(), z(), z(), z()
+        Atb, bA = z(), z()
         self._gemm(self.A_dev, self.lda, b_dev, ld, Atb, ld, n, K, m)          # A'b
         self._gemm(self.Qinv, self.ldn, Atb, ld, bA, ld, n, K, n)              # Q A'b   (Q symmetric)
+        return dict(K=K, ld=ld, b_dev=b_dev, reg_dev=reg_dev, eta=eta, bA=bA, state=[z(), z(), z(), z()],
+                    R=torch.zeros((m, ld), dtype=F64, device=dev), fvals=torch.zeros(K, dtype=F64, device=dev))
+
+    def _run(self, cols, prep=None):
+        """ADMM on the column subset ``cols`` (one chunk).  Returns (alpha device [n x K], objective [K], iters)."""
+        dev, n, m, L = self.device, self.n, self.m, self.L
+        prep = prep or self._prepare(cols)
+        K, ld, b_dev, reg_dev, eta, bA = (prep[k] for k in ("K", "ld", "b_dev", "reg_dev", "eta", "bA"))
+        alpha, u, z0, z1 = prep["state"]
+        for t_ in (alpha, u, z0, z1):
+            t_.zero_()  # LassoSolver.py:226-236: every solve() restarts from zero
         npart = _abi.lib().ipm_lasso_partials_doubles(n, K)
         partials = torch.zeros(npart, dtype=F64, device=dev)
         norms = torch.zeros(4, dtype=F64, device=dev)
@@ -107,8 +121,7 @@ class LassoSolver:
         stop_mult = self.EPS_ABS * np.sqrt(n * K)  # LassoSolver.py:200, 361
         zin, zout = z0, z1
         it = 0
-        R = torch.zeros((m, ld), dtype=F64, device=dev) if self.compute_loss else None
-        fvals = torch.zeros(K, dtype=F64, device=dev)
+        R, fvals = prep["R"], prep["fvals"]
         for it in range(self.max_iters):
             check = it % self.check_stop == self.check_stop - 1
             L("ipm_lasso_admm_step_f64", self.Qt.data_ptr(), self.ldn, n, K, bA.data_ptr(), eta.data_ptr(), self.rho,
@@ -126,8 +139,6 @@ class LassoSolver:
                 tol_dual = stop_mult + self.EPS_REL * self.rho * u_norm
                 if r_norm < tol_primal and d_norm < tol_dual:
                     break
-        if R is None:
-            R = torch.zeros((m, ld), dtype=F64, device=dev)
         self._objective(alpha, b_dev, reg_dev, ld, K, R, fvals)
         return alpha, fvals, it
 
@@ -144,7 +155,7 @@ class LassoSolver:
         reports ``iteration + 1``, several chunks report the list of ``iteration`` per chunk (:479)."""
         Ktot = self.num_samples
         if self.num_chunks == 1:
-            alpha, f, it = self._run(np.arange(Ktot))
+            alpha, f, it = self._run(np.arange(Ktot), self._prep)
             self.alpha = alpha[:, :Ktot]
             self.X = HostArray(self.alpha.cpu().numpy())
             self.solutions = HostArray(f.cpu().numpy())

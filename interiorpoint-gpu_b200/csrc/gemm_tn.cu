@@ -62,6 +62,7 @@ struct PlainEpilogue {
       }
     }
   }
+  __device__ __forceinline__ void extra(int) const {}  // never launched with extra CTAs
 };
 
 }  // namespace ipm

@@ -102,6 +102,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  {
+    // CTAs beyond the tile count belong to the epilogue functor (e.g. the Lasso tail rows that would otherwise
+    // cost a whole extra tile row); functors without such work never get launched with extra CTAs.
+    const int ntiles = upper ? tiles_n * (tiles_n + 1) / 2 : tiles_m * tiles_n;
+    if ((int)blockIdx.x >= ntiles) {
+      epi.extra((int)blockIdx.x - ntiles);
+      return;
+    }
+  }
   int ti, tj;
   decode_tile(blockIdx.x, tiles_m, tiles_n, upper != 0, ti, tj);
   const int m0 = ti * BM, n0 = tj * BN;

@@ -9,11 +9,20 @@
 // each output tile reads bA / u / alpha once, writes alpha+, u+ and z+ = u+ - alpha+ (into the OTHER z buffer:
 // other CTAs are still reading z), and, on stop-check iterations, leaves four partial sums of squares per warp
 // (|x - alpha+|^2, |rho (alpha+ - alpha)|^2, |alpha+|^2, |u+|^2) for the batch-coupled stop test (:273-298).
+//
+// Tail rows: n = 512 + 1 (bias) would cost a fifth tile row of which 1/128 is useful and a second wave on the
+// 148 SMs.  Rows beyond the last full 128-row tile (when there are at most 8 of them) are instead computed by a
+// few extra CTAs of the same launch as plain dot products (thread = column), so cfg-5 is ONE wave: 128 DMMA
+// tiles + 16 tail CTAs.
 #include "common.cuh"
 #include "gemm_tn_core.cuh"
 #include "tensormap.cuh"
 
 namespace ipm {
+
+constexpr int TAIL_MAX = 8;      // tail rows handled by the dot-product CTAs
+constexpr int TAIL_COLS = 256;   // columns per tail CTA
+constexpr int WARPS_PER_CTA = gemm::CONSUMER_WARPS + 1;
 
 struct LassoEpilogue {
   const double* bA;
@@ -21,56 +30,147 @@ struct LassoEpilogue {
   double* alpha;
   double* u;
   double* z_out;
+  const double* Qt;    // tail rows only
+  const double* z_in;  // tail rows only
   long long ld;        // common leading dimension of bA / alpha / u / z
-  int n, K;
+  long long ldq;
+  int n, K, n_main;    // rows [0, n_main) by DMMA tiles, [n_main, n) by tail CTAs
   double rho;
   int add_bias, positive, want_norms;
-  double* partials;    // [gridDim.x][8 warps][4]
+  double* partials;    // [gridDim.x][WARPS_PER_CTA][4]
+
+  struct Sums {
+    double r, d, a, u;
+  };
+
+  __device__ __forceinline__ void update(int row, int col, double xacc, double b, double uo, double ao, double& an,
+                                         double& un, Sums& s) const {
+    const double x = b + xacc;
+    const double v = x + uo;
+    const double et = eta[col];
+    an = fmax(v - et, 0.0);
+    if (!positive) an -= fmax(-v - et, 0.0);
+    if (add_bias && row == 0) an = v;
+    un = uo + x - an;
+    if (want_norms) {
+      const double r = x - an, dd = rho * (an - ao);
+      s.r = fma(r, r, s.r);
+      s.d = fma(dd, dd, s.d);
+      s.a = fma(an, an, s.a);
+      s.u = fma(un, un, s.u);
+    }
+  }
+
+  __device__ __forceinline__ void flush(Sums s) const {
+    if (!want_norms) return;
+    s.r = warp_sum(s.r);
+    s.d = warp_sum(s.d);
+    s.a = warp_sum(s.a);
+    s.u = warp_sum(s.u);
+    if ((threadIdx.x & 31) == 0) {
+      double* p = partials + ((long long)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5)) * 4;
+      p[0] = s.r; p[1] = s.d; p[2] = s.a; p[3] = s.u;
+    }
+  }
 
   __device__ __forceinline__ void tile(const double (&acc)[8][4][2], int m_base, int n_base, int g8, int l4) const {
-    double s_r = 0.0, s_d = 0.0, s_a = 0.0, s_u = 0.0;
+    Sums s{0.0, 0.0, 0.0, 0.0};
+    const bool interior = (m_base + 64 <= n_main) && (n_base + 32 <= K);
+    if (interior) {
+      // batched 16-byte loads: all inputs of two 8-row groups first, then the math, then the stores
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = m_base + i * 8 + g8;
+      for (int ib = 0; ib < 8; ib += 2) {
+        double2 vb[2][4], vu[2][4], va[2][4];
 #pragma unroll
-      for (int jn = 0; jn < 4; ++jn) {
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int col = n_base + jn * 8 + 2 * l4 + e;
-          if (row < n && col < K) {
+          for (int jn = 0; jn < 4; ++jn) {
+            const long long idx = (long long)(m_base + (ib + i) * 8 + g8) * ld + n_base + jn * 8 + 2 * l4;
+            vb[i][jn] = *reinterpret_cast<const double2*>(bA + idx);
+            vu[i][jn] = *reinterpret_cast<const double2*>(u + idx);
+            va[i][jn] = *reinterpret_cast<const double2*>(alpha + idx);
+          }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int jn = 0; jn < 4; ++jn) {
+            const int row = m_base + (ib + i) * 8 + g8, col = n_base + jn * 8 + 2 * l4;
             const long long idx = (long long)row * ld + col;
-            const double x = bA[idx] + acc[i][jn][e];
-            const double uo = u[idx], ao = alpha[idx];
-            const double v = x + uo;
-            const double et = eta[col];
-            double an = fmax(v - et, 0.0);
-            if (!positive) an -= fmax(-v - et, 0.0);
-            if (add_bias && row == 0) an = v;
-            const double un = uo + x - an;
-            alpha[idx] = an;
-            u[idx] = un;
-            z_out[idx] = un - an;
-            if (want_norms) {
-              const double r = x - an, dd = rho * (an - ao);
-              s_r = fma(r, r, s_r);
-              s_d = fma(dd, dd, s_d);
-              s_a = fma(an, an, s_a);
-              s_u = fma(un, un, s_u);
+            double2 an, un;
+            update(row, col, acc[ib + i][jn][0], vb[i][jn].x, vu[i][jn].x, va[i][jn].x, an.x, un.x, s);
+            update(row, col + 1, acc[ib + i][jn][1], vb[i][jn].y, vu[i][jn].y, va[i][jn].y, an.y, un.y, s);
+            *reinterpret_cast<double2*>(alpha + idx) = an;
+            *reinterpret_cast<double2*>(u + idx) = un;
+            *reinterpret_cast<double2*>(z_out + idx) = make_double2(un.x - an.x, un.y - an.y);
+          }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = m_base + i * 8 + g8;
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = n_base + jn * 8 + 2 * l4 + e;
+            if (row < n_main && col < K) {
+              const long long idx = (long long)row * ld + col;
+              double an, un;
+              update(row, col, acc[i][jn][e], bA[idx], u[idx], alpha[idx], an, un, s);
+              alpha[idx] = an;
+              u[idx] = un;
+              z_out[idx] = un - an;
             }
           }
         }
       }
     }
-    if (want_norms) {
-      s_r = warp_sum(s_r);
-      s_d = warp_sum(s_d);
-      s_a = warp_sum(s_a);
-      s_u = warp_sum(s_u);
-      if ((threadIdx.x & 31) == 0) {
-        double* p = partials + ((long long)blockIdx.x * gemm::CONSUMER_WARPS + (threadIdx.x >> 5)) * 4;
-        p[0] = s_r; p[1] = s_d; p[2] = s_a; p[3] = s_u;
+    flush(s);
+  }
+
+  // tail rows [n_main, n): x[r][c] = bA + sum_k Q~[k][r] z[k][c]   (thread = column, coalesced z reads)
+  __device__ __forceinline__ void extra(int bid) const {
+    Sums s{0.0, 0.0, 0.0, 0.0};
+    const int c = bid * TAIL_COLS + threadIdx.x;
+    const int nt = n - n_main;
+    if (threadIdx.x < TAIL_COLS && c < K) {
+      double acc[TAIL_MAX];
+#pragma unroll
+      for (int q = 0; q < TAIL_MAX; ++q) acc[q] = 0.0;
+      int k = 0;
+      for (; k + 15 < n; k += 16) {  // 16 independent loads in flight per thread
+        double zk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) zk[j] = z_in[(long long)(k + j) * ld + c];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const double* qrow = Qt + (long long)(k + j) * ldq + n_main;
+#pragma unroll
+          for (int q = 0; q < TAIL_MAX; ++q)
+            if (q < nt) acc[q] = fma(__ldg(qrow + q), zk[j], acc[q]);
+        }
+      }
+      for (; k < n; ++k) {
+        const double zk = z_in[(long long)k * ld + c];
+        const double* qrow = Qt + (long long)k * ldq + n_main;
+#pragma unroll
+        for (int q = 0; q < TAIL_MAX; ++q)
+          if (q < nt) acc[q] = fma(__ldg(qrow + q), zk, acc[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < TAIL_MAX; ++q) {
+        if (q < nt) {
+          const int row = n_main + q;
+          const long long idx = (long long)row * ld + c;
+          double an, un;
+          update(row, c, acc[q], bA[idx], u[idx], alpha[idx], an, un, s);
+          alpha[idx] = an;
+          u[idx] = un;
+          z_out[idx] = un - an;
+        }
       }
     }
+    flush(s);
   }
 };
 
@@ -96,16 +196,27 @@ lasso_objective_kernel(const double* __restrict__ R, long long ldr, int m, const
                        double* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= K) return;
-  double sq = 0.0, l1 = 0.0;
-  for (int r = 0; r < m; ++r) {
+  double sq0 = 0.0, sq1 = 0.0, sq2 = 0.0, sq3 = 0.0, l1 = 0.0;
+  int r = 0;
+  for (; r + 3 < m; r += 4) {
+    const double v0 = R[(long long)r * ldr + c], v1 = R[(long long)(r + 1) * ldr + c];
+    const double v2 = R[(long long)(r + 2) * ldr + c], v3 = R[(long long)(r + 3) * ldr + c];
+    sq0 = fma(v0, v0, sq0); sq1 = fma(v1, v1, sq1); sq2 = fma(v2, v2, sq2); sq3 = fma(v3, v3, sq3);
+  }
+  for (; r < m; ++r) {
     const double v = R[(long long)r * ldr + c];
-    sq = fma(v, v, sq);
+    sq0 = fma(v, v, sq0);
   }
   for (int j = add_bias ? 1 : 0; j < n; ++j) {
     const double a = alpha[(long long)j * lda + c];
     l1 += positive ? a : fabs(a);
   }
-  out[c] = sq / (2.0 * m) + reg[c] * l1;
+  out[c] = ((sq0 + sq1) + (sq2 + sq3)) / (2.0 * m) + reg[c] * l1;
+}
+
+static inline int lasso_n_main(int n) {
+  const int tail = n % gemm::BM;
+  return (n >= gemm::BM && tail > 0 && tail <= TAIL_MAX) ? n - tail : n;
 }
 
 }  // namespace ipm
@@ -113,7 +224,10 @@ lasso_objective_kernel(const double* __restrict__ R, long long ldr, int m, const
 using namespace ipm;
 
 extern "C" long long ipm_lasso_partials_doubles(int n, int K) {
-  return (long long)ceil_div(n, gemm::BM) * ceil_div(K, gemm::BN) * gemm::CONSUMER_WARPS * 4;
+  const int n_main = lasso_n_main(n);
+  const long long ctas = (long long)ceil_div(n_main, gemm::BM) * ceil_div(K, gemm::BN) +
+                         (n_main < n ? ceil_div(K, TAIL_COLS) : 0);
+  return ctas * WARPS_PER_CTA * 4;
 }
 
 // One ADMM iteration for all K problems.  Qt: n x n (ldq), z_in/z_out/bA/alpha/u: n x K (ld).  z_out != z_in.
@@ -123,28 +237,32 @@ extern "C" int ipm_lasso_admm_step_f64(const double* Qt, int ldq, int n, int K, 
                                        int ld, int add_bias, int positive, int want_norms, double* partials,
                                        double* norms_out, void* stream) {
   if (!Qt || !bA || !eta || !alpha || !u || !z_in || !z_out || z_in == z_out || n <= 0 || K <= 0 || ldq < n ||
-      ld < K || (want_norms && (!partials || !norms_out)))
+      ld < K || (ld & 1) || (want_norms && (!partials || !norms_out)))
     return IPM_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+  const int n_main = lasso_n_main(n);
   CUtensorMap tmA, tmB;
   int rc = make_operand_map(&tmA, Qt, ldq, n, n);  // Q~ symmetric: Q~[k][i] is the A operand (k rows, i columns)
   if (rc) return rc;
   rc = make_operand_map(&tmB, z_in, ld, n, K);
   if (rc) return rc;
-  const int tiles = ceil_div(n, gemm::BM) * ceil_div(K, gemm::BN);
-  LassoEpilogue epi{bA, eta, alpha, u, z_out, ld, n, K, rho, add_bias, positive, want_norms, partials};
+  const int tiles = ceil_div(n_main, gemm::BM) * ceil_div(K, gemm::BN);
+  const int tail_ctas = n_main < n ? ceil_div(K, TAIL_COLS) : 0;
+  LassoEpilogue epi{bA, eta, alpha, u, z_out, Qt, z_in, ld, ldq, n, K, n_main, rho, add_bias, positive, want_norms,
+                    partials};
   auto kern = gemm::gemm_tn_kernel<false, LassoEpilogue>;
   static bool attr_set = false;
   if (!attr_set) {
     IPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
     attr_set = true;
   }
-  if (want_norms)
-    IPM_CUDA_CHECK(cudaMemsetAsync(partials, 0, sizeof(double) * tiles * gemm::CONSUMER_WARPS * 4, st));
-  kern<<<tiles, gemm::THREADS, gemm::SMEM_BYTES, st>>>(tmA, tmB, n, K, n, nullptr, 0, epi);
+  const long long nparts = (long long)(tiles + tail_ctas) * WARPS_PER_CTA * 4;
+  if (want_norms) IPM_CUDA_CHECK(cudaMemsetAsync(partials, 0, sizeof(double) * nparts, st));
+  // M = n_main rows through the DMMA tiles (K of the contraction is still the full n)
+  kern<<<tiles + tail_ctas, gemm::THREADS, gemm::SMEM_BYTES, st>>>(tmA, tmB, n_main, K, n, nullptr, 0, epi);
   IPM_LAUNCH_CHECK();
   if (want_norms) {
-    lasso_norms_kernel<<<1, 256, 0, st>>>(partials, tiles * gemm::CONSUMER_WARPS, norms_out);
+    lasso_norms_kernel<<<1, 256, 0, st>>>(partials, (int)(nparts / 4), norms_out);
     IPM_LAUNCH_CHECK();
   }
   return IPM_OK;
