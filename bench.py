@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--cpu-newton-steps", type=int, default=2, help="full-size Newton steps in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--shard", default="instances", choices=["instances", "rows"],
+                    help="N > 1: independent LP instance per GPU (weak, no collective) or ONE LP row-sharded with an "
+                         "NCCL all-reduce of the partial Hessian (strong)")
     ap.add_argument("--lasso-k", type=int, default=4096, help="Lasso batch size (0 disables the Lasso section)")
     return ap.parse_args()
 
@@ -227,7 +230,8 @@ def main():
 
     from ipm_b200.LPSolver import LPSolver
 
-    prob, m = workload(args, rank)
+    rows_mode = world > 1 and args.shard == "rows"
+    prob, m = workload(args, 0 if rows_mode else rank)
     n = args.n
     host = {k: (torch.as_tensor(v).pin_memory().numpy() if isinstance(v, np.ndarray) else v) for k, v in prob.items()}
     x0 = prob["x0"].copy()
@@ -239,7 +243,7 @@ def main():
 
     # ------------------------------------------------------------------ resident-data arm
     solver = LPSolver(**{k: v for k, v in host.items() if k != "x0"}, x0=x0.copy(), check_cvxpy=False,
-                      suppress_print=True)
+                      suppress_print=True, shard_rows=rows_mode)
     x0_dev = solver.x_dev.clone()
 
     def one_solve():
@@ -250,7 +254,7 @@ def main():
     for _ in range(args.warmup):
         one_solve()
     L = solver.launcher
-    L.timed_ops = {"ipm_gemm_tn_f64": []}
+    L.timed_ops = {"ipm_gemm_tn_f64": [], "range:hessian_formation": []}
     launches0 = L.kernel_launches()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -264,8 +268,11 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = L.kernel_launches() - launches0
     hess = [a.elapsed_time(b) for a, b, tag in L.timed_ops["ipm_gemm_tn_f64"] if tag == "hessian"]
+    hform = [a.elapsed_time(b) for a, b, _ in L.timed_ops["range:hessian_formation"]]
+    comm_bytes = getattr(solver.ns, "comm_bytes", 0)
     L.timed_ops = None
     value_ref = solver.value
+    m_local = solver.data.m
 
     # ------------------------------------------------------------------ end-to-end arm (host buffers)
     e2e_ms, e2e_newton, h2d, d2h = None, 0, 0, 0
@@ -275,7 +282,7 @@ def main():
 
         def e2e_step():
             s = LPSolver(**{k: v for k, v in host.items() if k != "x0"}, x0=x0.copy(), check_cvxpy=False,
-                         suppress_print=True)
+                         suppress_print=True, shard_rows=rows_mode)
             s.solve()
             xs = s.xstar  # device -> host read of the result
             return sum(s.inner_iters), s.data.h2d_bytes + 8 * n, xs.nbytes + 8
@@ -313,7 +320,9 @@ def main():
         tsum = stats.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms, e2e_ms = float(tmax[0]), float(tmax[2])
-        newton, e2e_newton, launches = float(tsum[1]), float(tsum[3]), float(tsum[4])
+        launches = float(tsum[4])
+        if not rows_mode:  # independent instances: work adds up; one sharded problem: every rank counted the same steps
+            newton, e2e_newton = float(tsum[1]), float(tsum[3])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -321,16 +330,20 @@ def main():
 
     value = newton / (ms * 1e-3)
     hess_ms = float(np.mean(hess)) if hess else None
-    flops = float(m) * n * (n + 1)
+    flops = float(m_local) * n * (n + 1)  # rows resident on this rank (all m rows unless row-sharded)
     achieved = flops / (hess_ms * 1e-3) / 1e12 if hess_ms else None
     line = {
         "metric": "newton_steps_per_s", "value": value, "unit": "Newton steps/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if rows_mode else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"dense LP n={n} m={m} box+-3, warm start (BASELINE configs[1]); one step = one "
                                "LPSolver.solve()", "l2": "inputs (C = %.2f GB) larger than L2" % (8e-9 * m * n),
-                   "per_rank": "independent LP instance per GPU, no collective" if world > 1 else "single GPU"},
-        "time_to_solve_s": ms * 1e-3 / args.steps, "newton_steps_per_solve": newton / args.steps / world,
+                   "per_rank": ("ONE LP, inequality rows sharded over the GPUs, NCCL all-reduce of the partial Hessian"
+                                if rows_mode else "independent LP instance per GPU, no collective")
+                   if world > 1 else "single GPU"},
+        "time_to_solve_s": ms * 1e-3 / args.steps,
+        "newton_steps_per_solve": newton / args.steps / (1 if rows_mode else world),
         "objective": value_ref, "gpu_launches": int(launches), "clocks": clk.summary(),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
                      "frac": achieved / FP64_TENSOR_PEAK_TFLOPS if achieved else None,
@@ -340,6 +353,11 @@ def main():
                      "peak_source": "FP64 DMMA issue-rate microbenchmark on this pool (tools/fp64_peak.cu, "
                                     "profiles/fp64_peak_r01.json); MEASURED_PEAKS.json has no FP64 entry"},
     }
+    if rows_mode and hform:
+        line["hessian_formation"] = {"ms": float(np.mean(hform)), "what": "local partial C_r' diag(w) C_r + NCCL "
+                                     "all-reduce of the n x n buffer + diagonal terms, per Newton step (rank 0)",
+                                     "allreduce_bytes_per_newton_step": comm_bytes / max(newton + args.warmup *
+                                                                                        newton / args.steps, 1)}
     if e2e_ms:
         line["e2e"] = {"value": e2e_newton / (e2e_ms * 1e-3), "unit": "Newton steps/s", "h2d_bytes_per_step": int(h2d),
                        "d2h_bytes_per_step": int(d2h), "time_to_solve_s": e2e_ms * 1e-3 / args.steps}

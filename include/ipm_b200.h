@@ -135,6 +135,10 @@ int ipm_ls_armijo_f64(int nc, const double* s0, const double* p1, const double* 
                       const int* kmax, const double* sumlog, const double* terms, double t, double alpha,
                       int update_slacks_every, const double* L_direct, const double* nneg, int textbook, double* out,
                       void* stream);
+/* out[0] = sum log(s(table[*kmax]) + 1e-15) over this rank's slack entries (row-sharded problems all-reduce it and
+ * pass the result as L_direct). */
+int ipm_ls_logsum_f64(int nc, const double* s0, const double* p1, const double* p2, const double* table, int len,
+                      const int* kmax, double* out, void* stream);
 /* Residual-norm search of the infeasible-start method.  out[5] = {step, stuck, index, r0, r(step)}.
  * NewtonSolverInfeasibleStart.py:207-273. */
 int ipm_ls_residual_f64(int n, int p, const double* r0d, const double* u0, const double* u1, const double* q0,

@@ -4,17 +4,22 @@ method with Cholesky Newton steps (feasible start, or infeasible start when ``A`
 
 import numpy as np
 import torch
+import torch.distributed as tdist
 
 try:
     from . import _abi
     from ._solver_base import BarrierSolverBase, as_bound, check_bounds, check_pair, default_x0, HostArray
     from .engine import F64, Launcher, LinearNewton, LinearProblemData
     from .PhaseOneSolver import PhaseOneSolver
+    from .dist import row_range
+    from .sharded_engine import ShardedLinearNewton
 except ImportError:  # flat-module use
     import _abi
     from _solver_base import BarrierSolverBase, as_bound, check_bounds, check_pair, default_x0, HostArray
     from engine import F64, Launcher, LinearNewton, LinearProblemData
     from PhaseOneSolver import PhaseOneSolver
+    from dist import row_range
+    from sharded_engine import ShardedLinearNewton
 
 
 class LPSolver(BarrierSolverBase):
@@ -22,7 +27,7 @@ class LPSolver(BarrierSolverBase):
                  max_outer_iters=20, max_inner_iters=50, phase1_max_inner_iters=500, epsilon=1e-10,
                  inner_epsilon=1e-5, check_cvxpy=True, linear_solve_method="cholesky", max_cg_iters=50, alpha=0.2,
                  beta=0.6, mu=15, suppress_print=False, use_gpu=False, try_diag=True, track_loss=False,
-                 get_dual_variables=False, phase1_tol=0, phase1_t0=0.01, x0=None, update_slacks_every=0):
+                 get_dual_variables=False, phase1_tol=0, phase1_t0=0.01, x0=None, update_slacks_every=0, shard_rows=False):
         self.A, self.c, self.C, self.b, self.d = A, c, C, b, d
         if c is not None and c.ndim != 1:
             raise ValueError("c must be 1-dimensional!")
@@ -56,18 +61,32 @@ class LPSolver(BarrierSolverBase):
         self._eq_tol = 1e-4 * self.n  # LPSolver.py:600-602
         # host -> device (LPSolver.py:160-176): the only bulk transfer of a solve
         self.launcher = Launcher(self.device)
-        self.data = LinearProblemData(self.n, self.device, c=c, C=C, d=d, lb=self.lb, ub=self.ub, A=A, b=b)
+        # optional extension (not in the reference): shard the inequality rows of ONE problem over the ranks of an
+        # initialised torch.distributed group (partial Hessian + NCCL all-reduce, see sharded_engine.py)
+        C_loc, d_loc, lb_loc, ub_loc, newton_cls = C, d, self.lb, self.ub, LinearNewton
+        self.sharded = bool(shard_rows) and tdist.is_available() and tdist.is_initialized() and \
+            tdist.get_world_size() > 1
+        if self.sharded:
+            if C is None or A is not None:
+                raise NotImplementedError("shard_rows needs inequality rows and no equality constraints")
+            lo, hi = row_range(C.shape[0], tdist.get_rank(), tdist.get_world_size())
+            C_loc, d_loc = C[lo:hi], d[lo:hi]
+            if tdist.get_rank() != 0:
+                lb_loc = ub_loc = None  # bound rows belong to rank 0
+            newton_cls = ShardedLinearNewton
+        self.data = LinearProblemData(self.n, self.device, c=c, C=C_loc, d=d_loc, lb=lb_loc, ub=ub_loc, A=A, b=b)
         self.x_dev = torch.as_tensor(self.x).to(device=self.device, dtype=F64).clone()
         if C is not None:
             self.phase1_solver = PhaseOneSolver(
                 C=C, d=d, lower_bound=self.lb, upper_bound=self.ub, x0=self.x, max_outer_iters=max_outer_iters,
                 max_inner_iters=phase1_max_inner_iters, epsilon=epsilon, inner_epsilon=inner_epsilon, alpha=alpha,
                 beta=beta, mu=mu, suppress_print=suppress_print, n=self.n, tol=phase1_tol, t0=phase1_t0,
-                update_slacks_every=update_slacks_every, _data=self.data, _launcher=self.launcher)
+                update_slacks_every=update_slacks_every, _data=self.data, _launcher=self.launcher,
+                _newton_cls=newton_cls)
         diagonal = C is None and try_diag  # LPSolver.py:436-446
         if diagonal and not self.bounded:
             raise ValueError("LP without inequality constraints or bounds has no barrier Hessian")
-        self.ns = LinearNewton(self.data, phase1=False, max_iters=max_inner_iters, epsilon=inner_epsilon, alpha=alpha,
+        self.ns = newton_cls(self.data, phase1=False, max_iters=max_inner_iters, epsilon=inner_epsilon, alpha=alpha,
                                beta=beta, update_slacks_every=update_slacks_every, diagonal=diagonal,
                                launcher=self.launcher)
 

@@ -26,7 +26,7 @@ class PhaseOneSolver:
                  max_inner_iters=20, epsilon=1e-8, inner_epsilon=1e-5, linear_solve_method="cholesky",
                  max_cg_iters=50, alpha=0.2, beta=0.6, mu=15, t0=1, suppress_print=False, use_gpu=False,
                  track_loss=False, n=None, tol=0.1, socp=False, socp_params=None, use_psd_condition=False,
-                 update_slacks_every=0, _data=None, _launcher=None):
+                 update_slacks_every=0, _data=None, _launcher=None, _newton_cls=None):
         _abi.require_device()
         self.C, self.d, self.lb, self.ub = C, d, lower_bound, upper_bound
         self.n = n if n is not None else len(x0)
@@ -51,7 +51,7 @@ class PhaseOneSolver:
         else:
             data = _data if _data is not None else LinearProblemData(self.n, device, C=C, d=d, lb=lower_bound,
                                                                      ub=upper_bound)
-            self.ns = LinearNewton(data, phase1=True, max_iters=max_inner_iters, epsilon=inner_epsilon, alpha=alpha,
+            self.ns = (_newton_cls or LinearNewton)(data, phase1=True, max_iters=max_inner_iters, epsilon=inner_epsilon, alpha=alpha,
                                    beta=beta, phase1_tol=tol, use_psd_condition=use_psd_condition,
                                    update_slacks_every=update_slacks_every, launcher=_launcher)
         self.data = data

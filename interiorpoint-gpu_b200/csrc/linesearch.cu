@@ -309,6 +309,31 @@ extern "C" int ipm_lincomb3_f64(int n, double ca, const double* a, double cb, co
   return IPM_OK;
 }
 
+// out[0] = sum_i log(s0_i + a*p1_i + a^2*p2_i + 1e-15) at a = table[min(*kmax, len-1)] over this rank's entries
+// (row-sharded problems: the partial sums are all-reduced and handed to ipm_ls_armijo_f64 as L_direct).
+__global__ void __launch_bounds__(1024, 1)
+ls_logsum_kernel(int nc, const double* __restrict__ s0, const double* __restrict__ p1,
+                 const double* __restrict__ p2, const double* __restrict__ table, int len,
+                 const int* __restrict__ kmax_ptr, double* __restrict__ out) {
+  __shared__ double red[32];
+  int k = *kmax_ptr;
+  if (k > len - 1) k = len - 1;
+  const double a = table[k];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < nc; i += blockDim.x)
+    acc += log(trial_slack(s0[i], p1[i], p2 ? p2[i] : 0.0, a) + LOG_GUARD);
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) out[0] = acc;
+}
+
+extern "C" int ipm_ls_logsum_f64(int nc, const double* s0, const double* p1, const double* p2, const double* table,
+                                 int len, const int* kmax, double* out, void* stream) {
+  if (nc < 0 || !table || len < 2 || !kmax || !out || (nc > 0 && (!s0 || !p1))) return IPM_ERR_ARG;
+  ls_logsum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nc, s0, p1, p2, table, len, kmax, out);
+  IPM_LAUNCH_CHECK();
+  return IPM_OK;
+}
+
 // out[0] = table[min(*kmax, len - 1)]  (step chosen by the feasibility back-off, kept on the device)
 __global__ void table_lookup_kernel(const double* __restrict__ table, int len, const int* __restrict__ kmax,
                                     double* __restrict__ out) {

@@ -58,6 +58,27 @@ class Launcher:
         """Kernels launched by libipm_b200 since this launcher was created (process-wide counter)."""
         return int(_abi.lib().ipm_launch_count() - self._base)
 
+    def timed_range(self, tag):
+        """Context manager: CUDA events around a group of launches/collectives (only while bench.py profiles)."""
+        launcher = self
+
+        class _R:
+            def __enter__(self_r):
+                self_r.rec = launcher.timed_ops.get("range:" + tag) if launcher.timed_ops is not None else None
+                if self_r.rec is not None:
+                    self_r.e0 = torch.cuda.Event(enable_timing=True)
+                    self_r.e0.record()
+                return self_r
+
+            def __exit__(self_r, *exc):
+                if self_r.rec is not None:
+                    e1 = torch.cuda.Event(enable_timing=True)
+                    e1.record()
+                    self_r.rec.append((self_r.e0, e1, tag))
+                return False
+
+        return _R()
+
     def __call__(self, name, *args):
         self.calls += 1
         rec = self.timed_ops.get(name) if self.timed_ops is not None else None
