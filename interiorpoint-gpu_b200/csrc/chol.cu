@@ -219,7 +219,11 @@ static int get_side_stream(SideStream** out) {
   if (dev < 0 || dev >= 16) return IPM_ERR_ARG;
   SideStream* s = &g_side[dev];
   if (!s->ready) {
-    IPM_CUDA_CHECK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    // highest priority: the single-CTA panel chain must get the next free SM while the bulk trailing update of
+    // the previous block still has CTAs queued on the caller's stream
+    int prio_lo = 0, prio_hi = 0;
+    IPM_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    IPM_CUDA_CHECK(cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, prio_hi));
     IPM_CUDA_CHECK(cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming));
     IPM_CUDA_CHECK(cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming));
     IPM_CUDA_CHECK(cudaEventCreateWithFlags(&s->chain, cudaEventDisableTiming));
@@ -338,181 +342,5 @@ extern "C" int ipm_trsm_upper_t_f64(const double* U, int ldu, int n, double* B, 
       if (rc) return rc;
     }
   }
-  return IPM_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Vector triangular solves (HBM-bound: U is read once).  Right-looking in 128-wide strips, ONE kernel per
-// strip: every CTA re-solves the 128x128 diagonal block in shared memory (4 warp-level 32x32 substitutions
-// with shuffles -- cheaper than a second launch plus a grid-wide dependency), CTA 0 publishes the strip's
-// solution, and each CTA applies the strip to its slice of the remaining right-hand side.
-//   trans = 1:  solve U^T y = b  (top -> bottom)      trans = 0:  solve U x = b  (bottom -> top)
-// `work` is the right-hand side (updated in place), `out` receives the solution (must not alias work).
-// ------------------------------------------------------------------------------------------------
-constexpr int TS_LD = NB + 1;
-
-__device__ __forceinline__ void trsv_block_solve(double* __restrict__ S, double* __restrict__ xs, int nb, int trans) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nsb = (nb + 31) >> 5;
-  for (int s = 0; s < nsb; ++s) {
-    const int sb = trans ? s : nsb - 1 - s;
-    const int base = sb * 32;
-    const int bl = min(32, nb - base);
-    if (warp == 0) {
-      const bool act = lane < bl;
-      double v = act ? xs[base + lane] : 0.0;
-      // reciprocal of the pivot once per lane: keeps the division off the 32-step dependent chain
-      const double rdg = act ? 1.0 / S[(base + lane) * TS_LD + base + lane] : 1.0;
-      if (trans) {
-        for (int l = 0; l < bl; ++l) {
-          const double yl = __shfl_sync(0xffffffffu, v * rdg, l);
-          if (lane == l) v = yl;
-          else if (lane > l && act) v = fma(-S[(base + l) * TS_LD + base + lane], yl, v);
-        }
-      } else {
-        for (int l = bl - 1; l >= 0; --l) {
-          const double xl = __shfl_sync(0xffffffffu, v * rdg, l);
-          if (lane == l) v = xl;
-          else if (lane < l) v = fma(-S[(base + lane) * TS_LD + base + l], xl, v);
-        }
-      }
-      if (act) xs[base + lane] = v;
-    }
-    __syncthreads();
-    // apply the solved sub-block to the entries of this 128-block still to be solved
-    if (trans) {
-      const int cidx = tid;
-      if (cidx >= base + bl && cidx < nb) {
-        double a0 = 0.0, a1 = 0.0;
-        for (int l = 0; l + 1 < bl; l += 2) {
-          a0 = fma(S[(base + l) * TS_LD + cidx], xs[base + l], a0);
-          a1 = fma(S[(base + l + 1) * TS_LD + cidx], xs[base + l + 1], a1);
-        }
-        if (bl & 1) a0 = fma(S[(base + bl - 1) * TS_LD + cidx], xs[base + bl - 1], a0);
-        xs[cidx] -= a0 + a1;
-      }
-    } else {
-      const int ridx = tid;
-      if (ridx < base) {
-        double a0 = 0.0, a1 = 0.0;
-        for (int l = 0; l + 1 < bl; l += 2) {
-          a0 = fma(S[ridx * TS_LD + base + l], xs[base + l], a0);
-          a1 = fma(S[ridx * TS_LD + base + l + 1], xs[base + l + 1], a1);
-        }
-        if (bl & 1) a0 = fma(S[ridx * TS_LD + base + bl - 1], xs[base + bl - 1], a0);
-        xs[ridx] -= a0 + a1;
-      }
-    }
-    __syncthreads();
-  }
-}
-
-__global__ void __launch_bounds__(128, 1)
-trsv_strip_kernel(const double* __restrict__ U, long long ld, int n, int k0, int nb, double* __restrict__ work,
-                  double* __restrict__ out, int trans) {
-  extern __shared__ double S[];  // NB x TS_LD
-  __shared__ double xs[NB];
-  __shared__ double part[4][64];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const double* Ukk = U + (long long)k0 * ld + k0;
-  const bool vec = (nb == NB) && !(ld & 1) && !(((uintptr_t)Ukk) & 15);
-  if (vec) {
-#pragma unroll 16
-    for (int q = 0; q < 64; ++q) {
-      const int idx = tid + 128 * q;  // double2 index
-      const int r = idx >> 6, c = (idx & 63) * 2;
-      if (c + 1 >= r) {
-        const double2 v = *reinterpret_cast<const double2*>(Ukk + (long long)r * ld + c);
-        S[r * TS_LD + c] = v.x;
-        S[r * TS_LD + c + 1] = v.y;
-      }
-    }
-  } else {
-    for (int idx = tid; idx < nb * NB; idx += 128) {
-      const int r = idx >> 7, c = idx & 127;
-      if (c < nb && c >= r) S[r * TS_LD + c] = Ukk[(long long)r * ld + c];
-    }
-  }
-  if (tid < nb) xs[tid] = work[k0 + tid];
-  __syncthreads();
-  trsv_block_solve(S, xs, nb, trans);
-  if (blockIdx.x == 0 && tid < nb) out[k0 + tid] = xs[tid];
-  if (trans) {
-    // work[j] -= sum_i U[k0+i][j] * y_i   for this CTA's 64 columns j > k0+nb-1; warps split the 128 rows
-    const int rest = n - k0 - nb;
-    const int j0 = blockIdx.x * 64;
-    if (j0 >= rest) return;
-    const double* Us = Ukk + nb + j0;
-    const int j = 2 * lane;
-    double a0 = 0.0, a1 = 0.0;
-    const bool pair = j0 + j + 1 < rest, one = j0 + j < rest;
-    const bool v2 = pair && !(ld & 1) && !(((uintptr_t)Us) & 15);
-    const int i0 = warp * 32, i1 = min(nb, i0 + 32);
-    if (v2) {
-#pragma unroll 16
-      for (int i = i0; i < i1; ++i) {
-        const double2 m = *reinterpret_cast<const double2*>(Us + (long long)i * ld + j);
-        a0 = fma(m.x, xs[i], a0);
-        a1 = fma(m.y, xs[i], a1);
-      }
-    } else if (one) {
-      for (int i = i0; i < i1; ++i) {
-        a0 = fma(Us[(long long)i * ld + j], xs[i], a0);
-        if (pair) a1 = fma(Us[(long long)i * ld + j + 1], xs[i], a1);
-      }
-    }
-    part[warp][j] = a0;
-    part[warp][j + 1] = a1;
-    __syncthreads();
-    if (tid < 64 && j0 + tid < rest)
-      work[k0 + nb + j0 + tid] -= (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
-  } else {
-    // work[i] -= sum_j U[i][k0+j] * x_j   for this CTA's 64 rows i < k0; one warp per row, 16 rows per warp
-    const int r0 = blockIdx.x * 64;
-    if (r0 >= k0) return;
-    const bool v2 = (nb == NB) && !(ld & 1) && !(((uintptr_t)(U + k0)) & 15);
-    for (int rr = warp; rr < 64; rr += 4) {
-      const int i = r0 + rr;
-      if (i >= k0) break;
-      const double* row = U + (long long)i * ld + k0;
-      double a = 0.0;
-      if (v2) {
-        const double2 m0 = *reinterpret_cast<const double2*>(row + 2 * lane);
-        const double2 m1 = *reinterpret_cast<const double2*>(row + 64 + 2 * lane);
-        a = fma(m0.x, xs[2 * lane], a);
-        a = fma(m0.y, xs[2 * lane + 1], a);
-        a = fma(m1.x, xs[64 + 2 * lane], a);
-        a = fma(m1.y, xs[64 + 2 * lane + 1], a);
-      } else {
-        for (int jj = lane; jj < nb; jj += 32) a = fma(row[jj], xs[jj], a);
-      }
-      a = warp_sum(a);
-      if (lane == 0) work[i] -= a;
-    }
-  }
-}
-
-// b is overwritten with the solution; ws holds n doubles of scratch.
-extern "C" int ipm_trsv_upper_f64(const double* U, int ld, int n, double* b, int trans, double* ws, void* stream) {
-  if (!U || !b || !ws || n < 0 || ld < n) return IPM_ERR_ARG;
-  if (n == 0) return IPM_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int smem = NB * TS_LD * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
-    IPM_CUDA_CHECK(cudaFuncSetAttribute(trsv_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
-  const int nblk = ceil_div(n, NB);
-  for (int s = 0; s < nblk; ++s) {
-    const int kb = trans ? s : nblk - 1 - s;
-    const int k0 = kb * NB;
-    const int nb = n - k0 < NB ? n - k0 : NB;
-    const int todo = trans ? n - k0 - nb : k0;
-    const int grid = todo > 0 ? ceil_div(todo, 64) : 1;
-    trsv_strip_kernel<<<grid, 128, smem, st>>>(U, ld, n, k0, nb, b, ws, trans);
-    IPM_LAUNCH_CHECK();
-  }
-  IPM_CUDA_CHECK(cudaMemcpyAsync(b, ws, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
   return IPM_OK;
 }

@@ -131,6 +131,51 @@ def test_potrf_trsv(n):
     assert res.max() < 1e-12
 
 
+@pytest.mark.parametrize("n,odd_ld", [(1, False), (37, False), (128, False), (200, True), (777, False), (2500, False),
+                                      (1031, True)])
+def test_trsv_both_directions(n, odd_ld):
+    """Persistent left-looking trsv (csrc/trsv.cu) against scipy.linalg.solve_triangular, both directions, ragged
+    sizes, and the scalar-load path (odd leading dimension)."""
+    from scipy.linalg import solve_triangular
+
+    rs = np.random.RandomState(n)
+    U = np.triu(rs.uniform(-1, 1, (n, n))) / np.sqrt(n) + np.diag(rs.uniform(0.5, 2.0, n))
+    b = rs.randn(n)
+    if odd_ld:
+        ld = n + 1 if (n + 1) % 2 else n + 2
+        Ud = torch.full((n, ld), float("nan"), dtype=torch.float64, device="cuda")
+        Ud[:, :n] = torch.as_tensor(U, device="cuda")
+    else:
+        Ud, ld = padded(U)
+    for trans in (1, 0):
+        bd = dev(b)
+        _abi.call("ipm_trsv_upper_f64", Ud.data_ptr(), ld, n, bd.data_ptr(), trans, None, None)
+        torch.cuda.synchronize()
+        x = bd.cpu().numpy()
+        ref = solve_triangular(U, b, trans=trans, lower=False)
+        M = U.T if trans else U
+        res = np.abs(M @ x - b) / (np.abs(M) @ np.abs(x) + np.abs(b))
+        assert res.max() < 1e-13
+        np.testing.assert_allclose(x, ref, rtol=1e-9, atol=1e-12)
+
+
+def test_trsv_more_blocks_than_sms():
+    """n / 128 > #SMs: every CTA owns several solution blocks (ascending order keeps the flag chain deadlock-free)."""
+    n = 148 * 128 + 333
+    g = torch.Generator(device="cuda").manual_seed(1)
+    U = torch.rand((n, n), dtype=torch.float64, device="cuda", generator=g)
+    U.mul_(2.0).sub_(1.0).div_(float(np.sqrt(n))).triu_()
+    U.diagonal().copy_(torch.rand(n, dtype=torch.float64, device="cuda", generator=g) + 0.5)
+    b = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    for trans in (1, 0):
+        x = b.clone()
+        _abi.call("ipm_trsv_upper_f64", U.data_ptr(), n, n, x.data_ptr(), trans, None, None)
+        torch.cuda.synchronize()
+        M = U.T if trans else U
+        res = (M @ x - b).abs() / (M.abs() @ x.abs() + b.abs())
+        assert float(res.max()) < 1e-13
+
+
 def test_potrf_reports_first_bad_pivot():
     n = 200
     H = spd(n, 3, cond_pow=1)
