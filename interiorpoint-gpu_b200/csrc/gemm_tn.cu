@@ -1,4 +1,7 @@
 // ipm_gemm_tn_f64: D = beta*D + alpha * A^T diag(w) B   (FP64, TMA + DMMA, see gemm_tn_core.cuh)
+#include <atomic>
+#include <mutex>
+
 #include "common.cuh"
 #include "gemm_tn_core.cuh"
 #include "tensormap.cuh"
@@ -69,6 +72,46 @@ struct PlainEpilogue {
 
 using namespace ipm;
 
+// Stream-K scratch of the persistent kernel: library-owned, one slot per (device, stream) that ever launched a
+// long-K contraction (allocated once, never per call).  Calls on one stream serialise, so a slot is never shared
+// by two kernels in flight.
+namespace {
+constexpr int kMaxDev = 16, kSlotsPerDev = 4;
+struct SkSlot {
+  cudaStream_t stream;
+  double* partials;
+  unsigned int* flags;
+  bool used;
+};
+SkSlot g_sk[kMaxDev][kSlotsPerDev];
+int g_num_sms[kMaxDev];
+std::atomic<unsigned> g_sk_epoch{0};
+std::mutex g_sk_mutex;
+
+// returns nullptr when every slot of the device belongs to another stream (caller falls back to one CTA per tile)
+SkSlot* get_sk_slot(int dev, cudaStream_t st, int* rc) {
+  std::lock_guard<std::mutex> lock(g_sk_mutex);
+  *rc = IPM_OK;
+  for (int i = 0; i < kSlotsPerDev; ++i)
+    if (g_sk[dev][i].used && g_sk[dev][i].stream == st) return &g_sk[dev][i];
+  for (int i = 0; i < kSlotsPerDev; ++i) {
+    SkSlot* s = &g_sk[dev][i];
+    if (s->used) continue;
+    const size_t slots = (size_t)g_num_sms[dev];
+    if (cudaMalloc(&s->partials, slots * gemm::BM * gemm::BN * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&s->flags, slots * sizeof(unsigned)) != cudaSuccess ||
+        cudaMemset(s->flags, 0, slots * sizeof(unsigned)) != cudaSuccess) {
+      *rc = ipm_set_cuda_error(cudaGetLastError());
+      return nullptr;
+    }
+    s->stream = st;
+    s->used = true;
+    return s;
+  }
+  return nullptr;
+}
+}  // namespace
+
 extern "C" int ipm_gemm_tn_f64(const double* A, int lda, const double* B, int ldb, const double* w, double alpha,
                                double beta, double* D, int ldd, int M, int N, int K, int upper, void* stream) {
   if (!A || !B || !D || M <= 0 || N <= 0 || K < 0 || lda < M || ldb < N || ldd < N) return IPM_ERR_ARG;
@@ -83,7 +126,41 @@ extern "C" int ipm_gemm_tn_f64(const double* A, int lda, const double* B, int ld
   const int tm = ceil_div(M, gemm::BM), tn = ceil_div(N, gemm::BN);
   const int tri_tiles = upper == 1;  // upper == 2: all tiles, but still store only col >= row
   const int tiles = tri_tiles ? tn * (tn + 1) / 2 : tm * tn;
+  const int ktiles = ceil_div(K, gemm::BK);
   PlainEpilogue epi{D, ldd, M, N, alpha, beta, upper};
+
+  // Long-K contraction with more tiles than SMs: persistent CTAs + stream-K remainder (no partial last wave).
+  int dev = 0;
+  IPM_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < kMaxDev && !g_num_sms[dev])
+    IPM_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev));
+  const int G = (dev >= 0 && dev < kMaxDev) ? g_num_sms[dev] : 0;
+  if (G > 0 && ktiles >= 64 && tiles > G) {
+    SkSlot* slot = get_sk_slot(dev, st, &rc);
+    if (rc) return rc;
+    if (slot) {
+      const int rem = tiles % G;
+      const long long U = (long long)rem * ktiles;
+      long long P = U / 8;  // at least 8 k-tiles (K = 128) per stream-K slice
+      if (P < rem) P = rem;
+      if (P > G) P = G;
+      if (P < 1) P = 1;
+      unsigned epoch = ++g_sk_epoch;
+      if (epoch == 0) epoch = ++g_sk_epoch;
+      gemm::StreamK sk{slot->partials, slot->flags, epoch, (int)P};
+      if (w) {
+        auto kern = gemm::gemm_tn_persistent_kernel<true, PlainEpilogue>;
+        IPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
+        kern<<<G, gemm::THREADS, gemm::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, w, tri_tiles, epi, sk);
+      } else {
+        auto kern = gemm::gemm_tn_persistent_kernel<false, PlainEpilogue>;
+        IPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
+        kern<<<G, gemm::THREADS, gemm::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, nullptr, tri_tiles, epi, sk);
+      }
+      IPM_LAUNCH_CHECK();
+      return IPM_OK;
+    }
+  }
   if (w) {
     auto kern = gemm::gemm_tn_kernel<true, PlainEpilogue>;
     IPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));

@@ -9,8 +9,11 @@
 //
 // Blackwell mapping: tcgen05.mma has no FP64 kind, so the math is DMMA (mma.sync.m8n8k4.f64, the only
 // FP64 tensor shape sm_100a issues natively -- m16n8k{4,8,16} lower to it); operand tiles are staged by
-// TMA (cp.async.bulk.tensor.2d, 128B swizzle) into a 4-stage mbarrier ring by one producer warp and
-// consumed by 8 MMA warps (warp tile 64x32, 64 FP64 accumulators per thread).
+// TMA (cp.async.bulk.tensor.2d, 128B swizzle) into a 6-stage mbarrier ring and consumed by 8 MMA warps (warp
+// tile 64x32, 64 FP64 accumulators per thread).  There is no dedicated producer warp: a ninth warp would put
+// three warps on one SM sub-partition and cap every thread at 168 registers (16K registers per sub-partition),
+// which spills the double-buffered fragments.  Instead lane 0 of warp 0 keeps the ring PREFETCH k-tiles ahead
+// of its own consumption (one expect_tx + 16 TMA issues per k-tile, hidden behind the 128 DMMAs of that tile).
 //
 // Shared-memory tile layout (per operand, per stage): 8 column chunks of [16 k-rows][16 doubles = 128 B],
 // each written by one TMA box with CU_TENSOR_MAP_SWIZZLE_128B: 16-byte unit c of row r lands at unit
@@ -25,9 +28,10 @@
 namespace ipm {
 namespace gemm {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4;
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 6;
+constexpr int PREFETCH = STAGES - 2;  // k-tiles in flight ahead of warp 0's consumption
 constexpr int CONSUMER_WARPS = 8;
-constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+constexpr int THREADS = CONSUMER_WARPS * 32;
 constexpr int CHUNK_BYTES = BK * 128;               // one TMA box: 16 rows x 128 B
 constexpr int OPERAND_BYTES = (BM / 16) * CHUNK_BYTES;  // 16 KiB
 constexpr int STAGE_BYTES = 2 * OPERAND_BYTES;      // A + B
@@ -88,18 +92,196 @@ __device__ __forceinline__ void decode_tile(int lin, int tiles_m, int tiles_n, b
   tj = t + (lin - (t * T - t * (t - 1) / 2));
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Pipeline pieces.  `it` counts the k-tiles that went through the CTA's ring (stage = it % STAGES, phase parity
+// = (it / STAGES) & 1); the producer cursor and the consumers advance it identically, so the ring keeps
+// streaming across tile boundaries in the persistent kernel.
+// ---------------------------------------------------------------------------------------------------------
+struct Ring {
+  uint32_t full0, empty0, tiles0;
+};
+
+__device__ __forceinline__ Ring setup_ring(uint8_t* smem_raw) {
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  Ring ring{smem_u32(bars), smem_u32(bars + STAGES), smem_u32(smem)};
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(ring.full0 + 8 * s, 1);
+      mbar_init(ring.empty0 + 8 * s, CONSUMER_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  return ring;
+}
+
+// Work of one CTA = a short list of segments (output tile, k-tile range).  Schedule concept:
+//   int count() const;   void segment(int sg, int& m0, int& n0, int& k0, int& k1) const;   (k1 > k0)
+//
+// Producer cursor (warp 0; every lane tracks it, lane 0 issues): walks the segment list one k-tile per call.
+template <class Schedule>
+struct Producer {
+  const Schedule& sch;
+  const CUtensorMap *tmA, *tmB;
+  Ring ring;
+  int sg, kt, k1, m0, n0;
+  uint32_t it;
+
+  __device__ __forceinline__ Producer(const Schedule& s, const CUtensorMap* a, const CUtensorMap* b, const Ring& r)
+      : sch(s), tmA(a), tmB(b), ring(r), sg(-1), kt(0), k1(0), m0(0), n0(0), it(0) {
+    next_segment();
+  }
+  __device__ __forceinline__ void next_segment() {
+    ++sg;
+    if (sg < sch.count()) sch.segment(sg, m0, n0, kt, k1);
+  }
+  __device__ __forceinline__ void issue(int lane) {
+    if (sg >= sch.count()) return;
+    if (lane == 0) {
+      const uint32_t s = it % STAGES;
+      if (it >= STAGES) mbar_wait(ring.empty0 + 8 * s, ((it / STAGES) - 1) & 1);
+      const uint32_t full = ring.full0 + 8 * s;
+      mbar_expect_tx(full, STAGE_BYTES);
+      const uint32_t dstA = ring.tiles0 + s * STAGE_BYTES, dstB = dstA + OPERAND_BYTES;
+#pragma unroll
+      for (int c = 0; c < BM / 16; ++c) tma_load_2d(dstA + c * CHUNK_BYTES, tmA, m0 + c * 16, kt * BK, full);
+#pragma unroll
+      for (int c = 0; c < BN / 16; ++c) tma_load_2d(dstB + c * CHUNK_BYTES, tmB, n0 + c * 16, kt * BK, full);
+    }
+    __syncwarp();
+    ++it;
+    if (++kt >= k1) next_segment();
+  }
+};
+
+// Per-lane constants of a consumer warp (warp grid 2 (m) x 4 (n), warp tile 64 x 32).
+struct LaneMap {
+  uint32_t off[2][2];  // byte offset inside a [16 x 128B] chunk for even/odd column block and row parity
+  uint32_t a_warp, b_warp;
+  int l4, g8;
+};
+
+__device__ __forceinline__ LaneMap make_lane_map(int warp, int lane) {
+  LaneMap lm;
+  lm.l4 = lane & 3;
+  lm.g8 = lane >> 2;
+  const int wm = warp >> 2, wn = warp & 3;
+  // unit16 = ((blk & 1) * 4 + (g8 >> 1)) ^ (2 * l4 + jb)
+#pragma unroll
+  for (int e = 0; e < 2; ++e)
+#pragma unroll
+    for (int jb = 0; jb < 2; ++jb)
+      lm.off[e][jb] = (uint32_t)(((((e * 4) + (lm.g8 >> 1)) ^ (2 * lm.l4 + jb)) << 4) + (lm.g8 & 1) * 8);
+  lm.a_warp = (uint32_t)(wm * 4) * CHUNK_BYTES;                  // 64 cols = 4 chunks
+  lm.b_warp = OPERAND_BYTES + (uint32_t)(wn * 2) * CHUNK_BYTES;  // 32 cols = 2 chunks
+  return lm;
+}
+
+// Fragments of k-group j (4 k-rows) of the stage at shared address st.
+__device__ __forceinline__ void load_frags(double (&a)[8], double (&b)[4], uint32_t st, const LaneMap& lm, int j) {
+  const uint32_t rowoff = (uint32_t)((j >> 1) * 8 + 2 * lm.l4 + (j & 1)) * 128u;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t addr = st + lm.a_warp + (uint32_t)(i >> 1) * CHUNK_BYTES + rowoff + lm.off[i & 1][j & 1];
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[i]) : "r"(addr));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t addr = st + lm.b_warp + (uint32_t)(i >> 1) * CHUNK_BYTES + rowoff + lm.off[i & 1][j & 1];
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b[i]) : "r"(addr));
+  }
+}
+
+__device__ __forceinline__ void load_weights(double (&wk)[4], const double* __restrict__ w, int kt, int K, int l4) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int kk = kt * BK + (j >> 1) * 8 + 2 * l4 + (j & 1);
+    wk[j] = kk < K ? __ldg(w + kk) : 0.0;
+  }
+}
+
+// acc += sum over k-tiles [kt_begin, kt_end).  Software pipelined: the fragments of k-group j+1 (and the row
+// weights of the next k-tile) are in flight while the 32 DMMAs of group j issue; warp 0 tops the TMA ring up by
+// one k-tile per consumed k-tile.
+template <bool HAS_W, class Schedule>
+__device__ __forceinline__ void consume_ktiles(double (&acc)[8][4][2], const Ring& ring, const LaneMap& lm,
+                                               const double* __restrict__ w, int K, int kt_begin, int kt_end,
+                                               uint32_t& it, int warp, int lane, Producer<Schedule>& prod) {
+  double wk[4], wn[4];
+  if (HAS_W) load_weights(wk, w, kt_begin, K, lm.l4);
+  uint32_t s = it % STAGES;
+  mbar_wait(ring.full0 + 8 * s, (it / STAGES) & 1);
+  uint32_t st = ring.tiles0 + s * STAGE_BYTES;
+  double a[2][8], b[2][4];
+  load_frags(a[0], b[0], st, lm, 0);
+  for (int kt = kt_begin; kt < kt_end; ++kt) {
+    const bool has_next = kt + 1 < kt_end;
+    if (HAS_W && has_next) load_weights(wn, w, kt + 1, K, lm.l4);
+    if (warp == 0) prod.issue(lane);
+    uint32_t s_next = s, st_next = st;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cur = j & 1, nxt = cur ^ 1;
+      if (j < 3) {
+        load_frags(a[nxt], b[nxt], st, lm, j + 1);
+      } else if (has_next) {
+        s_next = (it + 1) % STAGES;
+        mbar_wait(ring.full0 + 8 * s_next, ((it + 1) / STAGES) & 1);
+        st_next = ring.tiles0 + s_next * STAGE_BYTES;
+        load_frags(a[nxt], b[nxt], st_next, lm, 0);
+      }
+      if (HAS_W) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b[cur][i] *= wk[j];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], a[cur][i], b[cur][jn]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(ring.empty0 + 8 * s);
+    ++it;
+    s = s_next;
+    st = st_next;
+    if (HAS_W) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wk[j] = wn[j];
+    }
+  }
+}
+
+__device__ __forceinline__ void zero_acc(double (&acc)[8][4][2]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+}
+
 // Epilogue concept:  void tile(const double (&acc)[8][4][2], int m_base, int n_base, int g8, int l4) const
 //   called once per consumer warp with its 64x32 accumulator tile; the functor does its own bounds checks.
+//   acc[i][jn][e] -> row = m_base + i*8 + g8,  col = n_base + jn*8 + 2*l4 + e
+//
+// ---------------------------------------------------------------------------------------------------------
+// One CTA per output tile (grid = #tiles [+ extra CTAs owned by the epilogue functor]).  Used for short-K
+// contractions (Cholesky / TRSM updates, Schur, Lasso) where CTAs must retire quickly so that concurrent streams
+// (the Cholesky look-ahead chain) get SMs.
+// ---------------------------------------------------------------------------------------------------------
+struct OneTile {
+  int m0, n0, ktiles;
+  __device__ __forceinline__ int count() const { return ktiles > 0 ? 1 : 0; }
+  __device__ __forceinline__ void segment(int, int& m, int& n, int& k0, int& k1) const {
+    m = m0, n = n0, k0 = 0, k1 = ktiles;
+  }
+};
+
 template <bool HAS_W, class Epilogue>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                const double* __restrict__ w, int upper, Epilogue epi) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
-  const uint32_t tiles0 = smem_u32(smem);
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
   {
@@ -111,100 +293,129 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       return;
     }
   }
+  const Ring ring = setup_ring(smem_raw);
   int ti, tj;
   decode_tile(blockIdx.x, tiles_m, tiles_n, upper != 0, ti, tj);
-  const int m0 = ti * BM, n0 = tj * BN;
-  const int ktiles = (K + BK - 1) / BK;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, CONSUMER_WARPS);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
-
-  if (warp == CONSUMER_WARPS) {
-    // ---------------- TMA producer ----------------
-    if (lane == 0) {
-      for (int kt = 0; kt < ktiles; ++kt) {
-        const int s = kt % STAGES;
-        if (kt >= STAGES) mbar_wait(empty0 + 8 * s, ((kt / STAGES) - 1) & 1);
-        const uint32_t full = full0 + 8 * s;
-        mbar_expect_tx(full, STAGE_BYTES);
-        const uint32_t dstA = tiles0 + s * STAGE_BYTES, dstB = dstA + OPERAND_BYTES;
-#pragma unroll
-        for (int c = 0; c < BM / 16; ++c) tma_load_2d(dstA + c * CHUNK_BYTES, &tmA, m0 + c * 16, kt * BK, full);
-#pragma unroll
-        for (int c = 0; c < BN / 16; ++c) tma_load_2d(dstB + c * CHUNK_BYTES, &tmB, n0 + c * 16, kt * BK, full);
-      }
-    }
-    return;
-  }
-
-  // ---------------- DMMA consumers: warp grid 2 (m) x 4 (n), warp tile 64 x 32 ----------------
-  const int wm = warp >> 2, wn = warp & 3;
-  const int l4 = lane & 3, g8 = lane >> 2;
+  const OneTile sch{ti * BM, tj * BN, (K + BK - 1) / BK};
+  Producer<OneTile> prod(sch, &tmA, &tmB, ring);
+  if (warp == 0)
+    for (int p = 0; p < PREFETCH; ++p) prod.issue(lane);
+  const LaneMap lm = make_lane_map(warp, lane);
   double acc[8][4][2];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  zero_acc(acc);
+  uint32_t it = 0;
+  if (sch.ktiles > 0) consume_ktiles<HAS_W>(acc, ring, lm, w, K, 0, sch.ktiles, it, warp, lane, prod);
+  epi.tile(acc, sch.m0 + (warp >> 2) * 64, sch.n0 + (warp & 3) * 32, lm.g8, lm.l4);
+}
 
-  // byte offset of this lane's element inside a [16 x 128B] chunk, for even / odd column-block index and for
-  // the two row parities (jb = j & 1):   unit16 = ((blk & 1) * 4 + (g8 >> 1)) ^ (2 * l4 + jb)
-  uint32_t off[2][2];
-#pragma unroll
-  for (int e = 0; e < 2; ++e)
-#pragma unroll
-    for (int jb = 0; jb < 2; ++jb)
-      off[e][jb] = (uint32_t)(((((e * 4) + (g8 >> 1)) ^ (2 * l4 + jb)) << 4) + (g8 & 1) * 8);
+// ---------------------------------------------------------------------------------------------------------
+// Persistent variant for long-K contractions (the Hessian C' diag(w) C): grid = G <= #SMs CTAs, every CTA
+// resident.  The first (ntiles / G) * G tiles are processed data-parallel (tile r*G + c); the remaining
+// rem < G tiles would cost a whole extra wave (2080 tiles on 148 SMs = 14.05 waves), so their rem * ktiles
+// k-tile units are split evenly over the first `ctas` CTAs instead ("stream-K" remainder).  A CTA whose slice
+// does not start at a tile's first k-tile writes its 128x128 partial to its workspace slot and raises its flag;
+// the CTA that owns the tile's first k-tile adds the partials in ascending CTA order (deterministic) and runs
+// the epilogue.  The TMA ring streams across tile boundaries (no pipeline drain between tiles).
+// ---------------------------------------------------------------------------------------------------------
+struct StreamK {
+  double* partials;       // gridDim.x slots of BM*BN doubles
+  unsigned int* flags;    // gridDim.x flags; a slot is valid when its flag equals `epoch`
+  unsigned int epoch;
+  int ctas;               // CTAs 0 .. ctas-1 share the remainder tiles (1 <= ctas <= min(gridDim.x, rem * ktiles))
+};
 
-  const uint32_t a_warp = (uint32_t)(wm * 4) * CHUNK_BYTES;                   // 64 cols = 4 chunks
-  const uint32_t b_warp = OPERAND_BYTES + (uint32_t)(wn * 2) * CHUNK_BYTES;   // 32 cols = 2 chunks
+struct PersistentSchedule {
+  int tiles_m, tiles_n, upper, ktiles, G, c, waves, nseg;
+  int seg_tile[2], seg_k0[2], seg_k1[2];
+  __device__ __forceinline__ int count() const { return nseg + waves; }
+  __device__ __forceinline__ int tile_of(int sg) const { return sg < nseg ? seg_tile[sg] : (sg - nseg) * G + c; }
+  __device__ __forceinline__ void segment(int sg, int& m, int& n, int& k0, int& k1) const {
+    int ti, tj;
+    decode_tile(tile_of(sg), tiles_m, tiles_n, upper != 0, ti, tj);
+    m = ti * BM, n = tj * BN;
+    k0 = sg < nseg ? seg_k0[sg] : 0;
+    k1 = sg < nseg ? seg_k1[sg] : ktiles;
+  }
+};
 
-  for (int kt = 0; kt < ktiles; ++kt) {
-    const int s = kt % STAGES;
-    double wk[4];
-    if (HAS_W) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int kk = kt * BK + (j >> 1) * 8 + 2 * l4 + (j & 1);
-        wk[j] = kk < K ? __ldg(w + kk) : 0.0;
-      }
-    }
-    mbar_wait(full0 + 8 * s, (kt / STAGES) & 1);
-    const uint32_t st = tiles0 + s * STAGE_BYTES;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t rowoff = (uint32_t)((j >> 1) * 8 + 2 * l4 + (j & 1)) * 128u;
-      double a[8], b[4];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t addr = st + a_warp + (uint32_t)(i >> 1) * CHUNK_BYTES + rowoff + off[i & 1][j & 1];
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[i]) : "r"(addr));
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t addr = st + b_warp + (uint32_t)(i >> 1) * CHUNK_BYTES + rowoff + off[i & 1][j & 1];
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b[i]) : "r"(addr));
-        if (HAS_W) b[i] *= wk[j];
-      }
+__device__ __forceinline__ void cta_barrier_1() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <bool HAS_W, class Epilogue>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+                          int K, const double* __restrict__ w, int upper, Epilogue epi, StreamK sk) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  PersistentSchedule sch;
+  sch.tiles_m = (M + BM - 1) / BM, sch.tiles_n = (N + BN - 1) / BN, sch.upper = upper;
+  const int ntiles = upper ? sch.tiles_n * (sch.tiles_n + 1) / 2 : sch.tiles_m * sch.tiles_n;
+  const int ktiles = (K + BK - 1) / BK;
+  const int G = gridDim.x, c = blockIdx.x;
+  sch.ktiles = ktiles, sch.G = G, sch.c = c, sch.waves = ntiles / G, sch.nseg = 0;
+  const int dp_tiles = sch.waves * G, rem = ntiles - dp_tiles;
+  const int P = sk.ctas;
+  const long long U = (long long)rem * ktiles;
+  const long long u0 = c < P ? U * c / P : 0, u1 = c < P ? U * (c + 1) / P : 0;
+  sch.seg_tile[0] = sch.seg_tile[1] = sch.seg_k0[0] = sch.seg_k0[1] = sch.seg_k1[0] = sch.seg_k1[1] = 0;
+  if (u1 > u0) {
+    // the CTA's (at most two) stream-K segments
+    const int ta = (int)(u0 / ktiles), ka = (int)(u0 - (long long)ta * ktiles);
+    const int len = (int)(u1 - u0);
+    const int first = min(len, ktiles - ka);
+    sch.seg_tile[0] = dp_tiles + ta, sch.seg_k0[0] = ka, sch.seg_k1[0] = ka + first, sch.nseg = 1;
+    if (len > first) sch.seg_tile[1] = dp_tiles + ta + 1, sch.seg_k0[1] = 0, sch.seg_k1[1] = len - first, sch.nseg = 2;
+  }
+  const Ring ring = setup_ring(smem_raw);
+  Producer<PersistentSchedule> prod(sch, &tmA, &tmB, ring);
+  if (warp == 0)
+    for (int p = 0; p < PREFETCH; ++p) prod.issue(lane);
+  const LaneMap lm = make_lane_map(warp, lane);
+  uint32_t it = 0;
+  double acc[8][4][2];
+  for (int sg = 0; sg < sch.count(); ++sg) {
+    int m0, n0, k0, k1;
+    sch.segment(sg, m0, n0, k0, k1);
+    const bool is_sk = sg < sch.nseg;
+    zero_acc(acc);
+    consume_ktiles<HAS_W>(acc, ring, lm, w, K, k0, k1, it, warp, lane, prod);
+    if (is_sk && k0 != 0) {
+      // partial of a tile owned by a lower CTA
+      double* slot = sk.partials + (size_t)c * (BM * BN) + tid;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int jn = 0; jn < 4; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], a[i], b[jn]);
+        for (int j = 0; j < 4; ++j) {
+          __stcg(slot + ((i * 4 + j) * 2 + 0) * THREADS, acc[i][j][0]);
+          __stcg(slot + ((i * 4 + j) * 2 + 1) * THREADS, acc[i][j][1]);
+        }
+      __threadfence();
+      cta_barrier_1();
+      if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(sk.flags + c), "r"(sk.epoch) : "memory");
+      continue;
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty0 + 8 * s);
+    if (is_sk && k1 < ktiles) {
+      // owner of the tile's first k-tiles: add the partials of the CTAs that cover the rest of the tile
+      const long long tile_end = (long long)(sch.seg_tile[sg] - dp_tiles + 1) * ktiles;
+      for (int c2 = c + 1; c2 < P && U * c2 / P < tile_end; ++c2) {
+        if (tid == 0) {
+          unsigned v;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sk.flags + c2) : "memory");
+          } while (v != sk.epoch);
+        }
+        cta_barrier_1();
+        const double* slot = sk.partials + (size_t)c2 * (BM * BN) + tid;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            acc[i][j][0] += __ldcg(slot + ((i * 4 + j) * 2 + 0) * THREADS);
+            acc[i][j][1] += __ldcg(slot + ((i * 4 + j) * 2 + 1) * THREADS);
+          }
+      }
+    }
+    epi.tile(acc, m0 + (warp >> 2) * 64, n0 + (warp & 3) * 32, lm.g8, lm.l4);
   }
-
-  // ---------------- epilogue ----------------
-  // The functor sees the warp's whole 64x32 accumulator tile so it can batch its global loads:
-  //   acc[i][jn][e] -> row = m_base + i*8 + g8,  col = n_base + jn*8 + 2*l4 + e
-  epi.tile(acc, m0 + wm * 64, n0 + wn * 32, g8, l4);
 }
 
 }  // namespace gemm

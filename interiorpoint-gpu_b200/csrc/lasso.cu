@@ -22,7 +22,7 @@ namespace ipm {
 
 constexpr int TAIL_MAX = 8;      // tail rows handled by the dot-product CTAs
 constexpr int TAIL_COLS = 256;   // columns per tail CTA
-constexpr int WARPS_PER_CTA = gemm::CONSUMER_WARPS + 1;
+constexpr int WARPS_PER_CTA = gemm::THREADS / 32;
 
 struct LassoEpilogue {
   const double* bA;

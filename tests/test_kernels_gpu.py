@@ -64,6 +64,45 @@ def test_gemm_tn(M, N, K, use_w, upper):
     assert torch.count_nonzero(Dd[:, N:]) == 0  # padding untouched
 
 
+@pytest.mark.parametrize("M,N,K,use_w,upper", [
+    (2304, 2304, 1030, True, 1),    # 171 upper tiles on 148 SMs: 1 full wave + 23 stream-K remainder tiles
+    (1000, 2500, 1024, False, 0),   # 160 tiles: 12 remainder tiles, K a multiple of the k-tile
+    (2400, 2400, 3000, True, 1),    # 190 tiles, ragged M / K
+    (1280, 2048, 1200, True, 0),    # 160 tiles, rectangular, weighted
+])
+def test_gemm_tn_persistent_stream_k(M, N, K, use_w, upper):
+    """Long-K contractions with more tiles than SMs take the persistent kernel (data-parallel waves + stream-K
+    remainder with deterministic fix-up, gemm_tn_core.cuh); checked against float64 torch.matmul on the device and
+    for run-to-run bit reproducibility."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.rand((K, M), dtype=torch.float64, device="cuda", generator=g) * 4 - 2
+    B = A if upper else torch.rand((K, N), dtype=torch.float64, device="cuda", generator=g) * 4 - 2
+    w = 10.0 ** (torch.rand(K, dtype=torch.float64, device="cuda", generator=g) * 8 - 4) if use_w else None
+    D0 = torch.rand((M, N), dtype=torch.float64, device="cuda", generator=g)
+    alpha, beta = 0.75, -0.5
+    Ad, lda = padded(A)
+    Bd, ldb = (Ad, lda) if upper else padded(B)
+    outs = []
+    for _ in range(2):
+        Dd, ldd = padded(D0)
+        _abi.call("ipm_gemm_tn_f64", Ad.data_ptr(), lda, Bd.data_ptr(), ldb, _abi.ptr(w), alpha, beta, Dd.data_ptr(),
+                  ldd, M, N, K, upper, None)
+        torch.cuda.synchronize()
+        outs.append(Dd)
+    assert torch.equal(outs[0], outs[1])  # deterministic fix-up order
+    got = outs[0][:, :N]
+    Aw = A * w[:, None] if use_w else A
+    ref = beta * D0 + alpha * (Aw.T @ B)
+    scale = Aw.abs().T @ B.abs() + D0.abs()
+    err = (got - ref).abs() / scale
+    if upper:
+        assert float(torch.triu(err).max()) < 1e-14
+        assert torch.equal(torch.tril(got, -1), torch.tril(D0, -1))
+    else:
+        assert float(err.max()) < 1e-14
+    assert torch.count_nonzero(outs[0][:, N:]) == 0
+
+
 def test_gemm_tn_beta_zero_ignores_nan_output():
     rs = np.random.RandomState(0)
     A = rs.randn(50, 40)
