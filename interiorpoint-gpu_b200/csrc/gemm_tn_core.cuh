@@ -12,8 +12,10 @@
 // TMA (cp.async.bulk.tensor.2d, 128B swizzle) into a 6-stage mbarrier ring and consumed by 8 MMA warps (warp
 // tile 64x32, 64 FP64 accumulators per thread).  There is no dedicated producer warp: a ninth warp would put
 // three warps on one SM sub-partition and cap every thread at 168 registers (16K registers per sub-partition),
-// which spills the double-buffered fragments.  Instead lane 0 of warp 0 keeps the ring PREFETCH k-tiles ahead
-// of its own consumption (one expect_tx + 16 TMA issues per k-tile, hidden behind the 128 DMMAs of that tile).
+// which spills the double-buffered fragments.  Instead every warp keeps the ring PREFETCH k-tiles ahead of its
+// own consumption: lane 0 of warp c issues the two TMA boxes of column chunk c (one of A, one of B) of each
+// k-tile, so the producer work is symmetric (a single producing warp becomes the pace-setter of the CTA: the
+// other seven run into the prefetch horizon and idle their DMMA pipes).
 //
 // Shared-memory tile layout (per operand, per stage): 8 column chunks of [16 k-rows][16 doubles = 128 B],
 // each written by one TMA box with CU_TENSOR_MAP_SWIZZLE_128B: 16-byte unit c of row r lands at unit
@@ -107,7 +109,7 @@ __device__ __forceinline__ Ring setup_ring(uint8_t* smem_raw) {
   Ring ring{smem_u32(bars), smem_u32(bars + STAGES), smem_u32(smem)};
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(ring.full0 + 8 * s, 1);
+      mbar_init(ring.full0 + 8 * s, CONSUMER_WARPS);
       mbar_init(ring.empty0 + 8 * s, CONSUMER_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -120,7 +122,7 @@ __device__ __forceinline__ Ring setup_ring(uint8_t* smem_raw) {
 // Work of one CTA = a short list of segments (output tile, k-tile range).  Schedule concept:
 //   int count() const;   void segment(int sg, int& m0, int& n0, int& k0, int& k1) const;   (k1 > k0)
 //
-// Producer cursor (warp 0; every lane tracks it, lane 0 issues): walks the segment list one k-tile per call.
+// Producer cursor (every warp keeps its own copy; lane 0 issues): walks the segment list one k-tile per call.
 template <class Schedule>
 struct Producer {
   const Schedule& sch;
@@ -137,18 +139,18 @@ struct Producer {
     ++sg;
     if (sg < sch.count()) sch.segment(sg, m0, n0, kt, k1);
   }
-  __device__ __forceinline__ void issue(int lane) {
+  // Every warp calls this once per consumed k-tile: lane 0 of warp `wp` waits until the ring slot is free, posts
+  // its share of the transaction bytes and issues the two TMA boxes (column chunk `wp` of A and of B).
+  __device__ __forceinline__ void issue(int wp, int lane) {
     if (sg >= sch.count()) return;
     if (lane == 0) {
       const uint32_t s = it % STAGES;
       if (it >= STAGES) mbar_wait(ring.empty0 + 8 * s, ((it / STAGES) - 1) & 1);
       const uint32_t full = ring.full0 + 8 * s;
-      mbar_expect_tx(full, STAGE_BYTES);
-      const uint32_t dstA = ring.tiles0 + s * STAGE_BYTES, dstB = dstA + OPERAND_BYTES;
-#pragma unroll
-      for (int c = 0; c < BM / 16; ++c) tma_load_2d(dstA + c * CHUNK_BYTES, tmA, m0 + c * 16, kt * BK, full);
-#pragma unroll
-      for (int c = 0; c < BN / 16; ++c) tma_load_2d(dstB + c * CHUNK_BYTES, tmB, n0 + c * 16, kt * BK, full);
+      mbar_expect_tx(full, 2 * CHUNK_BYTES);
+      const uint32_t dstA = ring.tiles0 + s * STAGE_BYTES + wp * CHUNK_BYTES, dstB = dstA + OPERAND_BYTES;
+      tma_load_2d(dstA, tmA, m0 + wp * 16, kt * BK, full);
+      tma_load_2d(dstB, tmB, n0 + wp * 16, kt * BK, full);
     }
     __syncwarp();
     ++it;
@@ -204,7 +206,7 @@ __device__ __forceinline__ void load_weights(double (&wk)[4], const double* __re
 
 // acc += sum over k-tiles [kt_begin, kt_end).  Software pipelined: the fragments of k-group j+1 (and the row
 // weights of the next k-tile) are in flight while the 32 DMMAs of group j issue; warp 0 tops the TMA ring up by
-// one k-tile per consumed k-tile.
+// one k-tile per consumed k-tile (each warp its own two boxes).
 template <bool HAS_W, class Schedule>
 __device__ __forceinline__ void consume_ktiles(double (&acc)[8][4][2], const Ring& ring, const LaneMap& lm,
                                                const double* __restrict__ w, int K, int kt_begin, int kt_end,
@@ -219,7 +221,7 @@ __device__ __forceinline__ void consume_ktiles(double (&acc)[8][4][2], const Rin
   for (int kt = kt_begin; kt < kt_end; ++kt) {
     const bool has_next = kt + 1 < kt_end;
     if (HAS_W && has_next) load_weights(wn, w, kt + 1, K, lm.l4);
-    if (warp == 0) prod.issue(lane);
+    prod.issue(warp, lane);
     uint32_t s_next = s, st_next = st;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -298,8 +300,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   decode_tile(blockIdx.x, tiles_m, tiles_n, upper != 0, ti, tj);
   const OneTile sch{ti * BM, tj * BN, (K + BK - 1) / BK};
   Producer<OneTile> prod(sch, &tmA, &tmB, ring);
-  if (warp == 0)
-    for (int p = 0; p < PREFETCH; ++p) prod.issue(lane);
+  for (int p = 0; p < PREFETCH; ++p) prod.issue(warp, lane);
   const LaneMap lm = make_lane_map(warp, lane);
   double acc[8][4][2];
   zero_acc(acc);
@@ -367,8 +368,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   }
   const Ring ring = setup_ring(smem_raw);
   Producer<PersistentSchedule> prod(sch, &tmA, &tmB, ring);
-  if (warp == 0)
-    for (int p = 0; p < PREFETCH; ++p) prod.issue(lane);
+  for (int p = 0; p < PREFETCH; ++p) prod.issue(warp, lane);
   const LaneMap lm = make_lane_map(warp, lane);
   uint32_t it = 0;
   double acc[8][4][2];
