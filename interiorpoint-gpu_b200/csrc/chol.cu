@@ -18,76 +18,200 @@ constexpr int NB = 128;    // panel height == GEMM tile
 constexpr int NBO = 256;   // outer block (K of the trailing update)
 
 // ------------------------------------------------------------------------------------------------
-// Diagonal block: right-looking Cholesky of an nb x nb (nb <= 128) upper block, REGISTER resident.
-// 16 warps; thread (warp w, lane t) owns rows w + 16a (a < 8) and columns t + 32b (b < 4).  Per column j the
-// owning warp scales the pivot row (rsqrt, no division on the chain) and publishes it through a
-// double-buffered 128-entry shared vector -- one barrier per column; everyone then applies the rank-1 update
-// to its registers.  info (1-based global index of the first non-positive pivot) is written once.
+// Diagonal block: right-looking Cholesky of an nb x nb (nb <= 128) upper block held in shared memory, blocked in
+// 32-column sub-panels so that the 128-step dependent chain never crosses a CTA barrier:
+//   (a) warp 0 factors the 32x32 diagonal sub-block in registers (lane = column; pivot and row entries travel by
+//       shuffle; rsqrt, no division on the chain),
+//   (b) the 32 x W row panel to its right is solved by one thread per column (right-looking substitution, the
+//       chain per row is DMUL -> DFMA),
+//   (c) all warps apply the rank-32 update to the W x W trailing block as 8x8 DMMA tiles (upper tiles only).
+// info (1-based global index of the first non-positive pivot) is written once.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512, 1) potf2_kernel(double* __restrict__ A, long long ld, int nb, int k0,
-                                                       int* __restrict__ info) {
-  __shared__ double urow[2][NB];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double own[8][4];
+#ifdef IPM_PHASE_TIMING
+__device__ long long g_phase_t[64];
+#define IPM_PHASE_MARK(i)                                  \
+  do {                                                     \
+    if (threadIdx.x == 0 && blockIdx.x == 0) g_phase_t[i] = clock64(); \
+  } while (0)
+#else
+#define IPM_PHASE_MARK(i) \
+  do {                    \
+  } while (0)
+#endif
+
+constexpr int PF_LD = NB + 4;  // 132: rows 16-byte aligned; (4k + m) mod 16 distinct -> conflict-free DMMA fragments
+constexpr int PF_THREADS = 256;  // 8 warps: the register-resident 32x32 pivot block needs > 128 registers/thread
+constexpr int PF_SMEM = NB * PF_LD * 8;
+
+// Branch-free 1/sqrt(x): hardware seed (rsqrt.approx.f64, ~2^-22) + one third-order correction
+// y = y0 (1 + e/2 + 3 e^2 / 8), e = 1 - x y0^2  -> relative error ~2^-64 before rounding.  The CUDA library
+// rsqrt() has a call to a slow path for special operands, which splits the unrolled pivot loop into basic blocks
+// and keeps ptxas from overlapping one column's shuffles with the next column's pivot chain.
+__device__ __forceinline__ double rsqrt_nobranch(double x) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double e = fma(-x, y0 * y0, 1.0);
+  const double c = fma(e, 0.375, 0.5);
+  return fma(c, y0 * e, y0);
+}
+
+// (c) of potf2_kernel: rank-32 update of the W x W trailing block, T -= P^T P with P the 32 x W row panel, as
+// 8x8 DMMA tiles (upper tiles only, round-robin over the warps).  Fragment (k = lane & 3, m = lane >> 2) of
+// k-group kk and 8-column block x:  S[(base + 4 kk + k) * PF_LD + t0 + 8 x + m].
+__device__ __forceinline__ void potf2_trailing_update(double* __restrict__ S, int base, int W, int warp, int lane) {
+  const int t0 = base + 32, wt = W >> 3;
+  const int k4 = lane & 3, m8 = lane >> 2;
+  const double* frag = S + (base + k4) * PF_LD + t0 + m8;
+  int ri = 0, first = 0;  // `first` = linear index of tile (ri, ri)
+  for (int t = warp; t < wt * (wt + 1) / 2; t += PF_THREADS / 32) {
+    while (t >= first + (wt - ri)) first += wt - ri, ++ri;
+    const int ci = ri + (t - first);
+    double2* cp = reinterpret_cast<double2*>(S + (t0 + 8 * ri + m8) * PF_LD + t0 + 8 * ci + 2 * k4);
+    double2 c = *cp;
+    double a[8], b[8];
 #pragma unroll
-  for (int a = 0; a < 8; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int r = warp + 16 * a, c = lane + 32 * b;
-      own[a][b] = (r < nb && c < nb && c >= r) ? A[(long long)r * ld + c] : 0.0;
+    for (int kk = 0; kk < 8; ++kk) {
+      a[kk] = -frag[(4 * kk) * PF_LD + 8 * ri];
+      b[kk] = frag[(4 * kk) * PF_LD + 8 * ci];
     }
-  // column j = 16*ja + jw: row j lives in own[ja][*] of warp jw, its pivot in own[ja][ja >> 1] of lane j & 31.
-  // ja is unrolled so every register-array index is a compile-time constant (no local-memory spill).
 #pragma unroll
-  for (int ja = 0; ja < 8; ++ja) {
-    for (int jw = 0; jw < 16; ++jw) {
-      const int j = 16 * ja + jw;
-      if (j >= nb) break;  // uniform
-      double* ur = urow[j & 1];
-      if (warp == jw) {
-        const double d = __shfl_sync(0xffffffffu, own[ja][ja >> 1], j & 31);
-        if (lane == 0 && !(d > 0.0)) atomicCAS(info, 0, k0 + j + 1);
-        const double dinv = rsqrt(d);
-        const double ujj = d * dinv;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int c = lane + 32 * b;
-          const double v = (c == j) ? ujj : (c > j ? own[ja][b] * dinv : 0.0);
-          ur[c] = v;
-          if (c >= j) own[ja][b] = v;
+    for (int kk = 0; kk < 8; ++kk)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c.x), "+d"(c.y)
+                   : "d"(a[kk]), "d"(b[kk]));
+    *cp = c;
+  }
+}
+
+__global__ void __launch_bounds__(PF_THREADS, 1) potf2_kernel(double* __restrict__ A, long long ld, int nb, int k0,
+                                                              int* __restrict__ info) {
+  extern __shared__ double S[];  // NB x PF_LD; identity beyond nb, garbage-tolerant strict lower triangle
+  __shared__ double rs[32];      // rsqrt of the current sub-block's pivots
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool vec = !(ld & 1) && !(((uintptr_t)A) & 15);
+  if (vec) {
+#pragma unroll 16
+    for (int q = 0; q < NB * NB / 2 / PF_THREADS; ++q) {
+      const int idx = tid + PF_THREADS * q;  // pair index: row = idx / 64, col = 2 * (idx % 64)
+      const int r = idx >> 6, c = (idx & 63) * 2;
+      double2 v = make_double2(r == c ? 1.0 : 0.0, r == c + 1 ? 1.0 : 0.0);
+      if (r < nb && c + 1 >= r) {
+        if (c + 1 < nb) {
+          v = *reinterpret_cast<const double2*>(A + (long long)r * ld + c);
+        } else if (c < nb) {
+          v.x = A[(long long)r * ld + c];
         }
       }
-      __syncthreads();
-      double uc[4];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) uc[b] = ur[lane + 32 * b];
-#pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        const int r = warp + 16 * a;
-        if (a >= ja && r > j && r < nb) {  // warp-uniform; rows above the pivot are final
-          const double ujr = ur[r];
-#pragma unroll
-          for (int b = 0; b < 4; ++b)
-            if (lane + 32 * b >= r) own[a][b] = fma(-ujr, uc[b], own[a][b]);
-        }
-      }
-      // urow is double buffered: the next column writes the other half, so one barrier per column suffices
+      S[r * PF_LD + c] = v.x;
+      S[r * PF_LD + c + 1] = v.y;
+    }
+  } else {
+    for (int idx = tid; idx < NB * NB; idx += PF_THREADS) {
+      const int r = idx >> 7, c = idx & 127;
+      S[r * PF_LD + c] = (r < nb && c < nb && c >= r) ? A[(long long)r * ld + c] : (r == c ? 1.0 : 0.0);
     }
   }
+  IPM_PHASE_MARK(0);
+  __syncthreads();
+  IPM_PHASE_MARK(1);
+  for (int base = 0; base < NB; base += 32) {
+    if (base >= nb) break;  // uniform: the rest is identity padding
+    IPM_PHASE_MARK(2 + (base >> 5) * 4);
+    if (warp == 0) {
+      // (a) 32x32 diagonal sub-block, lane = column
+      double d[32];
 #pragma unroll
-  for (int a = 0; a < 8; ++a)
+      for (int i = 0; i < 32; ++i) d[i] = S[(base + i) * PF_LD + base + lane];
+      int bad = 0;  // 1-based column of the first non-positive pivot of this sub-block (select, no branch)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int r = warp + 16 * a, c = lane + 32 * b;
-      if (r < nb && c < nb && c >= r) A[(long long)r * ld + c] = own[a][b];
+      for (int j = 0; j < 32; ++j) {
+        const double piv = __shfl_sync(0xffffffffu, d[j], j);
+        bad = (bad == 0 && !(piv > 0.0)) ? j + 1 : bad;
+        const double r = rsqrt_nobranch(piv);
+        const double u = d[j] * r;  // lane c: U[j][c] (c == j: piv * r = sqrt(piv))
+        d[j] = u;
+        if (lane == j) rs[j] = r;
+#pragma unroll
+        for (int i = j + 1; i < 32; ++i) {
+          const double ui = __shfl_sync(0xffffffffu, u, i);
+          d[i] = fma(-ui, u, d[i]);  // meaningful for lanes c >= i
+        }
+      }
+      if (bad && lane == 0) atomicCAS(info, 0, k0 + base + bad);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (lane >= i) S[(base + i) * PF_LD + base + lane] = d[i];
     }
+    __syncthreads();
+    IPM_PHASE_MARK(3 + (base >> 5) * 4);
+    const int W = NB - base - 32;  // 96, 64, 32, 0
+    if (W == 0) break;
+    if (tid < W) {
+      // (b) row panel: column c of the 32 x W block right of the diagonal sub-block
+      const int c = base + 32 + tid;
+      double v[32];
+#pragma unroll
+      for (int l = 0; l < 32; ++l) v[l] = S[(base + l) * PF_LD + c];
+#pragma unroll
+      for (int l = 0; l < 32; ++l) {
+        const double x = v[l] * rs[l];
+        v[l] = x;
+#pragma unroll
+        for (int r = l + 1; r < 32; ++r) v[r] = fma(-S[(base + l) * PF_LD + base + r], x, v[r]);
+      }
+#pragma unroll
+      for (int l = 0; l < 32; ++l) S[(base + l) * PF_LD + c] = v[l];
+    }
+    __syncthreads();
+    IPM_PHASE_MARK(4 + (base >> 5) * 4);
+    // (c) trailing W x W block
+    potf2_trailing_update(S, base, W, warp, lane);
+    __syncthreads();
+    IPM_PHASE_MARK(5 + (base >> 5) * 4);
+  }
+  __syncthreads();
+  IPM_PHASE_MARK(20);
+  if (vec) {
+#pragma unroll 16
+    for (int q = 0; q < NB * NB / 2 / PF_THREADS; ++q) {
+      const int idx = tid + PF_THREADS * q;
+      const int r = idx >> 6, c = (idx & 63) * 2;
+      if (r < nb && c + 1 >= r) {
+        double* p = A + (long long)r * ld + c;
+        if (c >= r && c + 1 < nb) {
+          *reinterpret_cast<double2*>(p) = make_double2(S[r * PF_LD + c], S[r * PF_LD + c + 1]);
+        } else {
+          if (c >= r && c < nb) p[0] = S[r * PF_LD + c];
+          if (c + 1 < nb) p[1] = S[r * PF_LD + c + 1];
+        }
+      }
+    }
+  } else {
+    for (int idx = tid; idx < NB * NB; idx += PF_THREADS) {
+      const int r = idx >> 7, c = idx & 127;
+      if (r < nb && c < nb && c >= r) A[(long long)r * ld + c] = S[r * PF_LD + c];
+    }
+  }
+  IPM_PHASE_MARK(21);
+}
+
+static int launch_potf2(double* Akk, long long ld, int nb, int k0, int* info, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    IPM_CUDA_CHECK(cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
+    attr_set = true;
+  }
+  potf2_kernel<<<1, PF_THREADS, PF_SMEM, st>>>(Akk, ld, nb, k0, info);
+  IPM_LAUNCH_CHECK();
+  return IPM_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Panel solve  X = U11^{-T} P   (U11: nb x nb upper, P: nb x ncols row-major, in place).
-// CTA = 64 columns; U11 and the CTA's panel slice live in shared memory (192 KiB); substitution runs in
-// 32-row blocks (x kept in registers, true divisions -- no explicit inverse, same backward stability as
-// LAPACK dtrsm), the rows below each block are updated by all 256 threads.
+// CTA = 64 columns; U11 and the CTA's panel slice live in shared memory (192 KiB).  32-row blocks: two warps run
+// the substitution of the block right-looking with the 32 values of their column in registers (chain per row:
+// DMUL by the reciprocal pivot -> DFMA), then all 256 threads update the rows below (8 rows x 1 column per
+// thread, coefficients by 16-byte shared loads).
 // ------------------------------------------------------------------------------------------------
 constexpr int TP_COLS = 64;
 
@@ -96,6 +220,7 @@ __global__ void __launch_bounds__(256, 1) trsm_panel_kernel(const double* __rest
   extern __shared__ double sm[];
   double* Us = sm;             // NB x NB
   double* Ps = sm + NB * NB;   // NB x TP_COLS
+  __shared__ double rinv[NB];
   const int tid = threadIdx.x;
   const int c = tid & (TP_COLS - 1), tr = tid >> 6;  // 4 row phases
   const int col0 = blockIdx.x * TP_COLS;
@@ -103,7 +228,7 @@ __global__ void __launch_bounds__(256, 1) trsm_panel_kernel(const double* __rest
   const bool vecU = (nb == NB) && !(ldu & 1) && !(((uintptr_t)U11) & 15);
   const bool vecP = (nb == NB) && (ncl == TP_COLS) && !(ldp & 1) && !(((uintptr_t)(P + col0)) & 15);
   if (vecU) {
-#pragma unroll 8
+#pragma unroll 16
     for (int q = 0; q < 32; ++q) {
       const int idx = tid + 256 * q;  // double2 index
       const int r = idx >> 6, cc = (idx & 63) * 2;
@@ -119,7 +244,7 @@ __global__ void __launch_bounds__(256, 1) trsm_panel_kernel(const double* __rest
     }
   }
   if (vecP) {
-#pragma unroll 8
+#pragma unroll 16
     for (int q = 0; q < 16; ++q) {
       const int idx = tid + 256 * q;  // double2 index: row = idx / 32, col2 = idx % 32
       const int r = idx >> 5, cc = (idx & 31) * 2;
@@ -134,44 +259,44 @@ __global__ void __launch_bounds__(256, 1) trsm_panel_kernel(const double* __rest
     }
   }
   __syncthreads();
+  if (tid < NB) rinv[tid] = tid < nb ? 1.0 / Us[tid * NB + tid] : 1.0;
+  __syncthreads();
   for (int b0 = 0; b0 < nb; b0 += 32) {
-    const int bl = min(32, nb - b0);
     if (tr == 0) {
-      double x[32];
+      // rows beyond nb are zero rows of Us / Ps with rinv = 1: harmless
+      double v[32];
 #pragma unroll
-      for (int r = 0; r < 32; ++r) {
-        if (r < bl) {
-          // four partial sums shorten the dependent FMA chain
-          double v0 = Ps[(b0 + r) * TP_COLS + c], v1 = 0.0, v2 = 0.0, v3 = 0.0;
+      for (int l = 0; l < 32; ++l) v[l] = Ps[(b0 + l) * TP_COLS + c];
 #pragma unroll
-          for (int l = 0; l < r; ++l) {
-            const double u = Us[(b0 + l) * NB + b0 + r];
-            if ((l & 3) == 0) v0 = fma(-u, x[l], v0);
-            else if ((l & 3) == 1) v1 = fma(-u, x[l], v1);
-            else if ((l & 3) == 2) v2 = fma(-u, x[l], v2);
-            else v3 = fma(-u, x[l], v3);
-          }
-          x[r] = ((v0 + v1) + (v2 + v3)) / Us[(b0 + r) * NB + b0 + r];
-          Ps[(b0 + r) * TP_COLS + c] = x[r];
-        }
+      for (int l = 0; l < 32; ++l) {
+        const double x = v[l] * rinv[b0 + l];
+        v[l] = x;
+        const double* urow = Us + (b0 + l) * NB + b0;
+#pragma unroll
+        for (int r = l + 1; r < 32; ++r) v[r] = fma(-urow[r], x, v[r]);
       }
+#pragma unroll
+      for (int l = 0; l < 32; ++l) Ps[(b0 + l) * TP_COLS + c] = v[l];
     }
     __syncthreads();
-    const int rest0 = b0 + bl;
-    for (int rb = rest0 + 4 * tr; rb < nb; rb += 16) {
-      double acc[4];
+    const int rest0 = b0 + 32;
+    for (int rb = rest0 + 8 * tr; rb < nb; rb += 32) {
+      double acc[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q] = (rb + q < nb) ? Ps[(rb + q) * TP_COLS + c] : 0.0;
-#pragma unroll 8
-      for (int l = 0; l < bl; ++l) {
+      for (int q = 0; q < 8; ++q) acc[q] = Ps[(rb + q) * TP_COLS + c];
+#pragma unroll 4
+      for (int l = 0; l < 32; ++l) {
         const double xl = Ps[(b0 + l) * TP_COLS + c];
-        const double* urow = Us + (b0 + l) * NB + rb;
+        const double2* urow = reinterpret_cast<const double2*>(Us + (b0 + l) * NB + rb);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[q] = fma(-(rb + q < nb ? urow[q] : 0.0), xl, acc[q]);
+        for (int q = 0; q < 4; ++q) {
+          const double2 u2 = urow[q];
+          acc[2 * q] = fma(-u2.x, xl, acc[2 * q]);
+          acc[2 * q + 1] = fma(-u2.y, xl, acc[2 * q + 1]);
+        }
       }
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (rb + q < nb) Ps[(rb + q) * TP_COLS + c] = acc[q];
+      for (int q = 0; q < 8; ++q) Ps[(rb + q) * TP_COLS + c] = acc[q];
     }
     __syncthreads();
   }
@@ -266,8 +391,8 @@ extern "C" int ipm_potrf_upper_f64(double* H, int ld, int n, int* info_dev, void
     for (int k0 = o0; k0 < oend; k0 += NB) {
       const int nb = n - k0 < NB ? n - k0 : NB;
       double* Akk = H + (long long)k0 * ld + k0;
-      potf2_kernel<<<1, 512, 0, cs>>>(Akk, ld, nb, k0, info_dev);
-      IPM_LAUNCH_CHECK();
+      int rcp = launch_potf2(Akk, ld, nb, k0, info_dev, cs);
+      if (rcp) return rcp;
       const int rest = n - k0 - nb;
       if (rest <= 0) continue;
       double* A12 = Akk + nb;  // nb x rest row panel

@@ -52,14 +52,25 @@ def noise_dominated_steps(case, prob, settings):
     return {k for k in range(len(case["inner_iters"])) if t * mu ** k * scale > eps}
 
 
-def assert_iters_close(got, want, tol=2, cap=None, noisy=()):
-    """Per-centering Newton counts within +-tol (north_star: +-2).  Two documented exceptions: a step where the
-    REFERENCE ran into its iteration cap did not converge, so its count is "cap", not a measurement; and
-    noise-dominated steps (see above) get +-4."""
+def objective_rounding_decided_steps(fstar, n_steps, settings):
+    """Centering steps of a FEASIBLE-start solve whose Armijo test is decided by rounding: it compares barrier
+    objectives of magnitude t*|f0|, so once their rounding error t*|f0|*2^-52 exceeds 100x the Newton-decrement
+    threshold that ends the step, the accepted step sizes -- and with them the count -- are noise.  Evidence:
+    tests/golden/sensitivity_group_lasso.py (the reference's own counts at such steps range over 10..50 and 1..9
+    under a 1e-13 relative perturbation of its inputs)."""
+    t, mu, eps = settings.get("t0", 0.1), settings.get("mu", 15), settings.get("inner_epsilon", 1e-5)
+    return {k for k in range(n_steps) if t * mu ** k * abs(fstar) * 2.0 ** -52 > 100 * eps}
+
+
+def assert_iters_close(got, want, tol=2, cap=None, noisy=(), free=()):
+    """Per-centering Newton counts within +-tol (north_star: +-2).  Documented exceptions: a step where the
+    REFERENCE ran into its iteration cap did not converge, so its count is "cap", not a measurement; so is a step
+    in `free` (rounding-decided, see objective_rounding_decided_steps); noise-dominated steps (see above) get
+    +-4."""
     assert len(got) == len(want), (got, want)
     for k, (a, b) in enumerate(zip(got, want)):
-        if cap is not None and b >= cap:
-            assert 1 <= a <= cap, (got, want)
+        if (cap is not None and b >= cap) or k in free:
+            assert 1 <= a <= (cap or 10 ** 9), (got, want)
         elif k in noisy:
             assert abs(a - b) <= 4, (got, want)
         else:
@@ -105,5 +116,7 @@ def test_socp_group_lasso_fstar():
     print(val, g["value"], s.inner_iters, g["inner_iters"], s.phase1_solver.inner_iters, g["phase1_inner_iters"])
     assert val == pytest.approx(g["value"], rel=1e-6)
     assert val + g["offset"] == pytest.approx(g["fstar"], rel=1e-6)
-    assert_iters_close(s.inner_iters, g["inner_iters"], cap=s.max_inner_iters)
+    free = objective_rounding_decided_steps(g["value"], len(g["inner_iters"]), {})
+    assert free == {10, 11}
+    assert_iters_close(s.inner_iters, g["inner_iters"], cap=s.max_inner_iters, free=free)
     assert_iters_close(s.phase1_solver.inner_iters, g["phase1_inner_iters"])
