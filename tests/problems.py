@@ -71,17 +71,21 @@ def lp_dense_family(seed, n, m=None, warm=False):
     return p
 
 
-def qp_dense_family(seed, n, p, k):
-    """BASELINE cfg-3 family: P = Pp'Pp/n + I, p equalities, k inequalities."""
+def qp_dense_family(seed, n, p, k, gram=None, with_feasible_point=False):
+    """BASELINE cfg-3 family: P = Pp'Pp/n + I, p equalities, k inequalities.
+    ``gram`` (optional) computes Pp'Pp -- the full-size tests pass a device matmul, NumPy needs ~10 s at n = 8192."""
     rs = np.random.RandomState(seed)
     Pp = rs.uniform(-2, 2, (n // 2, n))
-    P = Pp.T @ Pp / n + np.eye(n)
+    P = (Pp.T @ Pp if gram is None else gram(Pp)) / n + np.eye(n)
     A = rs.uniform(-2, 2, (p, n))
     C = rs.uniform(-2, 2, (k, n))
     x_feas = rs.uniform(-2, 2, n)
     q = rs.uniform(-2, 2, n)
     d = C @ x_feas + rs.uniform(0.1, 1, k)
-    return dict(P=P, q=q, A=A, b=A @ x_feas, C=C, d=d, lower_bound=-3, upper_bound=3)
+    out = dict(P=P, q=q, A=A, b=A @ x_feas, C=C, d=d, lower_bound=-3, upper_bound=3)
+    if with_feasible_point:
+        out["x_feas"] = x_feas  # strictly feasible by construction (not a solver argument: pop it before the call)
+    return out
 
 
 def socp_family(seed, n, M, k, p=0, margin=1.0, identity_P=True, warm=True):
