@@ -45,7 +45,7 @@ class PhaseOneSolver:
                 from cone_engine import ConeNewton, ConeProblemData
             data = _data if _data is not None else ConeProblemData(self.n, device, None, None, *socp_params,
                                                                    lb=lower_bound, ub=upper_bound)
-            self.ns = ConeNewton(data, phase1=True, max_iters=max_inner_iters, epsilon=inner_epsilon, alpha=alpha,
+            self.ns = (_newton_cls or ConeNewton)(data, phase1=True, max_iters=max_inner_iters, epsilon=inner_epsilon, alpha=alpha,
                                  beta=beta, phase1_tol=tol, use_psd_condition=use_psd_condition,
                                  update_slacks_every=update_slacks_every, launcher=_launcher)
         else:

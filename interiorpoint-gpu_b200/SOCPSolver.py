@@ -8,19 +8,24 @@ the B200 engine:
 
 import numpy as np
 import torch
+import torch.distributed as tdist
 
 try:
     from . import _abi
     from ._solver_base import BarrierSolverBase, as_bound, check_bounds, default_x0, HostArray
     from .cone_engine import ConeNewton, ConeProblemData
+    from .dist import row_range
     from .engine import F64, Launcher
     from .PhaseOneSolver import PhaseOneSolver
+    from .sharded_engine import ShardedConeNewton
 except ImportError:  # flat-module use
     import _abi
     from _solver_base import BarrierSolverBase, as_bound, check_bounds, default_x0, HostArray
     from cone_engine import ConeNewton, ConeProblemData
+    from dist import row_range
     from engine import F64, Launcher
     from PhaseOneSolver import PhaseOneSolver
+    from sharded_engine import ShardedConeNewton
 
 
 def _as_list(v):
@@ -35,7 +40,7 @@ class SOCPSolver(BarrierSolverBase):
                  phase1_max_inner_iters=500, epsilon=1e-10, inner_epsilon=1e-5, check_cvxpy=True,
                  linear_solve_method="cholesky", max_cg_iters=50, alpha=0.2, beta=0.6, mu=15, suppress_print=False,
                  use_gpu=False, try_diag=True, track_loss=False, get_dual_variables=False, phase1_tol=0,
-                 use_psd_condition=False, x0=None, update_slacks_every=0):
+                 use_psd_condition=False, x0=None, update_slacks_every=0, shard_rows=False):
         self.P, self.q, self.F, self.g = P, q, F, g
         if A is None:
             raise ValueError("No cone contraints detected. Run with LPSolver or QPSolver for better performance.")
@@ -112,15 +117,34 @@ class SOCPSolver(BarrierSolverBase):
         self.num_constraints = len(A) + (self.n if self.lb is not None else 0) + (self.n if self.ub is not None else 0)
         self._eq_tol = 1e-3  # SOCPSolver.py:699-703
         self.launcher = Launcher(self.device)
-        self.data = ConeProblemData(self.n, self.device, P, q, A, b, c, d, lb=self.lb, ub=self.ub, F=F, g=g)
+        # optional extension (not in the reference): shard whole cones of ONE problem over the ranks of an initialised
+        # torch.distributed group (partial Hessian + NCCL all-reduce, see sharded_engine.py; BASELINE configs[3])
+        newton_cls, lb_loc, ub_loc = ConeNewton, self.lb, self.ub
+        self.sharded = bool(shard_rows) and tdist.is_available() and tdist.is_initialized() and \
+            tdist.get_world_size() > 1
+        if self.sharded:
+            if F is not None:
+                raise NotImplementedError("shard_rows is implemented for SOCPs without equality constraints")
+            x_all = torch.as_tensor(self.x).to(device=self.device, dtype=F64).clone()
+            tdist.broadcast(x_all, src=0)  # default_x0 may be random (SOCPSolver.py:166): one x0 for all ranks
+            self.x = x_all.cpu().numpy()
+            lo, hi = row_range(len(A), tdist.get_rank(), tdist.get_world_size())
+            if hi <= lo:
+                raise ValueError("shard_rows needs at least one cone per rank")
+            A, b, c, d = A[lo:hi], (None if b is None else b[lo:hi]), (None if c is None else c[lo:hi]), (
+                None if d is None else d[lo:hi])
+            if tdist.get_rank() != 0:
+                lb_loc = ub_loc = None  # bound rows belong to rank 0
+            newton_cls = ShardedConeNewton
+        self.data = ConeProblemData(self.n, self.device, P, q, A, b, c, d, lb=lb_loc, ub=ub_loc, F=F, g=g)
         self.x_dev = torch.as_tensor(self.x).to(device=self.device, dtype=F64).clone()
         self.phase1_solver = PhaseOneSolver(
-            socp=True, socp_params=(A, b, c, d), lower_bound=self.lb, upper_bound=self.ub, x0=self.x,
+            socp=True, socp_params=(A, b, c, d), _newton_cls=newton_cls, lower_bound=self.lb, upper_bound=self.ub, x0=self.x,
             max_outer_iters=max_outer_iters, max_inner_iters=phase1_max_inner_iters, epsilon=epsilon,
             inner_epsilon=inner_epsilon, alpha=alpha, beta=beta, mu=mu, suppress_print=suppress_print, n=self.n,
             tol=phase1_tol, use_psd_condition=use_psd_condition, t0=phase1_t0,
             update_slacks_every=update_slacks_every, _data=self.data, _launcher=self.launcher)
-        self.ns = ConeNewton(self.data, phase1=False, max_iters=max_inner_iters, epsilon=inner_epsilon, alpha=alpha,
+        self.ns = newton_cls(self.data, phase1=False, max_iters=max_inner_iters, epsilon=inner_epsilon, alpha=alpha,
                              beta=beta, use_psd_condition=use_psd_condition, update_slacks_every=update_slacks_every,
                              launcher=self.launcher)
 

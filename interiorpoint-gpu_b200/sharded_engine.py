@@ -1,7 +1,8 @@
-"""Row-sharded Newton centering for ONE large LP / QP across the GPUs of a node.
+"""Row-sharded Newton centering for ONE large LP / QP / SOCP across the GPUs of a node.
 
-Every rank keeps a contiguous block of the inequality rows ``C[lo:hi], d[lo:hi]`` resident in its HBM; the iterate,
-the bounds and the objective are replicated (bound / objective terms are contributed by rank 0 only).  Per Newton
+Every rank keeps a contiguous block of the inequality rows ``C[lo:hi], d[lo:hi]`` (SOCP: a contiguous range of whole
+cones, i.e. of the rows of the stacked matrix W) resident in its HBM; the iterate, the bounds and the objective are
+replicated (bound / objective terms are contributed by rank 0 only).  Per Newton
 iteration the ranks exchange, over NCCL (NVLink 5 / NVSwitch):
 
     barrier sums (4 doubles, SUM; min slack, MIN) -> gradient partial (n doubles, SUM)
@@ -18,15 +19,19 @@ import torch.distributed as dist
 
 try:
     from . import _abi
+    from .cone_engine import ConeNewton
     from .engine import F64, LinearNewton
 except ImportError:  # flat-module use
     import _abi
+    from cone_engine import ConeNewton
     from engine import F64, LinearNewton
 
 
-class ShardedLinearNewton(LinearNewton):
-    def __init__(self, data, group=None, **kw):
-        super().__init__(data, **kw)
+class _RowSharded:
+    """Mixin (placed before the engine class in the MRO): wraps the barrier pieces of the single-GPU engine with the
+    collectives that make their outputs global."""
+
+    def _init_sharding(self, group):
         if self.equality:
             raise NotImplementedError("row sharding is implemented for the feasible-start method (no A x = b)")
         if self.update_slacks_every > 0 or self.diagonal:
@@ -34,8 +39,8 @@ class ShardedLinearNewton(LinearNewton):
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
-        self.ws.Lsum = torch.zeros(1, dtype=F64, device=data.device)
-        self.ws.mn = torch.zeros(1, dtype=F64, device=data.device)
+        self.ws.Lsum = torch.zeros(1, dtype=F64, device=self.d.device)
+        self.ws.mn = torch.zeros(1, dtype=F64, device=self.d.device)
         self.comm_bytes = 0
 
     def _sum(self, t):
@@ -62,6 +67,19 @@ class ShardedLinearNewton(LinearNewton):
         with self.L.timed_range("hessian_formation"):
             self._hessian_impl(t)
 
+    def _feasibility(self, z):
+        super()._feasibility(z)
+        dist.all_reduce(self.ws.kmax, op=dist.ReduceOp.MAX, group=self.group)
+
+    def slacks_at(self, x):
+        raise NotImplementedError("dual variables are not gathered in row-sharded mode")
+
+
+class ShardedLinearNewton(_RowSharded, LinearNewton):
+    def __init__(self, data, group=None, **kw):
+        super().__init__(data, **kw)
+        self._init_sharding(group)
+
     def _hessian_impl(self, t):
         d, ws, L = self.d, self.ws, self.L
         n, m = d.n, d.m
@@ -81,10 +99,6 @@ class ShardedLinearNewton(LinearNewton):
             L("ipm_hess_finish_f64", ws.H.data_ptr(), ws.ldh, n, None, ws.hxs.data_ptr() if self.phase1 else None,
               (ws.red.data_ptr() + 24) if self.phase1 else None, shift)
 
-    def _feasibility(self, z):
-        super()._feasibility(z)
-        dist.all_reduce(self.ws.kmax, op=dist.ReduceOp.MAX, group=self.group)
-
     def _verify_trial(self, z):
         """Global frozen log-sum for the Armijo test: local partial at a = table[kmax], SUM all-reduce."""
         d, ws, L = self.d, self.ws, self.L
@@ -93,5 +107,31 @@ class ShardedLinearNewton(LinearNewton):
         self._sum(ws.Lsum)
         return ws.Lsum.data_ptr(), None
 
-    def slacks_at(self, x):
-        raise NotImplementedError("dual variables are not gathered in row-sharded mode")
+
+class ShardedConeNewton(_RowSharded, ConeNewton):
+    """SOCP: every rank owns a contiguous range of whole cones (its slice of the stacked W).  The Armijo test
+    already evaluates the barrier AT the trial point (ConeNewton._verify_trial -> _eval), whose reductions the mixin
+    all-reduces, so frozen log-sum and feasibility verdict are global without further exchange."""
+
+    def __init__(self, data, group=None, **kw):
+        super().__init__(data, **kw)
+        self._init_sharding(group)
+
+    def _hessian_impl(self, t):
+        d, ws, L = self.d, self.ws, self.L
+        n = d.n
+        beta = 0.0
+        if d.is_qp and not self.phase1 and self.rank == 0:
+            L("ipm_scale_copy_upper_f64", ws.H.data_ptr(), ws.ldh, d.P.data_ptr(), d.ldp, n, t)
+            beta = 1.0
+        L.tag = "hessian"
+        L("ipm_gemm_tn_f64", d.W.data_ptr(), d.ldw, d.W.data_ptr(), d.ldw, ws.wts.data_ptr(), 1.0, beta, ws.H.data_ptr(),
+          ws.ldh, n, n, d.rows_w, 1)
+        L.tag = None
+        if d.nbounds:  # only rank 0 holds bounds
+            L("ipm_hess_finish_f64", ws.H.data_ptr(), ws.ldh, n, ws.hdiag.data_ptr(), None, None, 0.0)
+        self._sum(ws.H[:n] if not self.phase1 else ws.H)
+        shift = self.shift + (1e-9 if self.use_psd_condition else 0.0)
+        if self.phase1 or shift:
+            L("ipm_hess_finish_f64", ws.H.data_ptr(), ws.ldh, n, None, ws.hxs.data_ptr() if self.phase1 else None,
+              (ws.red.data_ptr() + 24) if self.phase1 else None, shift)

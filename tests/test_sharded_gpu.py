@@ -1,4 +1,4 @@
-"""Row-sharded LP across 2 GPUs (NCCL): same optimum / Newton counts as the reference goldens.
+"""Row-sharded LP and cone-sharded SOCP across 2 GPUs (NCCL): same optimum / Newton counts as the reference goldens.
 Skipped on a single-GPU box (the CPU gloo test covers the partitioning logic there)."""
 
 import os
@@ -20,10 +20,14 @@ def _worker(rank, world, port, name, q):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from ipm_b200.LPSolver import LPSolver
+    from ipm_b200.SOCPSolver import SOCPSolver
 
     case = {c["name"]: c for c in load_golden("barrier_cases.json")}[name]
     prob = getattr(problems, case["generator"])(**case["generator_kwargs"])
-    s = LPSolver(**prob, check_cvxpy=False, suppress_print=True, shard_rows=True, **case["settings"])
+    cls = {"LPSolver": LPSolver, "SOCPSolver": SOCPSolver}[case["solver"]]
+    np.random.seed(0)
+    s = cls(**prob, check_cvxpy=False, suppress_print=True, shard_rows=True, **case["settings"])
+    assert s.sharded
     val = s.solve()
     p1 = s.phase1_solver.inner_iters if case["phase1_inner_iters"] is not None else None
     if rank == 0:
@@ -32,8 +36,9 @@ def _worker(rank, world, port, name, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["lp_dense_n256_cold", "lp_dense_n97_ragged"])
-def test_row_sharded_lp_matches_reference(name):
+@pytest.mark.parametrize("name", ["lp_dense_n256_cold", "lp_dense_n97_ragged", "socp_n48_warm", "socp_n48_cold",
+                                  "socp_n96_warm"])
+def test_row_sharded_matches_reference(name):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
