@@ -15,9 +15,10 @@ timed region is the main barrier phase).  One bench "step" = one complete ``LPSo
   cpu_baseline : the CPU oracle (NumPy/SciPy restatement of the reference, oracle/) on this box's host cores on
           a bounded sample (a fixed number of full-size Newton steps).
 
-N > 1 (torchrun): every rank solves an independent instance of the same LP family (seed + rank) with no
-data-path collective ("weak" scaling; BASELINE north_star: batches of independent LP instances split across
-GPUs with no communication).
+N > 1 (torchrun): every rank solves its own copy of the same LP instance with no data-path collective ("weak"
+scaling; BASELINE north_star: batches of independent LP instances split across GPUs with no communication).  The
+copies are identical on purpose: instances drawn from different seeds need different numbers of Newton steps
+(76 .. 130 at this size), and the max-over-ranks time would then measure that imbalance instead of the hardware.
 
 `--impl reference` times the reference algorithm on the host CPU (oracle port; the reference itself is pure
 Python/NumPy and does not travel to the GPU box) for the same metric.
@@ -55,6 +56,10 @@ def parse():
                     help="N > 1: independent LP instance per GPU (weak, no collective) or ONE LP row-sharded with an "
                          "NCCL all-reduce of the partial Hessian (strong)")
     ap.add_argument("--lasso-k", type=int, default=4096, help="Lasso batch size (0 disables the Lasso section)")
+    ap.add_argument("--workload", default="lp", choices=["lp", "socp"],
+                    help="lp: BASELINE configs[1] (the headline); socp: configs[3] (n=16384, 256 cones of 64 rows, "
+                         "test_SOCP settings) -- use with --shard rows for the cone-sharded Hessian scaling numbers")
+    ap.add_argument("--cones", type=int, default=256)
     return ap.parse_args()
 
 
@@ -100,13 +105,13 @@ class ClockSampler:
 
 def hessian_dram_traffic(n, m):
     """DRAM bytes (read + write) per launch of the Hessian kernel from the committed `ncu --set full` capture
-    (profiles/syrk_hessian_ncu_r01.csv, taken at the default cfg-2 shape); None for any other shape."""
+    (profiles/syrk_hessian_ncu_r01b.csv, taken at the default cfg-2 shape); None for any other shape."""
     if (n, m) != (8192, 16384):
         return None
     try:
         import csv
 
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "syrk_hessian_ncu_r01.csv"))))
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "syrk_hessian_ncu_r01b.csv"))))
         h, units, first = rows[0], rows[1], rows[2]
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
         rd = float(first[h.index("dram__bytes_read.sum")]) * scale[units[h.index("dram__bytes_read.sum")]]
@@ -119,8 +124,12 @@ def hessian_dram_traffic(n, m):
 def workload(args, rank):
     import problems
 
+    if args.workload == "socp":
+        n = 16384 if args.n == 8192 else args.n  # --n default is the LP's
+        args.n = n
+        return problems.socp_family(seed=4, n=n, M=args.cones, k=64), args.cones * 66
     m = 2 * args.n if args.m is None else args.m
-    prob = problems.lp_dense_family(seed=8192 + rank, n=args.n, m=m, warm=True)
+    prob = problems.lp_dense_family(seed=8192, n=args.n, m=m, warm=True)
     return prob, m
 
 
@@ -228,12 +237,25 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from ipm_b200.LPSolver import LPSolver
+    from ipm_b200.LPSolver import LPSolver as _LP
+    from ipm_b200.SOCPSolver import SOCPSolver as _SOCP
+    import problems
 
     rows_mode = world > 1 and args.shard == "rows"
     prob, m = workload(args, 0 if rows_mode else rank)
     n = args.n
-    host = {k: (torch.as_tensor(v).pin_memory().numpy() if isinstance(v, np.ndarray) else v) for k, v in prob.items()}
+    socp = args.workload == "socp"
+    if socp:
+        args.lasso_k = 0
+        args.no_cpu_baseline = True
+
+        def LPSolver(**kw):  # same call shape as the LP arm
+            return _SOCP(**kw, **problems.SOCP_TEST_SETTINGS)
+        host = prob
+    else:
+        LPSolver = _LP
+        host = {k: (torch.as_tensor(v).pin_memory().numpy() if isinstance(v, np.ndarray) else v)
+                for k, v in prob.items()}
     x0 = prob["x0"].copy()
 
     def barrier():
@@ -272,7 +294,7 @@ def main():
     comm_bytes = getattr(solver.ns, "comm_bytes", 0)
     L.timed_ops = None
     value_ref = solver.value
-    m_local = solver.data.m
+    m_local = solver.data.rows_w if socp else solver.data.m
 
     # ------------------------------------------------------------------ end-to-end arm (host buffers)
     e2e_ms, e2e_newton, h2d, d2h = None, 0, 0, 0
@@ -337,10 +359,12 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong" if rows_mode else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"dense LP n={n} m={m} box+-3, warm start (BASELINE configs[1]); one step = one "
-                               "LPSolver.solve()", "l2": "inputs (C = %.2f GB) larger than L2" % (8e-9 * m * n),
-                   "per_rank": ("ONE LP, inequality rows sharded over the GPUs, NCCL all-reduce of the partial Hessian"
-                                if rows_mode else "independent LP instance per GPU, no collective")
+        "config": {"workload": (f"SOCP n={n}, {args.cones} cones of 64 rows, P=I, warm start, test_SOCP settings "
+                                "(BASELINE configs[3]); one step = one SOCPSolver.solve()" if socp else
+                                f"dense LP n={n} m={m} box+-3, warm start (BASELINE configs[1]); one step = one "
+                                "LPSolver.solve()"), "l2": "inputs (%.2f GB) larger than L2" % (8e-9 * m * n),
+                   "per_rank": ("ONE problem, constraint rows / whole cones sharded over the GPUs, NCCL all-reduce of "
+                                "the partial Hessian" if rows_mode else "one copy of the instance per GPU (independent solves), no collective")
                    if world > 1 else "single GPU"},
         "time_to_solve_s": ms * 1e-3 / args.steps,
         "newton_steps_per_solve": newton / args.steps / (1 if rows_mode else world),
@@ -348,7 +372,8 @@ def main():
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
                      "frac": achieved / FP64_TENSOR_PEAK_TFLOPS if achieved else None,
                      "traffic": hessian_dram_traffic(n, m), "algorithmic_bytes": 8.0 * (m * n + n * (n + 1) / 2),
-                     "kernel": "gemm_tn_kernel<true> (Hessian C'diag(w)C, upper tiles)",
+                     "kernel": "gemm_tn_persistent_kernel<true> (Hessian C'diag(w)C / W'diag(w)W, upper tiles, "
+                               "stream-K remainder)",
                      "flop_per_launch": flops, "ms_per_launch": hess_ms, "launches_timed": len(hess),
                      "peak_source": "FP64 DMMA issue-rate microbenchmark on this pool (tools/fp64_peak.cu, "
                                     "profiles/fp64_peak_r01.json); MEASURED_PEAKS.json has no FP64 entry"},

@@ -15,7 +15,9 @@ struct PlainEpilogue {
   double alpha, beta;
   int tri;  // != 0: store only col >= row (upper triangle of the output block)
 
-  __device__ __forceinline__ void tile(const double (&acc)[8][4][2], int m_base, int n_base, int g8, int l4) const {
+  template <int MI, int NI>
+  __device__ __forceinline__ void tile(const double (&acc)[MI][NI][2], int m_base, int n_base, int g8, int l4) const {
+    static_assert(MI == 8 && NI == 4, "PlainEpilogue is written for the 128x128 CTA tile");
     const bool vec_ok = ((ldd & 1) == 0) && ((((uintptr_t)D) & 15) == 0);
     // fast path: the warp tile is fully inside the matrix, fully on/above the diagonal, 16-byte aligned
     const bool interior = vec_ok && (m_base + 64 <= M) && (n_base + 32 <= N) && (!tri || n_base >= m_base + 63);
@@ -65,6 +67,8 @@ struct PlainEpilogue {
       }
     }
   }
+  __device__ __forceinline__ void prefetch(int, int, int, int) const {}
+  __device__ __forceinline__ void after_tile(int, int, int, int) const {}
   __device__ __forceinline__ void extra(int) const {}  // never launched with extra CTAs
 };
 

@@ -39,6 +39,23 @@ constexpr int OPERAND_BYTES = (BM / 16) * CHUNK_BYTES;  // 16 KiB
 constexpr int STAGE_BYTES = 2 * OPERAND_BYTES;      // A + B
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES * 8;
 
+// CTA tile shapes: 8 warps as a WM x (8 / WM) grid, each warp MI x NI blocks of 8 x 8 (MI * NI * 2 accumulators per
+// thread).  BM is always 128; BN = 112 exists because 4096 / 112 = 36.6 -> 37 column tiles x 4 row tiles = 148 CTAs,
+// exactly one wave on a B200, where the 128-wide tile leaves 20 SMs idle (Lasso batch, K = 4096 problems).
+struct Shape128x128 {
+  static constexpr int WM = 2, MI = 8, NI = 4;
+};
+struct Shape128x112 {
+  static constexpr int WM = 4, MI = 4, NI = 7;
+};
+template <class S>
+struct ShapeTraits {
+  static constexpr int WN = CONSUMER_WARPS / S::WM;
+  static constexpr int TILE_M = S::WM * S::MI * 8, TILE_N = WN * S::NI * 8;
+  static constexpr int A_CHUNKS = TILE_M / 16, B_CHUNKS = TILE_N / 16;
+  static_assert(TILE_M == BM && TILE_N <= BN && TILE_N % 16 == 0, "unsupported CTA tile");
+};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -94,6 +111,39 @@ __device__ __forceinline__ void decode_tile(int lin, int tiles_m, int tiles_n, b
   tj = t + (lin - (t * T - t * (t - 1) / 2));
 }
 
+// L2-friendly enumeration for the persistent kernel: tile rows are grouped into bands of BAND rows and a band is
+// walked column by column, so the ~148 tiles in flight at any time form a ~12 x 12 block that shares 12 A panels and
+// ~13 B panels (instead of 1 + 148 with the row-major order): every k-slice of a panel is fetched from HBM once and
+// hit in L2 by the other CTAs of the block.  upper: only tiles with tj >= ti.
+constexpr int BAND = 12;
+__device__ __forceinline__ void decode_tile_banded(int lin, int tiles_m, int tiles_n, bool upper, int& ti, int& tj) {
+  int b0 = 0, h = 0;
+  while (true) {
+    h = min(BAND, tiles_m - b0);
+    const int cnt = upper ? h * (tiles_n - b0) - h * (h - 1) / 2 : h * tiles_n;
+    if (lin < cnt || b0 + h >= tiles_m) break;
+    lin -= cnt;
+    b0 += h;
+  }
+  if (!upper) {
+    tj = lin / h;
+    ti = b0 + lin - tj * h;
+    return;
+  }
+  const int tri = h * (h + 1) / 2;  // the band's first h columns hold 1, 2, ..., h tiles
+  if (lin < tri) {
+    int c = 0;
+    while ((c + 1) * (c + 2) / 2 <= lin) ++c;
+    ti = b0 + (lin - c * (c + 1) / 2);
+    tj = b0 + c;
+  } else {
+    lin -= tri;
+    const int c = lin / h;
+    tj = b0 + h + c;
+    ti = b0 + lin - c * h;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Pipeline pieces.  `it` counts the k-tiles that went through the CTA's ring (stage = it % STAGES, phase parity
 // = (it / STAGES) & 1); the producer cursor and the consumers advance it identically, so the ring keeps
@@ -123,7 +173,7 @@ __device__ __forceinline__ Ring setup_ring(uint8_t* smem_raw) {
 //   int count() const;   void segment(int sg, int& m0, int& n0, int& k0, int& k1) const;   (k1 > k0)
 //
 // Producer cursor (every warp keeps its own copy; lane 0 issues): walks the segment list one k-tile per call.
-template <class Schedule>
+template <class Schedule, int B_CHUNKS = BN / 16>
 struct Producer {
   const Schedule& sch;
   const CUtensorMap *tmA, *tmB;
@@ -147,10 +197,10 @@ struct Producer {
       const uint32_t s = it % STAGES;
       if (it >= STAGES) mbar_wait(ring.empty0 + 8 * s, ((it / STAGES) - 1) & 1);
       const uint32_t full = ring.full0 + 8 * s;
-      mbar_expect_tx(full, 2 * CHUNK_BYTES);
+      mbar_expect_tx(full, (wp < B_CHUNKS ? 2 : 1) * CHUNK_BYTES);
       const uint32_t dstA = ring.tiles0 + s * STAGE_BYTES + wp * CHUNK_BYTES, dstB = dstA + OPERAND_BYTES;
       tma_load_2d(dstA, tmA, m0 + wp * 16, kt * BK, full);
-      tma_load_2d(dstB, tmB, n0 + wp * 16, kt * BK, full);
+      if (wp < B_CHUNKS) tma_load_2d(dstB, tmB, n0 + wp * 16, kt * BK, full);
     }
     __syncwarp();
     ++it;
@@ -158,40 +208,48 @@ struct Producer {
   }
 };
 
-// Per-lane constants of a consumer warp (warp grid 2 (m) x 4 (n), warp tile 64 x 32).
+// Per-lane constants of a consumer warp.  Column block b (8 columns) of an operand lives in chunk b >> 1 at
+// 16-byte unit ((b & 1) * 4 + (g8 >> 1)) ^ (2 * l4 + jb) of row (.., jb = row parity); the warp's first block may be
+// odd (128x112: b_blk0 = 7 wn), so its parity is folded into the two offset tables.
 struct LaneMap {
-  uint32_t off[2][2];  // byte offset inside a [16 x 128B] chunk for even/odd column block and row parity
-  uint32_t a_warp, b_warp;
-  int l4, g8;
+  uint32_t a_off[2][2], b_off[2][2];  // [block index parity relative to the warp's first block][row parity]
+  int a_blk0, b_blk0;
+  int l4, g8, wm, wn;
 };
 
+template <class S>
 __device__ __forceinline__ LaneMap make_lane_map(int warp, int lane) {
   LaneMap lm;
   lm.l4 = lane & 3;
   lm.g8 = lane >> 2;
-  const int wm = warp >> 2, wn = warp & 3;
-  // unit16 = ((blk & 1) * 4 + (g8 >> 1)) ^ (2 * l4 + jb)
+  constexpr int WN = ShapeTraits<S>::WN;
+  lm.wm = warp / WN, lm.wn = warp % WN;
+  lm.a_blk0 = lm.wm * S::MI, lm.b_blk0 = lm.wn * S::NI;
 #pragma unroll
   for (int e = 0; e < 2; ++e)
 #pragma unroll
-    for (int jb = 0; jb < 2; ++jb)
-      lm.off[e][jb] = (uint32_t)(((((e * 4) + (lm.g8 >> 1)) ^ (2 * lm.l4 + jb)) << 4) + (lm.g8 & 1) * 8);
-  lm.a_warp = (uint32_t)(wm * 4) * CHUNK_BYTES;                  // 64 cols = 4 chunks
-  lm.b_warp = OPERAND_BYTES + (uint32_t)(wn * 2) * CHUNK_BYTES;  // 32 cols = 2 chunks
+    for (int jb = 0; jb < 2; ++jb) {
+      const int pa = (lm.a_blk0 + e) & 1, pb = (lm.b_blk0 + e) & 1;
+      lm.a_off[e][jb] = (uint32_t)((((pa * 4) + (lm.g8 >> 1)) ^ (2 * lm.l4 + jb)) << 4) + (lm.g8 & 1) * 8;
+      lm.b_off[e][jb] = (uint32_t)((((pb * 4) + (lm.g8 >> 1)) ^ (2 * lm.l4 + jb)) << 4) + (lm.g8 & 1) * 8;
+    }
   return lm;
 }
 
 // Fragments of k-group j (4 k-rows) of the stage at shared address st.
-__device__ __forceinline__ void load_frags(double (&a)[8], double (&b)[4], uint32_t st, const LaneMap& lm, int j) {
+template <class S>
+__device__ __forceinline__ void load_frags(double (&a)[S::MI], double (&b)[S::NI], uint32_t st, const LaneMap& lm,
+                                           int j) {
   const uint32_t rowoff = (uint32_t)((j >> 1) * 8 + 2 * lm.l4 + (j & 1)) * 128u;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const uint32_t addr = st + lm.a_warp + (uint32_t)(i >> 1) * CHUNK_BYTES + rowoff + lm.off[i & 1][j & 1];
+  for (int i = 0; i < S::MI; ++i) {
+    const uint32_t addr = st + (uint32_t)((lm.a_blk0 + i) >> 1) * CHUNK_BYTES + rowoff + lm.a_off[i & 1][j & 1];
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a[i]) : "r"(addr));
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t addr = st + lm.b_warp + (uint32_t)(i >> 1) * CHUNK_BYTES + rowoff + lm.off[i & 1][j & 1];
+  for (int i = 0; i < S::NI; ++i) {
+    const uint32_t addr =
+        st + OPERAND_BYTES + (uint32_t)((lm.b_blk0 + i) >> 1) * CHUNK_BYTES + rowoff + lm.b_off[i & 1][j & 1];
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(b[i]) : "r"(addr));
   }
 }
@@ -207,17 +265,17 @@ __device__ __forceinline__ void load_weights(double (&wk)[4], const double* __re
 // acc += sum over k-tiles [kt_begin, kt_end).  Software pipelined: the fragments of k-group j+1 (and the row
 // weights of the next k-tile) are in flight while the 32 DMMAs of group j issue; warp 0 tops the TMA ring up by
 // one k-tile per consumed k-tile (each warp its own two boxes).
-template <bool HAS_W, class Schedule>
-__device__ __forceinline__ void consume_ktiles(double (&acc)[8][4][2], const Ring& ring, const LaneMap& lm,
+template <bool HAS_W, class S, class Prod>
+__device__ __forceinline__ void consume_ktiles(double (&acc)[S::MI][S::NI][2], const Ring& ring, const LaneMap& lm,
                                                const double* __restrict__ w, int K, int kt_begin, int kt_end,
-                                               uint32_t& it, int warp, int lane, Producer<Schedule>& prod) {
+                                               uint32_t& it, int warp, int lane, Prod& prod) {
   double wk[4], wn[4];
   if (HAS_W) load_weights(wk, w, kt_begin, K, lm.l4);
   uint32_t s = it % STAGES;
   mbar_wait(ring.full0 + 8 * s, (it / STAGES) & 1);
   uint32_t st = ring.tiles0 + s * STAGE_BYTES;
-  double a[2][8], b[2][4];
-  load_frags(a[0], b[0], st, lm, 0);
+  double a[2][S::MI], b[2][S::NI];
+  load_frags<S>(a[0], b[0], st, lm, 0);
   for (int kt = kt_begin; kt < kt_end; ++kt) {
     const bool has_next = kt + 1 < kt_end;
     if (HAS_W && has_next) load_weights(wn, w, kt + 1, K, lm.l4);
@@ -227,21 +285,21 @@ __device__ __forceinline__ void consume_ktiles(double (&acc)[8][4][2], const Rin
     for (int j = 0; j < 4; ++j) {
       const int cur = j & 1, nxt = cur ^ 1;
       if (j < 3) {
-        load_frags(a[nxt], b[nxt], st, lm, j + 1);
+        load_frags<S>(a[nxt], b[nxt], st, lm, j + 1);
       } else if (has_next) {
         s_next = (it + 1) % STAGES;
         mbar_wait(ring.full0 + 8 * s_next, ((it + 1) / STAGES) & 1);
         st_next = ring.tiles0 + s_next * STAGE_BYTES;
-        load_frags(a[nxt], b[nxt], st_next, lm, 0);
+        load_frags<S>(a[nxt], b[nxt], st_next, lm, 0);
       }
       if (HAS_W) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) b[cur][i] *= wk[j];
+        for (int i = 0; i < S::NI; ++i) b[cur][i] *= wk[j];
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < S::MI; ++i)
 #pragma unroll
-        for (int jn = 0; jn < 4; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], a[cur][i], b[cur][jn]);
+        for (int jn = 0; jn < S::NI; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], a[cur][i], b[cur][jn]);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(ring.empty0 + 8 * s);
@@ -255,16 +313,23 @@ __device__ __forceinline__ void consume_ktiles(double (&acc)[8][4][2], const Rin
   }
 }
 
-__device__ __forceinline__ void zero_acc(double (&acc)[8][4][2]) {
+template <int MI, int NI>
+__device__ __forceinline__ void zero_acc(double (&acc)[MI][NI][2]) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MI; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 }
 
-// Epilogue concept:  void tile(const double (&acc)[8][4][2], int m_base, int n_base, int g8, int l4) const
-//   called once per consumer warp with its 64x32 accumulator tile; the functor does its own bounds checks.
+// Epilogue concept:  template <int MI, int NI> void tile(const double (&acc)[MI][NI][2], int m_base, int n_base,
+//                                                        int g8, int l4) const
+//   called once per consumer warp with its (8 MI) x (8 NI) accumulator tile; the functor does its own bounds checks.
 //   acc[i][jn][e] -> row = m_base + i*8 + g8,  col = n_base + jn*8 + 2*l4 + e
+//                    void prefetch(int m0, int n0, int tile_m, int tile_n) const
+//   called by every thread when the CTA starts (one-CTA-per-tile kernel only): L2 prefetch of epilogue operands.
+//                    void after_tile(int ti, int tiles_m, int n0, int tile_n) const
+//   called by every thread of the CTA after its tile (one-CTA-per-tile kernel only): per-tile extra work such as
+//   the Lasso tail rows.
 //
 // ---------------------------------------------------------------------------------------------------------
 // One CTA per output tile (grid = #tiles [+ extra CTAs owned by the epilogue functor]).  Used for short-K
@@ -279,13 +344,14 @@ struct OneTile {
   }
 };
 
-template <bool HAS_W, class Epilogue>
+template <bool HAS_W, class Epilogue, class S = Shape128x128>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                const double* __restrict__ w, int upper, Epilogue epi) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr int TN = ShapeTraits<S>::TILE_N;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + TN - 1) / TN;
   {
     // CTAs beyond the tile count belong to the epilogue functor (e.g. the Lasso tail rows that would otherwise
     // cost a whole extra tile row); functors without such work never get launched with extra CTAs.
@@ -298,15 +364,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const Ring ring = setup_ring(smem_raw);
   int ti, tj;
   decode_tile(blockIdx.x, tiles_m, tiles_n, upper != 0, ti, tj);
-  const OneTile sch{ti * BM, tj * BN, (K + BK - 1) / BK};
-  Producer<OneTile> prod(sch, &tmA, &tmB, ring);
+  const OneTile sch{ti * BM, tj * TN, (K + BK - 1) / BK};
+  Producer<OneTile, ShapeTraits<S>::B_CHUNKS> prod(sch, &tmA, &tmB, ring);
   for (int p = 0; p < PREFETCH; ++p) prod.issue(warp, lane);
-  const LaneMap lm = make_lane_map(warp, lane);
-  double acc[8][4][2];
+  epi.prefetch(sch.m0, sch.n0, BM, TN);
+  const LaneMap lm = make_lane_map<S>(warp, lane);
+  double acc[S::MI][S::NI][2];
   zero_acc(acc);
   uint32_t it = 0;
-  if (sch.ktiles > 0) consume_ktiles<HAS_W>(acc, ring, lm, w, K, 0, sch.ktiles, it, warp, lane, prod);
-  epi.tile(acc, sch.m0 + (warp >> 2) * 64, sch.n0 + (warp & 3) * 32, lm.g8, lm.l4);
+  if (sch.ktiles > 0) consume_ktiles<HAS_W, S>(acc, ring, lm, w, K, 0, sch.ktiles, it, warp, lane, prod);
+  epi.tile(acc, sch.m0 + lm.wm * (S::MI * 8), sch.n0 + lm.wn * (S::NI * 8), lm.g8, lm.l4);
+  epi.after_tile(ti, tiles_m, sch.n0, TN);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -332,7 +400,7 @@ struct PersistentSchedule {
   __device__ __forceinline__ int tile_of(int sg) const { return sg < nseg ? seg_tile[sg] : (sg - nseg) * G + c; }
   __device__ __forceinline__ void segment(int sg, int& m, int& n, int& k0, int& k1) const {
     int ti, tj;
-    decode_tile(tile_of(sg), tiles_m, tiles_n, upper != 0, ti, tj);
+    decode_tile_banded(tile_of(sg), tiles_m, tiles_n, upper != 0, ti, tj);
     m = ti * BM, n = tj * BN;
     k0 = sg < nseg ? seg_k0[sg] : 0;
     k1 = sg < nseg ? seg_k1[sg] : ktiles;
@@ -369,15 +437,16 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   const Ring ring = setup_ring(smem_raw);
   Producer<PersistentSchedule> prod(sch, &tmA, &tmB, ring);
   for (int p = 0; p < PREFETCH; ++p) prod.issue(warp, lane);
-  const LaneMap lm = make_lane_map(warp, lane);
+  using S = Shape128x128;
+  const LaneMap lm = make_lane_map<S>(warp, lane);
   uint32_t it = 0;
-  double acc[8][4][2];
+  double acc[S::MI][S::NI][2];
   for (int sg = 0; sg < sch.count(); ++sg) {
     int m0, n0, k0, k1;
     sch.segment(sg, m0, n0, k0, k1);
     const bool is_sk = sg < sch.nseg;
     zero_acc(acc);
-    consume_ktiles<HAS_W>(acc, ring, lm, w, K, k0, k1, it, warp, lane, prod);
+    consume_ktiles<HAS_W, S>(acc, ring, lm, w, K, k0, k1, it, warp, lane, prod);
     if (is_sk && k0 != 0) {
       // partial of a tile owned by a lower CTA
       double* slot = sk.partials + (size_t)c * (BM * BN) + tid;
@@ -414,7 +483,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           }
       }
     }
-    epi.tile(acc, m0 + (warp >> 2) * 64, n0 + (warp & 3) * 32, lm.g8, lm.l4);
+    epi.tile(acc, m0 + lm.wm * 64, n0 + lm.wn * 32, lm.g8, lm.l4);
   }
 }
 

@@ -73,7 +73,9 @@ struct LassoEpilogue {
     }
   }
 
-  __device__ __forceinline__ void tile(const double (&acc)[8][4][2], int m_base, int n_base, int g8, int l4) const {
+  template <int MI, int NI>
+  __device__ __forceinline__ void tile(const double (&acc)[MI][NI][2], int m_base, int n_base, int g8, int l4) const {
+    static_assert(MI == 8 && NI == 4, "LassoEpilogue is written for the 128x128 CTA tile");
     Sums s{0.0, 0.0, 0.0, 0.0};
     const bool interior = (m_base + 64 <= n_main) && (n_base + 32 <= K);
     if (interior) {
@@ -127,6 +129,12 @@ struct LassoEpilogue {
     }
     flush(s);
   }
+
+  // Hooks of the one-CTA-per-tile kernel.  Both were tried for this epilogue on B200 and measured slower than doing
+  // nothing: an L2 prefetch of bA / u / alpha at CTA start (K = 512 shard: 85 -> 91 us per iteration), and folding
+  // the tail row into the tile CTAs instead of the 16 extra CTAs below (104 -> 118 us: it serialises behind the tile).
+  __device__ __forceinline__ void prefetch(int, int, int, int) const {}
+  __device__ __forceinline__ void after_tile(int, int, int, int) const {}
 
   // tail rows [n_main, n): x[r][c] = bA + sum_k Q~[k][r] z[k][c]   (thread = column, coalesced z reads)
   __device__ __forceinline__ void extra(int bid) const {
