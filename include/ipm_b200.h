@@ -55,6 +55,16 @@ int ipm_gemv_n_f64(const double* M, int ld, int rows, int cols, const double* x,
 long long ipm_gemv_t_ws_doubles(int rows, int cols, int nv);
 int ipm_gemv_t_f64(const double* M, int ld, int rows, int cols, const double* V, int nv, int ldv, double* Y, int ldy,
                    double alpha, double beta, double* ws, long long ws_doubles, void* stream);
+/* ---- sparse-aware variants (MIPLIB `.npy` LPs, testSolver.py:278-300, >99 % zeros) ------------- */
+/* y = alpha * S x + beta * y for S in CSR (int32 rowptr[rows+1], col, val).  Same call sites as ipm_gemv_n_f64 with
+ * CSR(C); with CSR(C^T) it replaces ipm_gemv_t_f64 (deterministic, no atomics). */
+int ipm_csr_gemv_f64(const int* rowptr, const int* col, const double* val, int rows, const double* x, double* y,
+                     double alpha, double beta, void* stream);
+/* H[out_i[e]][out_j[e]] += sum_{k in [segptr[e], segptr[e+1])} w[seg_row[k]] * seg_prod[k]   for e < nout: the
+ * structurally non-zero upper-triangle entries of C^T diag(w) C (segments precomputed on the host, ascending row
+ * order).  Replaces the Hessian SYRK of FunctionManager.py:301-312 for sparse C. */
+int ipm_sparse_syrk_f64(int nout, const int* segptr, const int* seg_row, const double* seg_prod, const int* out_i,
+                        const int* out_j, const double* w, double* H, int ld, void* stream);
 /* out[k] = a[k] . b[k], k < npairs <= 8; a, b, n are HOST arrays of device pointers / lengths.
  * gradf.dot(x), gradf.dot(xstep) NewtonSolver.py:129,168; c.dot(x) FunctionManager.py:159. */
 int ipm_dots_f64(int npairs, const double* const* a, const double* const* b, const int* n, double* out, void* stream);

@@ -27,7 +27,7 @@ class LPSolver(BarrierSolverBase):
                  max_outer_iters=20, max_inner_iters=50, phase1_max_inner_iters=500, epsilon=1e-10,
                  inner_epsilon=1e-5, check_cvxpy=True, linear_solve_method="cholesky", max_cg_iters=50, alpha=0.2,
                  beta=0.6, mu=15, suppress_print=False, use_gpu=False, try_diag=True, track_loss=False,
-                 get_dual_variables=False, phase1_tol=0, phase1_t0=0.01, x0=None, update_slacks_every=0, shard_rows=False):
+                 get_dual_variables=False, phase1_tol=0, phase1_t0=0.01, x0=None, update_slacks_every=0, shard_rows=False, sparse="auto"):
         self.A, self.c, self.C, self.b, self.d = A, c, C, b, d
         if c is not None and c.ndim != 1:
             raise ValueError("c must be 1-dimensional!")
@@ -74,7 +74,10 @@ class LPSolver(BarrierSolverBase):
             if tdist.get_rank() != 0:
                 lb_loc = ub_loc = None  # bound rows belong to rank 0
             newton_cls = ShardedLinearNewton
-        self.data = LinearProblemData(self.n, self.device, c=c, C=C_loc, d=d_loc, lb=lb_loc, ub=ub_loc, A=A, b=b)
+        # optional extension: `sparse` ("auto" | True | False) -- inequality rows that are almost all zeros (the MIPLIB
+        # .npy problems of testSolver.py:278-300) are kept as CSR and the Hessian is formed entry-wise (engine.SparseRows)
+        self.data = LinearProblemData(self.n, self.device, c=c, C=C_loc, d=d_loc, lb=lb_loc, ub=ub_loc, A=A, b=b,
+                                      sparse=False if self.sharded else sparse)
         self.x_dev = torch.as_tensor(self.x).to(device=self.device, dtype=F64).clone()
         if C is not None:
             self.phase1_solver = PhaseOneSolver(

@@ -66,7 +66,8 @@ class QPSolver(BarrierSolverBase):
             if tdist.get_rank() != 0:
                 lb_loc = ub_loc = None  # bound rows belong to rank 0
             newton_cls = ShardedLinearNewton
-        self.data = LinearProblemData(self.n, self.device, P=P, q=q, C=C_loc, d=d_loc, lb=lb_loc, ub=ub_loc, A=A, b=b)
+        self.data = LinearProblemData(self.n, self.device, P=P, q=q, C=C_loc, d=d_loc, lb=lb_loc, ub=ub_loc, A=A, b=b,
+                                      sparse=False)
         self.x_dev = torch.as_tensor(self.x).to(device=self.device, dtype=F64).clone()
         if C is not None:
             self.phase1_solver = PhaseOneSolver(

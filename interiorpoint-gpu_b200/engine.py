@@ -112,15 +112,85 @@ def to_dev_vector(a, device, n=None):
     return t.to(device=device, dtype=F64).contiguous()
 
 
+SPARSE_DENSITY = 0.02   # C is handled as sparse rows below this fill (auto mode)
+SPARSE_MIN_N = 256      # ... and only when the problem is large enough for the dense SYRK to matter
+
+
+def _looks_sparse(C):
+    """Fill below SPARSE_DENSITY?  A strided sample of <= 128 rows decides first, so that a dense 1 GB matrix is not
+    scanned on the host inside the constructor (bench.py's end-to-end arm times it)."""
+    sample = C[:: max(1, C.shape[0] // 128)]
+    if np.count_nonzero(sample) >= SPARSE_DENSITY * sample.size:
+        return False
+    return np.count_nonzero(C) < SPARSE_DENSITY * C.size
+
+
+class SparseRows:
+    """CSR(C), CSR(C^T) and the segment map of the Hessian pattern, resident in HBM.
+
+    C^T diag(w) C only has entries (i, j) where some row holds both columns.  For every such upper-triangle entry
+    the host lists, once, the contributing rows r (ascending) with their products c_ri * c_rj; the device kernel
+    ``ipm_sparse_syrk_f64`` then forms each entry with one thread in a fixed order.  C itself is never materialised
+    as a dense device matrix."""
+
+    def __init__(self, C, n, device):
+        import scipy.sparse as sp
+
+        S = sp.csr_matrix(np.asarray(C, dtype=np.float64))
+        S.sum_duplicates()
+        S.sort_indices()
+        St = S.T.tocsr()
+        St.sort_indices()
+        i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(device)  # noqa: E731
+        f64 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(device)  # noqa: E731
+        self.m, self.n, self.nnz = S.shape[0], n, int(S.nnz)
+        self.rowptr, self.col, self.val = i32(S.indptr), i32(S.indices), f64(S.data)
+        self.t_rowptr, self.t_col, self.t_val = i32(St.indptr), i32(St.indices), f64(St.data)
+        # all pairs (i <= j) of the non-zero columns of every row
+        counts = np.diff(S.indptr)
+        rows_i, rows_j, rows_r, prods = [], [], [], []
+        for k in np.unique(counts):
+            if k == 0:
+                continue
+            rr = np.nonzero(counts == k)[0]
+            starts = S.indptr[rr]
+            idx = starts[:, None] + np.arange(k)[None, :]
+            cols, vals = S.indices[idx], S.data[idx]          # [len(rr), k], columns ascending
+            a, b = np.triu_indices(k)
+            rows_i.append(cols[:, a].ravel()), rows_j.append(cols[:, b].ravel())
+            rows_r.append(np.repeat(rr, len(a))), prods.append((vals[:, a] * vals[:, b]).ravel())
+        if rows_i:
+            I, J = np.concatenate(rows_i).astype(np.int64), np.concatenate(rows_j).astype(np.int64)
+            R, Pv = np.concatenate(rows_r), np.concatenate(prods)
+            key = I * n + J
+            order = np.lexsort((R, key))                      # by output entry, then ascending row
+            key, R, Pv, I, J = key[order], R[order], Pv[order], I[order], J[order]
+            first = np.concatenate([[True], key[1:] != key[:-1]])
+            segptr = np.concatenate([np.nonzero(first)[0], [len(key)]])
+            out_i, out_j = I[first], J[first]
+        else:
+            segptr, R, Pv, out_i, out_j = np.zeros(1), np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0)
+        self.nout = len(out_i)
+        self.segptr, self.seg_row, self.seg_prod = i32(segptr), i32(R), f64(Pv)
+        self.out_i, self.out_j = i32(out_i), i32(out_j)
+        self.h2d_bytes = 4 * (len(S.indptr) + len(St.indptr) + 2 * S.nnz + len(segptr) + len(R)) + 8 * (
+            2 * S.nnz + len(Pv) + self.nout)
+
+
 class LinearProblemData:
     """Problem data resident in HBM.  C: m x n inequality rows, A: p x n equality rows (also kept transposed,
     n x p, because every contraction kernel wants the contracted index as the row index), P: n x n."""
 
-    def __init__(self, n, device, c=None, P=None, q=None, C=None, d=None, lb=None, ub=None, A=None, b=None):
+    def __init__(self, n, device, c=None, P=None, q=None, C=None, d=None, lb=None, ub=None, A=None, b=None,
+                 sparse="auto"):
         self.n, self.device = n, device
         self.m = 0 if C is None else C.shape[0]
         self.p = 0 if A is None else A.shape[0]
-        self.C, self.ldc = (None, 0) if C is None else to_dev_matrix(C, device)
+        self.sparse = None
+        if C is not None and sparse:
+            if sparse is True or (n >= SPARSE_MIN_N and isinstance(C, np.ndarray) and _looks_sparse(C)):
+                self.sparse = SparseRows(C, n, device)
+        self.C, self.ldc = (None, 0) if (C is None or self.sparse is not None) else to_dev_matrix(C, device)
         self.d = to_dev_vector(d, device)
         self.lb = to_dev_vector(lb, device, n)
         self.ub = to_dev_vector(ub, device, n)
@@ -135,6 +205,8 @@ class LinearProblemData:
         self.n_slacks = self.m + (n if ub is not None else 0) + (n if lb is not None else 0)
         self.h2d_bytes = sum(t.numel() * 8 for t in (self.C, self.d, self.lb, self.ub, self.P, self.q, self.A,
                                                      self.At, self.b) if t is not None)
+        if self.sparse is not None:
+            self.h2d_bytes += self.sparse.h2d_bytes
 
 
 class NewtonWorkspace:
@@ -227,12 +299,22 @@ class LinearNewton:
         slacks, inv, w, hdiag, red = slot.slacks, slot.inv, slot.w, slot.hdiag, slot.red
         n, m = d.n, d.m
         if m:
-            L("ipm_gemv_n_f64", d.C.data_ptr(), d.ldc, m, n, z.data_ptr(), ws.Cx.data_ptr(), 1.0, 0.0)
+            self._C_times(z, ws.Cx)
         s_ptr = z.data_ptr() + 8 * n if self.phase1 else None
         L("ipm_lin_barrier_eval_f64", m, n, _abi.ptr(ws.Cx) if m else None, _abi.ptr(d.d), z.data_ptr(),
           _abi.ptr(d.ub), _abi.ptr(d.lb), s_ptr, int(self.phase1),
           1e-15 if (self.phase1 or self.diagonal) else 0.0, slacks.data_ptr(), inv.data_ptr(), w.data_ptr(),
           hdiag.data_ptr(), red.data_ptr(), ws.ev_ws.data_ptr())
+
+    def _C_times(self, x, out):
+        """out = C x (dense row GEMV, or CSR for sparse C)."""
+        d, L = self.d, self.L
+        if d.sparse is not None:
+            sp = d.sparse
+            L("ipm_csr_gemv_f64", sp.rowptr.data_ptr(), sp.col.data_ptr(), sp.val.data_ptr(), d.m, x.data_ptr(),
+              out.data_ptr(), 1.0, 0.0)
+        else:
+            L("ipm_gemv_n_f64", d.C.data_ptr(), d.ldc, d.m, d.n, x.data_ptr(), out.data_ptr(), 1.0, 0.0)
 
     def _bound_inv_ptrs(self, inv):
         d = self.d
@@ -273,8 +355,14 @@ class LinearNewton:
                 vptr, ldv = ws.CtV_in.data_ptr(), m
             else:
                 vptr, ldv = inv.data_ptr(), m
-            L("ipm_gemv_t_f64", d.C.data_ptr(), d.ldc, m, n, vptr, nv, ldv, ws.CtV.data_ptr(), n, 1.0, 0.0,
-              ws.gt_ws.data_ptr(), ws.gt_ws_n)
+            if d.sparse is not None:  # C^T v through CSR(C^T): fixed summation order, no atomics
+                sp = d.sparse
+                for v in range(nv):
+                    L("ipm_csr_gemv_f64", sp.t_rowptr.data_ptr(), sp.t_col.data_ptr(), sp.t_val.data_ptr(), n,
+                      vptr + 8 * v * ldv, ws.CtV.data_ptr() + 8 * v * n, 1.0, 0.0)
+            else:
+                L("ipm_gemv_t_f64", d.C.data_ptr(), d.ldc, m, n, vptr, nv, ldv, ws.CtV.data_ptr(), n, 1.0, 0.0,
+                  ws.gt_ws.data_ptr(), ws.gt_ws_n)
         ub_p, lb_p = self._bound_inv_ptrs(inv)
         L("ipm_lin_grad_f64", n, t, _abi.ptr(lin), ws.CtV.data_ptr() if m else None, ub_p, lb_p, int(self.phase1),
           red.data_ptr() + 16, (ws.CtV.data_ptr() + 8 * n) if (m and nv == 2) else None, g.data_ptr(),
@@ -289,9 +377,15 @@ class LinearNewton:
         if d.is_qp and not self.phase1:
             L("ipm_scale_copy_upper_f64", ws.H.data_ptr(), ws.ldh, d.P.data_ptr(), d.ldp, n, t)
             beta = 1.0
-        elif m == 0:
+        elif m == 0 or d.sparse is not None:
             L("ipm_scale_copy_upper_f64", ws.H.data_ptr(), ws.ldh, None, 0, n, 0.0)
-        if m:
+        if m and d.sparse is not None:
+            sp = d.sparse
+            L.tag = "hessian"
+            L("ipm_sparse_syrk_f64", sp.nout, sp.segptr.data_ptr(), sp.seg_row.data_ptr(), sp.seg_prod.data_ptr(),
+              sp.out_i.data_ptr(), sp.out_j.data_ptr(), ws.w.data_ptr(), ws.H.data_ptr(), ws.ldh)
+            L.tag = None
+        elif m:
             L.tag = "hessian"
             L("ipm_gemm_tn_f64", d.C.data_ptr(), d.ldc, d.C.data_ptr(), d.ldc, ws.w.data_ptr(), 1.0, beta,
               ws.H.data_ptr(), ws.ldh, n, n, m, 1)
@@ -377,7 +471,7 @@ class LinearNewton:
         d, ws, L = self.d, self.ws, self.L
         n, m = d.n, d.m
         if m:
-            L("ipm_gemv_n_f64", d.C.data_ptr(), d.ldc, m, n, ws.dz.data_ptr(), ws.Cdx.data_ptr(), 1.0, 0.0)
+            self._C_times(ws.dz, ws.Cdx)
         L("ipm_ls_feas_lin_f64", m, n, ws.slacks.data_ptr(), ws.Cdx.data_ptr() if m else None, ws.dz.data_ptr(),
           int(d.ub is not None), int(d.lb is not None), int(self.phase1), self.table.data_ptr(), self.table_len,
           ws.p1.data_ptr(), ws.kmax.data_ptr())

@@ -255,3 +255,35 @@ def test_dots_and_axpy():
     torch.cuda.synchronize()
     np.testing.assert_allclose(out.cpu().numpy(), [a @ b, a @ a, c @ c], rtol=1e-13)
     np.testing.assert_array_equal(ad.cpu().numpy(), a + 0.36 * b)  # bit-exact NumPy rounding
+
+
+def test_sparse_rows_kernels():
+    """CSR GEMV (both orientations) and the segment-map Hessian C' diag(w) C against dense NumPy."""
+    from ipm_b200.engine import SparseRows
+
+    rs = np.random.RandomState(3)
+    m, n = 700, 333
+    Cm = np.where(rs.rand(m, n) < 0.01, rs.uniform(-2, 2, (m, n)), 0.0)
+    Cm[5] = 0.0  # an empty row
+    sp = SparseRows(Cm, n, torch.device("cuda"))
+    x, v, w = rs.randn(n), rs.randn(m), 10.0 ** rs.uniform(-3, 3, m)
+    xd, vd, wd = dev(x), dev(v), dev(w)
+    y, g = torch.zeros(m, dtype=torch.float64, device="cuda"), torch.zeros(n, dtype=torch.float64, device="cuda")
+    _abi.call("ipm_csr_gemv_f64", sp.rowptr.data_ptr(), sp.col.data_ptr(), sp.val.data_ptr(), m, xd.data_ptr(),
+              y.data_ptr(), 1.0, 0.0, None)
+    _abi.call("ipm_csr_gemv_f64", sp.t_rowptr.data_ptr(), sp.t_col.data_ptr(), sp.t_val.data_ptr(), n, vd.data_ptr(),
+              g.data_ptr(), 1.0, 0.0, None)
+    ld = 336
+    H0 = rs.randn(n, ld)
+    Hd = dev(H0)
+    _abi.call("ipm_sparse_syrk_f64", sp.nout, sp.segptr.data_ptr(), sp.seg_row.data_ptr(), sp.seg_prod.data_ptr(),
+              sp.out_i.data_ptr(), sp.out_j.data_ptr(), wd.data_ptr(), Hd.data_ptr(), ld, None)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(y.cpu().numpy(), Cm @ x, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(g.cpu().numpy(), Cm.T @ v, rtol=1e-13, atol=1e-13)
+    ref = H0.copy()
+    ref[:, :n] += np.triu((Cm * w[:, None]).T @ Cm)
+    got = Hd.cpu().numpy()
+    scale = np.abs(Cm * w[:, None]).T @ np.abs(Cm) + np.abs(H0[:, :n])
+    assert np.max(np.abs(got[:, :n] - ref[:, :n]) / (scale + 1e-300)) < 1e-14
+    np.testing.assert_array_equal(got[:, n:], H0[:, n:])
