@@ -55,6 +55,12 @@ int ipm_gemv_n_f64(const double* M, int ld, int rows, int cols, const double* x,
 long long ipm_gemv_t_ws_doubles(int rows, int cols, int nv);
 int ipm_gemv_t_f64(const double* M, int ld, int rows, int cols, const double* V, int nv, int ldv, double* Y, int ldy,
                    double alpha, double beta, double* ws, long long ws_doubles, void* stream);
+/* ---- L2 residency ----------------------------------------------------------------------------------------- */
+/* Mark [base, base + bytes) as persisting in L2 for kernels launched on `stream` (bytes == 0: clear).  *ratio_out
+ * receives the configured hit ratio (carve-out / window).  No counterpart in the reference: the B200's 126 MB L2
+ * holds the whole ADMM state (84 MB at K = 4096) that LassoSolver.py:240-337 re-reads every iteration. */
+int ipm_l2_persist(const void* base, unsigned long long bytes, double* ratio_out, void* stream);
+
 /* ---- sparse-aware variants (MIPLIB `.npy` LPs, testSolver.py:278-300, >99 % zeros) ------------- */
 /* y = alpha * S x + beta * y for S in CSR (int32 rowptr[rows+1], col, val).  Same call sites as ipm_gemv_n_f64 with
  * CSR(C); with CSR(C^T) it replaces ipm_gemv_t_f64 (deterministic, no atomics). */

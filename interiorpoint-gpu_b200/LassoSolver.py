@@ -7,6 +7,9 @@ Setup (AtA, Cholesky, explicit (A'A + m rho I)^{-1}, A'b, Q A'b; LassoSolver.py:
 GEMM / Cholesky kernels; every ADMM iteration is ONE fused kernel (csrc/lasso.cu); the batch-coupled stop test
 (:273-298) reads four scalars every ``check_stop`` iterations."""
 
+import ctypes as C
+import os
+
 import numpy as np
 import torch
 
@@ -58,6 +61,9 @@ class LassoSolver:
         self.X = np.zeros((self.n, self.num_samples))
         self.feasible, self.cvxpy_vals, self.cvxpy_sols = None, None, None
         self.h2d_bytes = (A.size + b.size + reg.size) * 8
+        # keep the ADMM state L2-resident between iterations (ipm_l2_persist); IPM_LASSO_L2=0 switches it off
+        self.l2_resident = os.environ.get("IPM_LASSO_L2", "1") != "0"
+        self.l2_hit_ratio = 0.0
         # one chunk: everything is precomputed and resident before solve() (LassoSolver.py:193-222)
         self._prep = self._prepare(np.arange(self.num_samples)) if self.num_chunks == 1 else None
 
@@ -99,11 +105,15 @@ class LassoSolver:
         b_dev, _ = to_dev_matrix(b, dev)
         reg_dev = torch.as_tensor(reg).to(dev)
         eta = reg_dev / self.rho
+        # bA and the four state arrays live in ONE allocation so that a single L2 access-policy window covers what
+        # every ADMM iteration re-reads (5 n ld doubles = 84 MB at n = 513, K = 4096; see _run)
+        block = torch.zeros((5, n, ld), dtype=F64, device=dev)
         z = lambda: torch.zeros((n, ld), dtype=F64, device=dev)  # noqa: E731
-        Atb, bA = z(), z()
+        Atb, bA = z(), block[0]
         self._gemm(self.A_dev, self.lda, b_dev, ld, Atb, ld, n, K, m)          # A'b
         self._gemm(self.Qinv, self.ldn, Atb, ld, bA, ld, n, K, n)              # Q A'b   (Q symmetric)
-        return dict(K=K, ld=ld, b_dev=b_dev, reg_dev=reg_dev, eta=eta, bA=bA, state=[z(), z(), z(), z()],
+        return dict(K=K, ld=ld, b_dev=b_dev, reg_dev=reg_dev, eta=eta, bA=bA, block=block,
+                    state=[block[1], block[2], block[3], block[4]],
                     R=torch.zeros((m, ld), dtype=F64, device=dev), fvals=torch.zeros(K, dtype=F64, device=dev))
 
     def _run(self, cols, prep=None):
@@ -122,6 +132,27 @@ class LassoSolver:
         zin, zout = z0, z1
         it = 0
         R, fvals = prep["R"], prep["fvals"]
+        block = prep["block"]
+        ratio = C.c_double(0.0)
+        if self.l2_resident:
+            _abi.call("ipm_l2_persist", block.data_ptr(), block.numel() * 8, C.byref(ratio), None)
+        try:
+            it = self._iterate(prep, alpha, u, zin, zout, partials, norms, host, stop_mult, cols, R, fvals)
+        finally:
+            if self.l2_resident:
+                _abi.call("ipm_l2_persist", None, 0, None, None)
+        self.l2_hit_ratio = ratio.value
+        self._objective(alpha, b_dev, reg_dev, ld, K, R, fvals)
+        return alpha, fvals, it
+
+    def _iterate(self, prep, alpha, u, zin, zout, partials, norms, host, stop_mult, cols, R, fvals):
+        """The ADMM loop (LassoSolver.py:240-337): one fused kernel per iteration, one host read-back per
+        ``check_stop`` iterations.  (Replaying blocks of ``check_stop`` iterations as a CUDA graph was measured on
+        B200 and gave nothing -- 100.6 vs 99.4 us per iteration: the gap between the dependent 95 us kernels is
+        device-side launch latency, which programmatic dependent launch addresses instead, csrc/lasso.cu.)"""
+        n, L = self.n, self.L
+        K, ld, b_dev, reg_dev, eta, bA = (prep[k] for k in ("K", "ld", "b_dev", "reg_dev", "eta", "bA"))
+        it = 0
         for it in range(self.max_iters):
             check = it % self.check_stop == self.check_stop - 1
             L("ipm_lasso_admm_step_f64", self.Qt.data_ptr(), self.ldn, n, K, bA.data_ptr(), eta.data_ptr(), self.rho,
@@ -139,8 +170,7 @@ class LassoSolver:
                 tol_dual = stop_mult + self.EPS_REL * self.rho * u_norm
                 if r_norm < tol_primal and d_norm < tol_dual:
                     break
-        self._objective(alpha, b_dev, reg_dev, ld, K, R, fvals)
-        return alpha, fvals, it
+        return it
 
     def _objective(self, alpha, b_dev, reg_dev, ld, K, R, out):
         """f = 1/(2m) ||A alpha - b||^2 + reg ||alpha[1:]||_1 per column (LassoSolver.py:314-325)."""

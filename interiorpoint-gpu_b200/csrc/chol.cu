@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) potf2_kernel(double* __restrict
   __shared__ double rs[32];      // rsqrt of the current sub-block's pivots
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool vec = !(ld & 1) && !(((uintptr_t)A) & 15);
+  pdl_wait();
   if (vec) {
 #pragma unroll 16
     for (int q = 0; q < NB * NB / 2 / PF_THREADS; ++q) {
@@ -201,7 +202,7 @@ static int launch_potf2(double* Akk, long long ld, int nb, int k0, int* info, cu
     IPM_CUDA_CHECK(cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
     attr_set = true;
   }
-  potf2_kernel<<<1, PF_THREADS, PF_SMEM, st>>>(Akk, ld, nb, k0, info);
+  IPM_CUDA_CHECK(launch_pdl(potf2_kernel, dim3(1), dim3(PF_THREADS), PF_SMEM, st, Akk, ld, nb, k0, info));
   IPM_LAUNCH_CHECK();
   return IPM_OK;
 }
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(256, 1) trsm_panel_kernel(const double* __rest
   const int ncl = min(TP_COLS, ncols - col0);
   const bool vecU = (nb == NB) && !(ldu & 1) && !(((uintptr_t)U11) & 15);
   const bool vecP = (nb == NB) && (ncl == TP_COLS) && !(ldp & 1) && !(((uintptr_t)(P + col0)) & 15);
+  pdl_wait();
   if (vecU) {
 #pragma unroll 16
     for (int q = 0; q < 32; ++q) {
@@ -325,7 +327,8 @@ static int launch_trsm_panel(const double* U11, long long ldu, int nb, double* P
     IPM_CUDA_CHECK(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  trsm_panel_kernel<<<ceil_div(ncols, TP_COLS), 256, smem, st>>>(U11, ldu, nb, P, ldp, ncols);
+  IPM_CUDA_CHECK(launch_pdl(trsm_panel_kernel, dim3(ceil_div(ncols, TP_COLS)), dim3(256), smem, st, U11, ldu, nb, P, ldp,
+                            ncols));
   IPM_LAUNCH_CHECK();
   return IPM_OK;
 }

@@ -28,6 +28,28 @@ namespace ipm {
 
 constexpr int kWarp = 32;
 
+// Programmatic dependent launch (sm_90+).  A kernel launched with launch_pdl() may be scheduled while the previous
+// kernel of the stream is still draining; it must execute pdl_wait() before it touches anything that kernel wrote
+// (a no-op when the launch did not carry the attribute).  Used on the chains of short dependent kernels (Cholesky
+// panel chain, ADMM iterations), where the ~3 us launch latency between kernels is a visible share of the chain.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -168,11 +168,13 @@ extern "C" int ipm_gemm_tn_f64(const double* A, int lda, const double* B, int ld
   if (w) {
     auto kern = gemm::gemm_tn_kernel<true, PlainEpilogue>;
     IPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
-    kern<<<tiles, gemm::THREADS, gemm::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, w, tri_tiles, epi);
+    IPM_CUDA_CHECK(launch_pdl(kern, dim3(tiles), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, M, N, K, w,
+                              tri_tiles, epi));
   } else {
     auto kern = gemm::gemm_tn_kernel<false, PlainEpilogue>;
     IPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
-    kern<<<tiles, gemm::THREADS, gemm::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, nullptr, tri_tiles, epi);
+    IPM_CUDA_CHECK(launch_pdl(kern, dim3(tiles), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, M, N, K,
+                              (const double*)nullptr, tri_tiles, epi));
   }
   IPM_LAUNCH_CHECK();
   return IPM_OK;

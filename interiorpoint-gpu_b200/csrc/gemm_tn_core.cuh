@@ -27,6 +27,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "common.cuh"
+
 namespace ipm {
 namespace gemm {
 
@@ -321,7 +323,7 @@ __device__ __forceinline__ void zero_acc(double (&acc)[MI][NI][2]) {
     for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 }
 
-// Epilogue concept:  template <int MI, int NI> void tile(const double (&acc)[MI][NI][2], int m_base, int n_base,
+// Epilogue concept:  template <int MI, int NI> void tile([const] double (&acc)[MI][NI][2], int m_base, int n_base,
 //                                                        int g8, int l4) const
 //   called once per consumer warp with its (8 MI) x (8 NI) accumulator tile; the functor does its own bounds checks.
 //   acc[i][jn][e] -> row = m_base + i*8 + g8,  col = n_base + jn*8 + 2*l4 + e
@@ -357,6 +359,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // cost a whole extra tile row); functors without such work never get launched with extra CTAs.
     const int ntiles = upper ? tiles_n * (tiles_n + 1) / 2 : tiles_m * tiles_n;
     if ((int)blockIdx.x >= ntiles) {
+      pdl_wait();
       epi.extra((int)blockIdx.x - ntiles);
       return;
     }
@@ -364,6 +367,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const Ring ring = setup_ring(smem_raw);
   int ti, tj;
   decode_tile(blockIdx.x, tiles_m, tiles_n, upper != 0, ti, tj);
+  pdl_wait();  // everything above (barrier init, tile decode) overlaps the previous kernel's drain
   const OneTile sch{ti * BM, tj * TN, (K + BK - 1) / BK};
   Producer<OneTile, ShapeTraits<S>::B_CHUNKS> prod(sch, &tmA, &tmB, ring);
   for (int p = 0; p < PREFETCH; ++p) prod.issue(warp, lane);

@@ -35,6 +35,7 @@ struct LassoEpilogue {
   long long ld;        // common leading dimension of bA / alpha / u / z
   long long ldq;
   int n, K, n_main;    // rows [0, n_main) by DMMA tiles, [n_main, n) by tail CTAs
+  int k_main;          // contraction rows [0, k_main) by DMMA k-tiles, [k_main, n) as rank-1 terms in the epilogue
   double rho;
   int add_bias, positive, want_norms;
   double* partials;    // [gridDim.x][WARPS_PER_CTA][4]
@@ -74,10 +75,34 @@ struct LassoEpilogue {
   }
 
   template <int MI, int NI>
-  __device__ __forceinline__ void tile(const double (&acc)[MI][NI][2], int m_base, int n_base, int g8, int l4) const {
+  __device__ __forceinline__ void tile(double (&acc)[MI][NI][2], int m_base, int n_base, int g8, int l4) const {
     static_assert(MI == 8 && NI == 4, "LassoEpilogue is written for the 128x128 CTA tile");
     Sums s{0.0, 0.0, 0.0, 0.0};
     const bool interior = (m_base + 64 <= n_main) && (n_base + 32 <= K);
+    // contraction rows beyond the last full k-tile (n = 513: the bias row, which would otherwise cost a 33rd k-tile
+    // of 16 rows for one): acc[i][jn][e] += sum_{k >= k_main} Q~[k][row_i] * z[k][col]   (in place: no registers)
+    for (int k = k_main; k < n; ++k) {
+      double qk[MI], zk[NI][2];
+#pragma unroll
+      for (int i = 0; i < MI; ++i) {
+        const int row = m_base + i * 8 + g8;
+        qk[i] = row < n_main ? __ldg(Qt + (long long)k * ldq + row) : 0.0;
+      }
+#pragma unroll
+      for (int jn = 0; jn < NI; ++jn)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = n_base + jn * 8 + 2 * l4 + e;
+          zk[jn][e] = col < K ? z_in[(long long)k * ld + col] : 0.0;
+        }
+#pragma unroll
+      for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int jn = 0; jn < NI; ++jn) {
+          acc[i][jn][0] = fma(qk[i], zk[jn][0], acc[i][jn][0]);
+          acc[i][jn][1] = fma(qk[i], zk[jn][1], acc[i][jn][1]);
+        }
+    }
     if (interior) {
       // batched 16-byte loads: all inputs of two 8-row groups first, then the math, then the stores
 #pragma unroll
@@ -256,7 +281,10 @@ extern "C" int ipm_lasso_admm_step_f64(const double* Qt, int ldq, int n, int K, 
   if (rc) return rc;
   const int tiles = ceil_div(n_main, gemm::BM) * ceil_div(K, gemm::BN);
   const int tail_ctas = n_main < n ? ceil_div(K, TAIL_COLS) : 0;
-  LassoEpilogue epi{bA, eta, alpha, u, z_out, Qt, z_in, ld, ldq, n, K, n_main, rho, add_bias, positive, want_norms,
+  // a k-tile holding <= 4 contraction rows is cheaper as rank-1 terms in the epilogue than as 128 DMMAs per warp
+  const int k_tail = n % gemm::BK;
+  const int k_main = (n > gemm::BK && k_tail > 0 && k_tail <= 4) ? n - k_tail : n;
+  LassoEpilogue epi{bA, eta, alpha, u, z_out, Qt, z_in, ld, ldq, n, K, n_main, k_main, rho, add_bias, positive, want_norms,
                     partials};
   auto kern = gemm::gemm_tn_kernel<false, LassoEpilogue>;
   static bool attr_set = false;
@@ -266,8 +294,11 @@ extern "C" int ipm_lasso_admm_step_f64(const double* Qt, int ldq, int n, int K, 
   }
   const long long nparts = (long long)(tiles + tail_ctas) * WARPS_PER_CTA * 4;
   if (want_norms) IPM_CUDA_CHECK(cudaMemsetAsync(partials, 0, sizeof(double) * nparts, st));
-  // M = n_main rows through the DMMA tiles (K of the contraction is still the full n)
-  kern<<<tiles + tail_ctas, gemm::THREADS, gemm::SMEM_BYTES, st>>>(tmA, tmB, n_main, K, n, nullptr, 0, epi);
+  // M = n_main rows through the DMMA tiles, contraction rows [0, k_main) through the k-tiles
+  // programmatic dependent launch: iteration i+1's CTAs are scheduled while iteration i drains (they wait in
+  // pdl_wait() before touching z / alpha / u)
+  IPM_CUDA_CHECK(launch_pdl(kern, dim3(tiles + tail_ctas), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, n_main,
+                            K, k_main, (const double*)nullptr, 0, epi));
   IPM_LAUNCH_CHECK();
   if (want_norms) {
     lasso_norms_kernel<<<1, 256, 0, st>>>(partials, (int)(nparts / 4), norms_out);

@@ -53,10 +53,13 @@ class Launcher:
         self._base = _abi.lib().ipm_launch_count()
         self.timed_ops = None  # {"op name": [(start_event, end_event, tag), ...]} when bench.py profiles live
         self.tag = None
+        self.stream = None     # raw cudaStream_t handed to every call (None = legacy default stream = torch's default)
+        self.graph_launches = 0  # kernels replayed through CUDA graphs (the library's host-side counter misses them)
 
     def kernel_launches(self):
-        """Kernels launched by libipm_b200 since this launcher was created (process-wide counter)."""
-        return int(_abi.lib().ipm_launch_count() - self._base)
+        """Kernels launched by libipm_b200 since this launcher was created (process-wide counter) plus the kernels
+        replayed through captured graphs."""
+        return int(_abi.lib().ipm_launch_count() - self._base) + self.graph_launches
 
     def timed_range(self, tag):
         """Context manager: CUDA events around a group of launches/collectives (only while bench.py profiles)."""
@@ -83,11 +86,11 @@ class Launcher:
         self.calls += 1
         rec = self.timed_ops.get(name) if self.timed_ops is not None else None
         if rec is None:
-            _abi.call(name, *args, None)
+            _abi.call(name, *args, self.stream)
             return
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _abi.call(name, *args, None)
+        _abi.call(name, *args, self.stream)
         e1.record()
         rec.append((e0, e1, self.tag))
 
