@@ -276,7 +276,7 @@ def main():
     for _ in range(args.warmup):
         one_solve()
     L = solver.launcher
-    L.timed_ops = {"ipm_gemm_tn_f64": [], "range:hessian_formation": []}
+    L.timed_ops = {"ipm_gemm_tn_f64": [], "ipm_syrk_scatter_f64": [], "range:hessian_formation": []}
     launches0 = L.kernel_launches()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -289,9 +289,11 @@ def main():
         barrier()
     ms = e0.elapsed_time(e1)
     launches = L.kernel_launches() - launches0
-    hess = [a.elapsed_time(b) for a, b, tag in L.timed_ops["ipm_gemm_tn_f64"] if tag == "hessian"]
+    hess = [a.elapsed_time(b) for key in ("ipm_gemm_tn_f64", "ipm_syrk_scatter_f64")
+            for a, b, tag in L.timed_ops[key] if tag == "hessian"]
     hform = [a.elapsed_time(b) for a, b, _ in L.timed_ops["range:hessian_formation"]]
     comm_bytes = getattr(solver.ns, "comm_bytes", 0)
+    solver_ns = solver.ns
     L.timed_ops = None
     value_ref = solver.value
     m_local = solver.data.rows_w if socp else solver.data.m
@@ -379,8 +381,11 @@ def main():
                                     "profiles/fp64_peak_r01.json); MEASURED_PEAKS.json has no FP64 entry"},
     }
     if rows_mode and hform:
-        line["hessian_formation"] = {"ms": float(np.mean(hform)), "what": "local partial C_r' diag(w) C_r + NCCL "
-                                     "all-reduce of the n x n buffer + diagonal terms, per Newton step (rank 0)",
+        peer = getattr(solver_ns, "peer", None) is not None
+        line["hessian_formation"] = {"ms": float(np.mean(hform)), "exchange": "peer-memory scatter / reduce / "
+                                     "broadcast kernels (no NCCL)" if peer else "NCCL all-reduce of the n x ld buffer",
+                                     "what": "local partial C_r' diag(w) C_r + exchange + diagonal terms, per Newton "
+                                     "step (rank 0)",
                                      "allreduce_bytes_per_newton_step": comm_bytes / max(newton + args.warmup *
                                                                                         newton / args.steps, 1)}
     if e2e_ms:

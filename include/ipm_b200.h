@@ -55,6 +55,21 @@ int ipm_gemv_n_f64(const double* M, int ld, int rows, int cols, const double* x,
 long long ipm_gemv_t_ws_doubles(int rows, int cols, int nv);
 int ipm_gemv_t_f64(const double* M, int ld, int rows, int cols, const double* V, int nv, int ldv, double* Y, int ldy,
                    double alpha, double beta, double* ws, long long ws_doubles, void* stream);
+/* ---- row-sharded Hessian over peer memory (no reference counterpart; BASELINE north_star / SURVEY 8(e)) ------- */
+/* Partial Hessian alpha * C_r' diag(w) C_r of this rank's K local rows, scattered tile by tile (128 x 128, upper
+ * triangle, tile t owned by rank t % R) into the owners' inboxes over NVLink, with a system-scope arrival flag per
+ * (tile, source).  peer_inbox / peer_flags: HOST arrays of R device pointers (symmetric allocations):
+ * inbox [R sources][slots][128*128] doubles, flags [slots][R] u32.  epoch != 0, identical on all ranks. */
+int ipm_syrk_scatter_f64(const double* C, int ldc, const double* w, int n, int K, double alpha, const double* base,
+                         int ldb, void* const* peer_inbox, void* const* peer_flags, int me, int R, int slots,
+                         unsigned int epoch, void* stream);
+/* For every owned tile: wait for the R partials, add them in rank order (+ tP * P), write the final tile into every
+ * rank's H (upper part) and bump that rank's completion counter; then park the stream until this rank's own counter
+ * reaches done_target (callers add #tiles per step).  All ranks end with bit-identical H. */
+int ipm_hess_reduce_bcast_f64(const double* inbox, const unsigned int* flags, void* const* peer_H,
+                              void* const* peer_done, int ldh, int n, int me, int R, int slots, unsigned int epoch,
+                              unsigned int done_target, const double* P, int ldp, double tP, void* stream);
+
 /* ---- L2 residency ----------------------------------------------------------------------------------------- */
 /* Mark [base, base + bytes) as persisting in L2 for kernels launched on `stream` (bytes == 0: clear).  *ratio_out
  * receives the configured hit ratio (carve-out / window).  No counterpart in the reference: the B200's 126 MB L2

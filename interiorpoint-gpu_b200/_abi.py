@@ -27,6 +27,10 @@ SIGNATURES = {
     "ipm_gemv_n_f64": (_i, [_dp, _i, _i, _i, _dp, _dp, _d, _d, _dp]),
     "ipm_gemv_t_ws_doubles": (_ll, [_i, _i, _i]),
     "ipm_gemv_t_f64": (_i, [_dp, _i, _i, _i, _dp, _i, _i, _dp, _i, _d, _d, _dp, _ll, _dp]),
+    "ipm_syrk_scatter_f64": (_i, [_dp, _i, _dp, _i, _i, _d, _dp, _i, C.POINTER(_dp), C.POINTER(_dp), _i, _i, _i, C.c_uint,
+                                  _dp]),
+    "ipm_hess_reduce_bcast_f64": (_i, [_dp, _dp, C.POINTER(_dp), C.POINTER(_dp), _i, _i, _i, _i, _i, C.c_uint, C.c_uint,
+                                       _dp, _i, _d, _dp]),
     "ipm_l2_persist": (_i, [_dp, C.c_ulonglong, C.POINTER(_d), _dp]),
     "ipm_csr_gemv_f64": (_i, [_dp, _dp, _dp, _i, _dp, _dp, _d, _d, _dp]),
     "ipm_sparse_syrk_f64": (_i, [_i, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp]),

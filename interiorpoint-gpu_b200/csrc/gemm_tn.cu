@@ -179,3 +179,226 @@ extern "C" int ipm_gemm_tn_f64(const double* A, int lda, const double* B, int ld
   IPM_LAUNCH_CHECK();
   return IPM_OK;
 }
+
+// =========================================================================================================
+// Row-sharded Hessian over peer memory (BASELINE north_star: "partial A'DA per GPU + allreduce over
+// NVLink before a replicated factorisation") WITHOUT a separate collective: the SYRK's epilogue is the
+// reduce-scatter, a small second kernel is the reduction + all-gather.
+//
+//   tile t of the upper triangle is OWNED by rank t % R.  Every rank runs the persistent SYRK over its own rows; the
+//   epilogue stores each finished 128x128 partial tile straight into the owner's inbox (peer memory over NVLink /
+//   NVSwitch, plain 16-byte stores) and raises a system-scope flag there.  ipm_hess_reduce_bcast_f64 then, for every
+//   owned tile, waits for the R flags, adds the partials in rank order (one owner, fixed order: all ranks end up with
+//   bit-identical Hessians, which the replicated factorisation relies on), writes the final tile into EVERY rank's H
+//   and bumps that rank's completion counter; ipm_hess_wait_f64 parks the stream until all tiles have arrived.
+//   The partial pushes overlap the SYRK main loop tile by tile; nothing on this path calls NCCL.
+// =========================================================================================================
+namespace ipm {
+
+constexpr int kMaxPeers = 8;
+constexpr int kTileElems = gemm::BM * gemm::BN;
+
+struct PeerPtrs {
+  double* inbox[kMaxPeers];         // rank r's inbox: [src rank][slot][128 * 128]
+  unsigned int* flags[kMaxPeers];   // rank r's arrival flags: [slot][src rank]
+};
+
+__device__ __forceinline__ int upper_tile_index(int ti, int tj, int T) { return ti * T - ti * (ti - 1) / 2 + (tj - ti); }
+
+struct PeerScatterEpilogue {
+  PeerPtrs peers;
+  const double* base;  // optional local n x ldb matrix added to the partial (rank 0: t*P + bound diagonal), upper part
+  long long ldb;
+  int n, T, me, R, slots;
+  double alpha;
+  unsigned int epoch;
+
+  template <int MI, int NI>
+  __device__ __forceinline__ void tile(const double (&acc)[MI][NI][2], int m_base, int n_base, int g8, int l4) const {
+    const int ti = m_base / gemm::BM, tj = n_base / gemm::BN;
+    const int t = upper_tile_index(ti, tj, T);
+    const int owner = t % R, slot = t / R;
+    double* dst = peers.inbox[owner] + ((size_t)me * slots + slot) * kTileElems;
+    const int r0 = m_base - ti * gemm::BM, c0 = n_base - tj * gemm::BN;  // warp offset inside the tile
+#pragma unroll
+    for (int i = 0; i < MI; ++i) {
+      const int rl = r0 + i * 8 + g8, row = ti * gemm::BM + rl;
+#pragma unroll
+      for (int jn = 0; jn < NI; ++jn) {
+        const int cl = c0 + jn * 8 + 2 * l4, col = tj * gemm::BN + cl;
+        double2 v = make_double2(alpha * acc[i][jn][0], alpha * acc[i][jn][1]);
+        if (base) {
+          if (row < n && col < n && col >= row) v.x += base[(long long)row * ldb + col];
+          if (row < n && col + 1 < n && col + 1 >= row) v.y += base[(long long)row * ldb + col + 1];
+        }
+        *reinterpret_cast<double2*>(dst + rl * gemm::BN + cl) = v;
+      }
+    }
+    // all eight warps of the CTA call tile() for the same output tile: publish once they have all stored
+    __threadfence_system();
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    if (threadIdx.x == 0) {
+      unsigned int* f = peers.flags[owner] + (size_t)slot * R + me;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+    }
+  }
+  __device__ __forceinline__ void extra(int) const {}
+};
+
+struct PeerHs {
+  double* H[kMaxPeers];
+  unsigned int* done[kMaxPeers];  // rank r's completion counter
+};
+
+// One CTA per owned tile (grid-stride): wait for the R partials, add them in rank order, write the final tile into
+// every rank's H (upper part only), count it as delivered there.
+__global__ void __launch_bounds__(256) hess_reduce_bcast_kernel(const double* __restrict__ inbox,
+                                                                const unsigned int* __restrict__ flags, PeerHs out,
+                                                                long long ldh, int n, int T, int me, int R, int slots,
+                                                                unsigned int epoch, const double* __restrict__ P,
+                                                                long long ldp, double tP) {
+  const int ntiles = T * (T + 1) / 2;
+  for (int slot = blockIdx.x; slot < slots; slot += gridDim.x) {
+    const int t = slot * R + me;
+    if (t >= ntiles) break;
+    // invert upper_tile_index
+    int ti = 0, first = 0;
+    while (t >= first + (T - ti)) first += T - ti, ++ti;
+    const int tj = ti + (t - first);
+    if (threadIdx.x < R) {
+      const unsigned int* f = flags + (size_t)slot * R + threadIdx.x;
+      unsigned v;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      } while (v != epoch);
+    }
+    __syncthreads();
+    // thread -> 32 double2 of the tile: idx2 = threadIdx.x + 256 q  (row = idx2 / 64, col = 2 (idx2 % 64))
+    double2 sum[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) sum[q] = make_double2(0.0, 0.0);
+    for (int src = 0; src < R; ++src) {
+      const double2* p = reinterpret_cast<const double2*>(inbox + ((size_t)src * slots + slot) * kTileElems);
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const double2 v = __ldcg(p + threadIdx.x + 256 * q);
+        sum[q].x += v.x;
+        sum[q].y += v.y;
+      }
+    }
+    if (P) {  // objective curvature t * P (replicated on every rank, added once by the tile's owner)
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int idx2 = threadIdx.x + 256 * q;
+        const int row = ti * gemm::BM + (idx2 >> 6), col = tj * gemm::BN + 2 * (idx2 & 63);
+        if (row < n && col < n) sum[q].x = fma(tP, P[(long long)row * ldp + col], sum[q].x);
+        if (row < n && col + 1 < n) sum[q].y = fma(tP, P[(long long)row * ldp + col + 1], sum[q].y);
+      }
+    }
+    for (int dstr = 0; dstr < R; ++dstr) {
+      double* Hd = out.H[(dstr + me) % R];  // stagger the destinations over the ranks
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int idx2 = threadIdx.x + 256 * q;
+        const int row = ti * gemm::BM + (idx2 >> 6), col = tj * gemm::BN + 2 * (idx2 & 63);
+        if (row < n) {
+          double* p = Hd + (long long)row * ldh + col;
+          if (col >= row && col + 1 < n) {
+            *reinterpret_cast<double2*>(p) = sum[q];
+          } else {
+            if (col >= row && col < n) p[0] = sum[q].x;
+            if (col + 1 >= row && col + 1 < n) p[1] = sum[q].y;
+          }
+        }
+      }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < R) {
+      unsigned int* d = out.done[threadIdx.x];
+      asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(d) : "memory");
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void hess_wait_kernel(const unsigned int* done, unsigned int target) {
+  unsigned v;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(done) : "memory");
+  } while ((int)(v - target) < 0);  // wrap-safe "v >= target"
+}
+
+}  // namespace ipm
+
+// Partial Hessian of this rank's rows, scattered tile by tile into the owners' inboxes.
+//   C: K x n local rows (ldc), w[K];  base/ldb: optional local addend (upper part);  peers: R device pointers each
+//   (host arrays) to every rank's inbox and flag array;  slots = ceil(#tiles / R);  epoch: same on all ranks, != 0.
+extern "C" int ipm_syrk_scatter_f64(const double* Cm, int ldc, const double* w, int n, int K, double alpha,
+                                    const double* base, int ldb, void* const* peer_inbox, void* const* peer_flags,
+                                    int me, int R, int slots, unsigned int epoch, void* stream) {
+  if (!Cm || !w || !peer_inbox || !peer_flags || n <= 0 || K <= 0 || ldc < n || R < 1 || R > kMaxPeers || me < 0 ||
+      me >= R || epoch == 0)
+    return IPM_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tm;
+  int rc = make_operand_map(&tm, Cm, ldc, K, n);
+  if (rc) return rc;
+  int dev = 0;
+  IPM_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDev) return IPM_ERR_ARG;
+  if (!g_num_sms[dev]) IPM_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev));
+  const int G = g_num_sms[dev];
+  SkSlot* slot = get_sk_slot(dev, st, &rc);
+  if (rc) return rc;
+  if (!slot) return IPM_ERR_ARG;
+  const int T = ceil_div(n, gemm::BN), tiles = T * (T + 1) / 2, ktiles = ceil_div(K, gemm::BK);
+  if (slots < ceil_div(tiles, R)) return IPM_ERR_ARG;
+  const int rem = tiles % G;
+  const long long U = (long long)rem * ktiles;
+  long long P = U / 8;
+  if (P < rem) P = rem;
+  if (P > G) P = G;
+  if (P < 1) P = 1;
+  unsigned sk_epoch = ++g_sk_epoch;
+  if (sk_epoch == 0) sk_epoch = ++g_sk_epoch;
+  gemm::StreamK sk{slot->partials, slot->flags, sk_epoch, (int)P};
+  PeerScatterEpilogue epi;
+  for (int r = 0; r < kMaxPeers; ++r) {
+    epi.peers.inbox[r] = r < R ? (double*)peer_inbox[r] : nullptr;
+    epi.peers.flags[r] = r < R ? (unsigned int*)peer_flags[r] : nullptr;
+  }
+  epi.base = base, epi.ldb = ldb, epi.n = n, epi.T = T, epi.me = me, epi.R = R, epi.slots = slots, epi.alpha = alpha;
+  epi.epoch = epoch;
+  auto kern = gemm::gemm_tn_persistent_kernel<true, PeerScatterEpilogue>;
+  IPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
+  kern<<<G, gemm::THREADS, gemm::SMEM_BYTES, st>>>(tm, tm, n, n, K, w, 1, epi, sk);
+  IPM_LAUNCH_CHECK();
+  return IPM_OK;
+}
+
+// Reduce the owned tiles and deliver them to every rank's H; then wait (on the stream) until this rank's H is complete.
+//   done_target: value this rank's completion counter reaches once all tiles of this step have arrived
+//   (callers add #tiles per step to a running target).  P (optional, n x ldp, replicated): t * P is added by the owner.
+extern "C" int ipm_hess_reduce_bcast_f64(const double* inbox, const unsigned int* flags, void* const* peer_H,
+                                         void* const* peer_done, int ldh, int n, int me, int R, int slots,
+                                         unsigned int epoch, unsigned int done_target, const double* P, int ldp,
+                                         double tP, void* stream) {
+  if (!inbox || !flags || !peer_H || !peer_done || n <= 0 || ldh < n || (ldh & 1) || R < 1 || R > kMaxPeers || me < 0 ||
+      me >= R)
+    return IPM_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  PeerHs out;
+  for (int r = 0; r < kMaxPeers; ++r) {
+    out.H[r] = r < R ? (double*)peer_H[r] : nullptr;
+    out.done[r] = r < R ? (unsigned int*)peer_done[r] : nullptr;
+  }
+  const int T = ceil_div(n, gemm::BN);
+  int grid = slots < 296 ? slots : 296;
+  if (grid < 1) grid = 1;
+  hess_reduce_bcast_kernel<<<grid, 256, 0, st>>>(inbox, flags, out, ldh, n, T, me, R, slots, epoch, P, ldp, tP);
+  IPM_LAUNCH_CHECK();
+  hess_wait_kernel<<<1, 1, 0, st>>>((const unsigned int*)peer_done[me], done_target);
+  IPM_LAUNCH_CHECK();
+  return IPM_OK;
+}

@@ -14,6 +14,9 @@ so every rank takes the same control-flow decisions without a broadcast.  The re
 this follows BASELINE.json's north_star ("partial A'DA per GPU + NCCL allreduce before a replicated factorisation").
 """
 
+import ctypes as C
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -42,6 +45,61 @@ class _RowSharded:
         self.ws.Lsum = torch.zeros(1, dtype=F64, device=self.d.device)
         self.ws.mn = torch.zeros(1, dtype=F64, device=self.d.device)
         self.comm_bytes = 0
+        self.peer = None
+        if os.environ.get("IPM_PEER_HESSIAN", "1") != "0" and self.world <= 8:
+            self._setup_peer_memory()
+
+    # ------------------------------------------------------------------ Hessian exchange over peer memory
+    def _setup_peer_memory(self):
+        """Symmetric (peer-mapped) allocations for the fused SYRK + reduce-scatter + all-gather (csrc/gemm_tn.cu,
+        ipm_syrk_scatter_f64 / ipm_hess_reduce_bcast_f64): the Hessian buffer itself, an inbox of partial tiles and the
+        arrival flags / completion counter.  Falls back to the NCCL all-reduce when the build of torch or the box has
+        no symmetric memory (all ranks take the same decision: the probe result is MIN-reduced)."""
+        ok = torch.ones(1, dtype=torch.int32, device=self.d.device)
+        st = None
+        try:
+            import torch.distributed._symmetric_memory as symm
+
+            grp = self.group if self.group is not None else dist.group.WORLD
+            n, ws = self.d.n, self.ws
+            T = (n + 127) // 128
+            slots = (T * (T + 1) // 2 + self.world - 1) // self.world
+            Hs = symm.empty((ws.H.shape[0], ws.H.shape[1]), dtype=F64, device=self.d.device)
+            inbox = symm.empty((self.world * slots * 128 * 128,), dtype=F64, device=self.d.device)
+            sig = symm.empty((slots * self.world + 64,), dtype=torch.int32, device=self.d.device)
+            Hs.zero_()
+            sig.zero_()
+            hH, hI, hS = (symm.rendezvous(t, grp.group_name) for t in (Hs, inbox, sig))
+            st = dict(slots=slots, tiles=T * (T + 1) // 2, H=Hs, inbox=inbox, sig=sig, handles=(hH, hI, hS),
+                      done_off=slots * self.world, epoch=0, target=0)
+            R = self.world
+            st["p_inbox"] = (C.c_void_p * R)(*[int(p) for p in hI.buffer_ptrs])
+            st["p_flags"] = (C.c_void_p * R)(*[int(p) for p in hS.buffer_ptrs])
+            st["p_H"] = (C.c_void_p * R)(*[int(p) for p in hH.buffer_ptrs])
+            st["p_done"] = (C.c_void_p * R)(*[int(p) + 4 * st["done_off"] for p in hS.buffer_ptrs])
+        except Exception as e:  # noqa: BLE001 -- any failure means "no peer path on this box"
+            ok.zero_()
+            self.peer_error = repr(e)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 1:
+            self.peer = st
+            self.ws.H = st["H"]  # the factorisation runs in the peer-mapped buffer the owners write into
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+
+    def _peer_hessian(self, rows_ptr, ld, K, w_ptr, P=None, ldp=0, tP=0.0):
+        """H (upper, n x n block of ws.H) = sum over ranks of rows' diag(w) rows [+ tP * P], identical bits on every
+        rank, without NCCL."""
+        pr, ws, L, d = self.peer, self.ws, self.L, self.d
+        pr["epoch"] += 1
+        pr["target"] = (pr["target"] + pr["tiles"]) & 0xFFFFFFFF
+        L.tag = "hessian"
+        L("ipm_syrk_scatter_f64", rows_ptr, ld, w_ptr, d.n, K, 1.0, None, 0, pr["p_inbox"], pr["p_flags"], self.rank,
+          self.world, pr["slots"], pr["epoch"])
+        L.tag = None
+        L("ipm_hess_reduce_bcast_f64", pr["inbox"].data_ptr(), pr["sig"].data_ptr(), pr["p_H"], pr["p_done"], ws.ldh,
+          d.n, self.rank, self.world, pr["slots"], pr["epoch"], pr["target"], _abi.ptr(P), ldp, tP)
+        self.comm_bytes += 2 * pr["tiles"] * 128 * 128 * 8 * (self.world - 1) // self.world
 
     def _sum(self, t):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
@@ -83,6 +141,17 @@ class ShardedLinearNewton(_RowSharded, LinearNewton):
     def _hessian_impl(self, t):
         d, ws, L = self.d, self.ws, self.L
         n, m = d.n, d.m
+        if self.peer is not None and m > 0:
+            qp = d.is_qp and not self.phase1
+            if self.rank != 0:
+                ws.hdiag.zero_()  # bound rows belong to rank 0
+            self._sum(ws.hdiag)
+            self._peer_hessian(d.C.data_ptr(), d.ldc, m, ws.w.data_ptr(), d.P if qp else None, d.ldp if qp else 0,
+                               t if qp else 0.0)
+            shift = self.shift + (1e-9 if self.use_psd_condition else 0.0)
+            L("ipm_hess_finish_f64", ws.H.data_ptr(), ws.ldh, n, ws.hdiag.data_ptr(),
+              ws.hxs.data_ptr() if self.phase1 else None, (ws.red.data_ptr() + 24) if self.phase1 else None, shift)
+            return
         beta = 0.0
         if d.is_qp and not self.phase1 and self.rank == 0:
             L("ipm_scale_copy_upper_f64", ws.H.data_ptr(), ws.ldh, d.P.data_ptr(), d.ldp, n, t)
@@ -116,10 +185,25 @@ class ShardedConeNewton(_RowSharded, ConeNewton):
     def __init__(self, data, group=None, **kw):
         super().__init__(data, **kw)
         self._init_sharding(group)
+        flag = torch.tensor([1 if data.nbounds else 0], dtype=torch.int32, device=data.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        self.bounds_anywhere = bool(int(flag.item()))
 
     def _hessian_impl(self, t):
         d, ws, L = self.d, self.ws, self.L
         n = d.n
+        if self.peer is not None:
+            qp = d.is_qp and not self.phase1
+            if self.bounds_anywhere:
+                if not d.nbounds:
+                    ws.hdiag.zero_()
+                self._sum(ws.hdiag)
+            self._peer_hessian(d.W.data_ptr(), d.ldw, d.rows_w, ws.wts.data_ptr(), d.P if qp else None,
+                               d.ldp if qp else 0, t if qp else 0.0)
+            shift = self.shift + (1e-9 if self.use_psd_condition else 0.0)
+            L("ipm_hess_finish_f64", ws.H.data_ptr(), ws.ldh, n, ws.hdiag.data_ptr() if self.bounds_anywhere else None,
+              ws.hxs.data_ptr() if self.phase1 else None, (ws.red.data_ptr() + 24) if self.phase1 else None, shift)
+            return
         beta = 0.0
         if d.is_qp and not self.phase1 and self.rank == 0:
             L("ipm_scale_copy_upper_f64", ws.H.data_ptr(), ws.ldh, d.P.data_ptr(), d.ldp, n, t)

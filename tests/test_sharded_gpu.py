@@ -31,7 +31,7 @@ def _worker(rank, world, port, name, q):
     val = s.solve()
     p1 = s.phase1_solver.inner_iters if case["phase1_inner_iters"] is not None else None
     if rank == 0:
-        q.put((val, s.inner_iters, p1, np.asarray(s.xstar)))
+        q.put((val, s.inner_iters, p1, np.asarray(s.xstar), s.ns.peer is not None, getattr(s.ns, "peer_error", None)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -50,10 +50,12 @@ def test_row_sharded_matches_reference(name):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q)) for r in range(2)]
     for p in procs:
         p.start()
-    val, iters, p1, x = q.get(timeout=300)
+    val, iters, p1, x, peer, peer_error = q.get(timeout=300)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+    # the Hessian exchange ran over peer memory (fused SYRK + reduce-scatter + all-gather), not the NCCL fallback
+    assert peer, peer_error
     assert val == pytest.approx(case["value"], rel=1e-6, abs=1e-9)
     assert len(iters) == len(case["inner_iters"])
     assert all(abs(a - b) <= 2 or b >= 50 for a, b in zip(iters, case["inner_iters"])), (iters, case["inner_iters"])
