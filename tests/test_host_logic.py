@@ -87,3 +87,53 @@ def test_host_array_answers_get():
     a = sb.HostArray(np.arange(3.0))
     np.testing.assert_array_equal(a.get(), np.arange(3.0))
     assert float(a.sum()) == 3.0
+
+
+def test_sparse_rows_segment_map_on_cpu():
+    """engine.SparseRows: the host-built CSR pair and the Hessian segment map, replayed in NumPy
+    exactly as ipm_csr_gemv_f64 / ipm_sparse_syrk_f64 consume them, against the dense formulas."""
+    import torch
+
+    from ipm_b200.engine import SparseRows, _looks_sparse
+
+    rs = np.random.RandomState(11)
+    m, n = 300, 270
+    Cm = np.where(rs.rand(m, n) < 0.012, rs.uniform(-2, 2, (m, n)), 0.0)
+    Cm[7] = 0.0
+    Cm[8, :] = 0.0
+    Cm[8, 5] = 1.5  # a single-entry row
+    assert _looks_sparse(Cm) and not _looks_sparse(rs.rand(200, 300))
+    sp = SparseRows(Cm, n, torch.device("cpu"))
+    rowptr, col, val = sp.rowptr.numpy(), sp.col.numpy(), sp.val.numpy()
+    x, v, w = rs.randn(n), rs.randn(m), rs.uniform(0.1, 5.0, m)
+    y = np.array([val[rowptr[r]:rowptr[r + 1]] @ x[col[rowptr[r]:rowptr[r + 1]]] for r in range(m)])
+    np.testing.assert_allclose(y, Cm @ x, rtol=1e-13, atol=1e-13)
+    trp, tc, tv = sp.t_rowptr.numpy(), sp.t_col.numpy(), sp.t_val.numpy()
+    g = np.array([tv[trp[j]:trp[j + 1]] @ v[tc[trp[j]:trp[j + 1]]] for j in range(n)])
+    np.testing.assert_allclose(g, Cm.T @ v, rtol=1e-13, atol=1e-13)
+    segptr, seg_row, seg_prod = sp.segptr.numpy(), sp.seg_row.numpy(), sp.seg_prod.numpy()
+    oi, oj = sp.out_i.numpy(), sp.out_j.numpy()
+    H = np.zeros((n, n))
+    for e in range(sp.nout):
+        k0, k1 = segptr[e], segptr[e + 1]
+        assert np.all(np.diff(seg_row[k0:k1]) > 0)       # ascending rows: fixed summation order on the device
+        H[oi[e], oj[e]] += w[seg_row[k0:k1]] @ seg_prod[k0:k1]
+    assert np.all(oi <= oj) and len(set(zip(oi, oj))) == sp.nout
+    np.testing.assert_allclose(H, np.triu((Cm * w[:, None]).T @ Cm), rtol=1e-12, atol=1e-13)
+
+
+def test_miplib_loader_validates_shapes(tmp_path):
+    from ipm_b200 import miplib
+
+    prob = miplib.synthetic_network_lp(seed=1, n=60, p=4, m=20, density=0.05)
+    f = tmp_path / "ok.npy"
+    miplib.save_lp(f, **prob)
+    got = miplib.load_lp(f)
+    assert set(got) == set(miplib.FIELDS) and got["A"].shape == (4, 60) and got["C"].shape == (20, 60)
+    no_eq = dict(prob, A=None, b=None)
+    miplib.save_lp(f, **no_eq)
+    assert miplib.load_lp(f)["A"] is None and miplib.load_lp(f)["b"] is None
+    bad = dict(prob, d=prob["d"][:-1])
+    miplib.save_lp(f, **bad)
+    with pytest.raises(ValueError):
+        miplib.load_lp(f)
