@@ -139,13 +139,13 @@ extern "C" int ipm_gemm_tn_f64(const double* A, int lda, const double* B, int ld
   if (dev >= 0 && dev < kMaxDev && !g_num_sms[dev])
     IPM_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev));
   const int G = (dev >= 0 && dev < kMaxDev) ? g_num_sms[dev] : 0;
-  if (G > 0 && ktiles >= 64 && tiles > G) {
+  if (G > 0 && ktiles >= 1024 / gemm::BK && tiles > G) {
     SkSlot* slot = get_sk_slot(dev, st, &rc);
     if (rc) return rc;
     if (slot) {
       const int rem = tiles % G;
       const long long U = (long long)rem * ktiles;
-      long long P = U / 8;  // at least 8 k-tiles (K = 128) per stream-K slice
+      long long P = U / (128 / gemm::BK);  // at least K = 128 per stream-K slice
       if (P < rem) P = rem;
       if (P > G) P = G;
       if (P < 1) P = 1;
@@ -356,7 +356,7 @@ extern "C" int ipm_syrk_scatter_f64(const double* Cm, int ldc, const double* w, 
   if (slots < ceil_div(tiles, R)) return IPM_ERR_ARG;
   const int rem = tiles % G;
   const long long U = (long long)rem * ktiles;
-  long long P = U / 8;
+  long long P = U / (128 / gemm::BK);
   if (P < rem) P = rem;
   if (P > G) P = G;
   if (P < 1) P = 1;

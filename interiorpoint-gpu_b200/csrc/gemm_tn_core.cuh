@@ -9,7 +9,7 @@
 //
 // Blackwell mapping: tcgen05.mma has no FP64 kind, so the math is DMMA (mma.sync.m8n8k4.f64, the only
 // FP64 tensor shape sm_100a issues natively -- m16n8k{4,8,16} lower to it); operand tiles are staged by
-// TMA (cp.async.bulk.tensor.2d, 128B swizzle) into a 6-stage mbarrier ring and consumed by 8 MMA warps (warp
+// TMA (cp.async.bulk.tensor.2d, 128B swizzle) into a 3-stage mbarrier ring of 32-row k-tiles and consumed by 8 MMA warps (warp
 // tile 64x32, 64 FP64 accumulators per thread).  There is no dedicated producer warp: a ninth warp would put
 // three warps on one SM sub-partition and cap every thread at 168 registers (16K registers per sub-partition),
 // which spills the double-buffered fragments.  Instead every warp keeps the ring PREFETCH k-tiles ahead of its
@@ -17,10 +17,10 @@
 // k-tile, so the producer work is symmetric (a single producing warp becomes the pace-setter of the CTA: the
 // other seven run into the prefetch horizon and idle their DMMA pipes).
 //
-// Shared-memory tile layout (per operand, per stage): 8 column chunks of [16 k-rows][16 doubles = 128 B],
+// Shared-memory tile layout (per operand, per stage): 8 column chunks of [32 k-rows][16 doubles = 128 B],
 // each written by one TMA box with CU_TENSOR_MAP_SWIZZLE_128B: 16-byte unit c of row r lands at unit
 // c ^ (r & 7).  An m8n8k4 fragment needs (k = lane&3, m = lane>>2); mapping the four k of one MMA to rows
-// {0,2,4,6} / {1,3,5,7} / {8,..} / {9,..} makes the 16 lanes of each half-warp hit 16 distinct 8-byte bank
+// {0,2,4,6} / {1,3,5,7} / {8,..} / {9,..} / ... makes the 16 lanes of each half-warp hit 16 distinct 8-byte bank
 // pairs, i.e. conflict-free LDS.64 (the k order inside a tile is arbitrary as long as A and B agree).
 #pragma once
 #include <cuda.h>
@@ -32,12 +32,15 @@
 namespace ipm {
 namespace gemm {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 6;
-constexpr int PREFETCH = STAGES - 2;  // k-tiles in flight ahead of warp 0's consumption
+constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
+constexpr int KGROUPS = BK / 4;        // m8n8k4 k-groups per k-tile
+constexpr int PREFETCH = STAGES - 1;   // k-tiles issued ahead of a warp's own consumption
+constexpr int ISSUE_AT = KGROUPS / 2;  // a warp tops the ring up in the MIDDLE of its k-tile: the slot it refills was
+                                       // released by everybody half a k-tile ago, so the empty-wait rarely spins
 constexpr int CONSUMER_WARPS = 8;
 constexpr int THREADS = CONSUMER_WARPS * 32;
-constexpr int CHUNK_BYTES = BK * 128;               // one TMA box: 16 rows x 128 B
-constexpr int OPERAND_BYTES = (BM / 16) * CHUNK_BYTES;  // 16 KiB
+constexpr int CHUNK_BYTES = BK * 128;               // one TMA box: BK rows x 128 B
+constexpr int OPERAND_BYTES = (BM / 16) * CHUNK_BYTES;  // 32 KiB
 constexpr int STAGE_BYTES = 2 * OPERAND_BYTES;      // A + B
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES * 8;
 
@@ -256,10 +259,11 @@ __device__ __forceinline__ void load_frags(double (&a)[S::MI], double (&b)[S::NI
   }
 }
 
-__device__ __forceinline__ void load_weights(double (&wk)[4], const double* __restrict__ w, int kt, int K, int l4) {
+// Row weights of the four k-groups 4h .. 4h+3 (h = half-tile index, counted over the whole contraction: 16 rows).
+__device__ __forceinline__ void load_weights(double (&wk)[4], const double* __restrict__ w, int half, int K, int l4) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int kk = kt * BK + (j >> 1) * 8 + 2 * l4 + (j & 1);
+    const int kk = half * 16 + (j >> 1) * 8 + 2 * l4 + (j & 1);
     wk[j] = kk < K ? __ldg(w + kk) : 0.0;
   }
 }
@@ -271,8 +275,9 @@ template <bool HAS_W, class S, class Prod>
 __device__ __forceinline__ void consume_ktiles(double (&acc)[S::MI][S::NI][2], const Ring& ring, const LaneMap& lm,
                                                const double* __restrict__ w, int K, int kt_begin, int kt_end,
                                                uint32_t& it, int warp, int lane, Prod& prod) {
+  static_assert(KGROUPS == 8, "the weight double-buffering below assumes two 16-row halves per k-tile");
   double wk[4], wn[4];
-  if (HAS_W) load_weights(wk, w, kt_begin, K, lm.l4);
+  if (HAS_W) load_weights(wk, w, 2 * kt_begin, K, lm.l4);
   uint32_t s = it % STAGES;
   mbar_wait(ring.full0 + 8 * s, (it / STAGES) & 1);
   uint32_t st = ring.tiles0 + s * STAGE_BYTES;
@@ -280,13 +285,14 @@ __device__ __forceinline__ void consume_ktiles(double (&acc)[S::MI][S::NI][2], c
   load_frags<S>(a[0], b[0], st, lm, 0);
   for (int kt = kt_begin; kt < kt_end; ++kt) {
     const bool has_next = kt + 1 < kt_end;
-    if (HAS_W && has_next) load_weights(wn, w, kt + 1, K, lm.l4);
-    prod.issue(warp, lane);
     uint32_t s_next = s, st_next = st;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < KGROUPS; ++j) {
       const int cur = j & 1, nxt = cur ^ 1;
-      if (j < 3) {
+      if (HAS_W && j == 0) load_weights(wn, w, 2 * kt + 1, K, lm.l4);                  // second half of this tile
+      if (HAS_W && j == 4 && has_next) load_weights(wn, w, 2 * kt + 2, K, lm.l4);      // first half of the next
+      if (j == ISSUE_AT) prod.issue(warp, lane);
+      if (j < KGROUPS - 1) {
         load_frags<S>(a[nxt], b[nxt], st, lm, j + 1);
       } else if (has_next) {
         s_next = (it + 1) % STAGES;
@@ -296,22 +302,22 @@ __device__ __forceinline__ void consume_ktiles(double (&acc)[S::MI][S::NI][2], c
       }
       if (HAS_W) {
 #pragma unroll
-        for (int i = 0; i < S::NI; ++i) b[cur][i] *= wk[j];
+        for (int i = 0; i < S::NI; ++i) b[cur][i] *= wk[j & 3];
       }
 #pragma unroll
       for (int i = 0; i < S::MI; ++i)
 #pragma unroll
         for (int jn = 0; jn < S::NI; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], a[cur][i], b[cur][jn]);
+      if (HAS_W && (j & 3) == 3) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) wk[q] = wn[q];
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(ring.empty0 + 8 * s);
     ++it;
     s = s_next;
     st = st_next;
-    if (HAS_W) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) wk[j] = wn[j];
-    }
   }
 }
 
