@@ -133,33 +133,42 @@ extern "C" int ipm_gemm_tn_f64(const double* A, int lda, const double* B, int ld
   const int ktiles = ceil_div(K, gemm::BK);
   PlainEpilogue epi{D, ldd, M, N, alpha, beta, upper};
 
-  // Long-K contraction with more tiles than SMs: persistent CTAs + stream-K remainder (no partial last wave).
+  // Persistent CTAs + stream-K in the two cases where one CTA per tile leaves SMs idle:
+  //   * long-K contraction with more tiles than SMs (the Hessian): no partial last wave;
+  //   * fewer tiles than SMs (the Cholesky panel chain's band / next-block updates once the trailing matrix is
+  //     small, the Schur complement): the k-tiles of every tile are spread over all SMs, so a 128 x rest update with
+  //     K = 128 takes one k-tile per SM plus the fix-up instead of a whole tile on a quarter of the SMs.
   int dev = 0;
   IPM_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev >= 0 && dev < kMaxDev && !g_num_sms[dev])
     IPM_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev));
   const int G = (dev >= 0 && dev < kMaxDev) ? g_num_sms[dev] : 0;
-  if (G > 0 && ktiles >= 1024 / gemm::BK && tiles > G) {
+  const bool many = tiles > G && ktiles >= 1024 / gemm::BK;
+  const bool few = tiles < G && ktiles >= 2 && (long long)tiles * ktiles >= 8;
+  if (G > 0 && (many || few)) {
     SkSlot* slot = get_sk_slot(dev, st, &rc);
     if (rc) return rc;
     if (slot) {
       const int rem = tiles % G;
       const long long U = (long long)rem * ktiles;
-      long long P = U / (128 / gemm::BK);  // at least K = 128 per stream-K slice
+      long long P = many ? U / (128 / gemm::BK) : U;  // many: at least K = 128 per stream-K slice; few: one k-tile
       if (P < rem) P = rem;
       if (P > G) P = G;
       if (P < 1) P = 1;
+      const int grid = many ? G : (int)P;
       unsigned epoch = ++g_sk_epoch;
       if (epoch == 0) epoch = ++g_sk_epoch;
       gemm::StreamK sk{slot->partials, slot->flags, epoch, (int)P};
       if (w) {
         auto kern = gemm::gemm_tn_persistent_kernel<true, PlainEpilogue>;
         IPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
-        kern<<<G, gemm::THREADS, gemm::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, w, tri_tiles, epi, sk);
+        IPM_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, M, N, K, w,
+                                  tri_tiles, epi, sk));
       } else {
         auto kern = gemm::gemm_tn_persistent_kernel<false, PlainEpilogue>;
         IPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
-        kern<<<G, gemm::THREADS, gemm::SMEM_BYTES, st>>>(tmA, tmB, M, N, K, nullptr, tri_tiles, epi, sk);
+        IPM_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, M, N, K,
+                                  (const double*)nullptr, tri_tiles, epi, sk));
       }
       IPM_LAUNCH_CHECK();
       return IPM_OK;

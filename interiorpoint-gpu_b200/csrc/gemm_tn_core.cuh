@@ -445,6 +445,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     if (len > first) sch.seg_tile[1] = dp_tiles + ta + 1, sch.seg_k0[1] = 0, sch.seg_k1[1] = len - first, sch.nseg = 2;
   }
   const Ring ring = setup_ring(smem_raw);
+  pdl_wait();
   Producer<PersistentSchedule> prod(sch, &tmA, &tmB, ring);
   for (int p = 0; p < PREFETCH; ++p) prod.issue(warp, lane);
   using S = Shape128x128;
