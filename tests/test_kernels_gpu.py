@@ -287,3 +287,52 @@ def test_sparse_rows_kernels():
     scale = np.abs(Cm * w[:, None]).T @ np.abs(Cm) + np.abs(H0[:, :n])
     assert np.max(np.abs(got[:, :n] - ref[:, :n]) / (scale + 1e-300)) < 1e-14
     np.testing.assert_array_equal(got[:, n:], H0[:, n:])
+
+
+@pytest.mark.parametrize("n,m,R", [(300, 500, 2), (1100, 900, 3), (257, 64, 1)])
+def test_peer_hessian_kernels_emulated_ranks(n, m, R):
+    """ipm_syrk_scatter_f64 + ipm_hess_reduce_bcast_f64 (row-sharded Hessian over peer memory) with R ranks emulated
+    on ONE device: every rank has its own inbox / flags / H / counter and its own stream, the "peer" pointers are
+    simply the other ranks' buffers.  All R Hessians must equal C' diag(w) C + tP * P and be bit-identical."""
+    rs = np.random.RandomState(n + m)
+    Cm = rs.uniform(-2, 2, (m, n))
+    w = 10.0 ** rs.uniform(-3, 3, m)
+    Pm = rs.uniform(-1, 1, (n, n))
+    Pm = Pm + Pm.T
+    tP = 0.75
+    T = (n + 127) // 128
+    tiles = T * (T + 1) // 2
+    slots = (tiles + R - 1) // R
+    ldh = (n + 15) // 16 * 16
+    bounds = [m * r // R for r in range(R + 1)]
+    Cd = [padded(Cm[bounds[r]:bounds[r + 1]]) for r in range(R)]
+    wd = [dev(w[bounds[r]:bounds[r + 1]]) for r in range(R)]
+    Pd, ldp = padded(Pm)
+    inbox = [torch.zeros(R * slots * 128 * 128, dtype=torch.float64, device="cuda") for _ in range(R)]
+    sig = [torch.zeros(slots * R + 64, dtype=torch.int32, device="cuda") for _ in range(R)]
+    H = [torch.full((n, ldh), 7.0, dtype=torch.float64, device="cuda") for _ in range(R)]
+    arr = lambda ts, off=0: (C.c_void_p * R)(*[t.data_ptr() + off for t in ts])  # noqa: E731
+    p_inbox, p_flags, p_H, p_done = arr(inbox), arr(sig), arr(H), arr(sig, 4 * slots * R)
+    # Emulation on one device and ONE stream: all ranks scatter first, then every rank reduces its owned tiles (all the
+    # flags it waits for are already raised) with done_target = 0, i.e. without parking the stream; the completion
+    # counters are checked on the host instead.  (Real ranks run these concurrently on their own devices.)
+    for step in (1, 2):  # two consecutive "Newton steps": epochs and the running completion counters
+        for r in range(R):
+            Cr, ldc = Cd[r]
+            _abi.call("ipm_syrk_scatter_f64", Cr.data_ptr(), ldc, wd[r].data_ptr(), n, bounds[r + 1] - bounds[r], 1.0,
+                      None, 0, p_inbox, p_flags, r, R, slots, step, None)
+        for r in range(R):
+            _abi.call("ipm_hess_reduce_bcast_f64", inbox[r].data_ptr(), sig[r].data_ptr(), p_H, p_done, ldh, n, r, R,
+                      slots, step, 0, Pd.data_ptr(), ldp, tP, None)
+        torch.cuda.synchronize()
+        for r in range(R):
+            assert int(sig[r][slots * R].item()) == step * tiles   # every tile of this step was delivered to rank r
+    ref = np.triu((Cm * w[:, None]).T @ Cm + tP * Pm)
+    scale = np.abs(Cm * w[:, None]).T @ np.abs(Cm) + np.abs(tP * Pm)
+    got0 = H[0].cpu().numpy()
+    iu = np.triu_indices(n)
+    assert np.max(np.abs(got0[:, :n][iu] - ref[iu]) / scale[iu]) < 1e-13
+    il = np.tril_indices(n, -1)
+    assert np.all(got0[:, :n][il] == 7.0) and np.all(got0[:, n:] == 7.0)   # strict lower triangle / padding untouched
+    for r in range(1, R):
+        assert torch.equal(H[r], H[0])                                       # bit-identical on every "rank"
