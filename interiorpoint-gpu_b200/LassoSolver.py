@@ -98,8 +98,9 @@ class LassoSolver:
         """Host->device transfer of the chunk's b / reg and the cached products A'b, Q A'b (LassoSolver.py:193-216
         for one chunk -- done once in the constructor, like the reference -- and :352-390 per chunk)."""
         dev, n, m = self.device, self.n, self.m
-        b = np.ascontiguousarray(self.b_host[:, cols])
-        reg = np.ascontiguousarray(self.reg_host[cols])
+        whole = len(cols) == self.num_samples  # one chunk: no fancy-index copy of the 67 MB right-hand side
+        b = self.b_host if whole else np.ascontiguousarray(self.b_host[:, cols])
+        reg = self.reg_host if whole else np.ascontiguousarray(self.reg_host[cols])
         K = b.shape[1]
         ld = _round_up(K, 16)
         b_dev, _ = to_dev_matrix(b, dev)
