@@ -146,6 +146,29 @@ def cpu_sample(prob, newton_steps):
     return sum(o.inner_iters), dt
 
 
+def blas_info():
+    """BLAS vendor / thread count behind NumPy on this host (report them with the CPU baseline)."""
+    try:
+        from threadpoolctl import threadpool_info
+
+        libs = [f"{i.get('internal_api', '?')} {i.get('version', '')} x{i.get('num_threads', '?')}"
+                for i in threadpool_info() if i.get("user_api") == "blas"]
+        return "; ".join(libs) or "unknown BLAS"
+    except Exception:
+        return "unknown BLAS"
+
+
+def blas_threads():
+    """Threads the NumPy BLAS actually uses (the `cores` of the CPU baseline); os.cpu_count() if unknown."""
+    try:
+        from threadpoolctl import threadpool_info
+
+        n = [i.get("num_threads") for i in threadpool_info() if i.get("user_api") == "blas"]
+        return int(max(n)) if n else os.cpu_count()
+    except Exception:
+        return os.cpu_count()
+
+
 def lasso_workload(K):
     """BASELINE configs[4]: A 2048x512 (+bias), K problems, generator of testSolver.py:1096-1104 (seed 5)."""
     n, rows = 512, 2048
@@ -207,7 +230,7 @@ def run_reference(args):
             steps += k
     total = sum(times)
     val = steps / total
-    cores = os.cpu_count()
+    cores = blas_threads()
     line = {
         "impl": "reference", "metric": "newton_steps_per_s", "value": val, "unit": "Newton steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
@@ -215,8 +238,8 @@ def run_reference(args):
         "config": {"workload": f"dense LP n={args.n} m={m} box+-3, warm start (BASELINE configs[1])",
                    "sample": "one full-size Newton iteration per step"},
         "cpu_baseline": {"value": val, "unit": "Newton steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} full-size Newton iterations of the oracle (NumPy/SciPy, BLAS threads = "
-                                   f"{cores})"},
+                         "sample": f"{steps} full-size Newton iterations of the oracle (NumPy/SciPy; BLAS: "
+                                   f"{blas_info()})"},
         "e2e": {"value": val, "unit": "Newton steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -405,9 +428,9 @@ def main():
                          "note": "2 n^2 K flop per ADMM iteration over the whole solve() incl. stop checks"}}
     if not args.no_cpu_baseline and world == 1:
         k, dt = cpu_sample(prob, args.cpu_newton_steps)
-        line["cpu_baseline"] = {"value": k / dt, "unit": "Newton steps/s", "cores": os.cpu_count(), "kind": "port",
+        line["cpu_baseline"] = {"value": k / dt, "unit": "Newton steps/s", "cores": blas_threads(), "kind": "port",
                                 "sample": f"{k} full-size Newton iterations (first centering step) of the oracle, "
-                                          f"{dt:.1f} s"}
+                                          f"{dt:.1f} s; NumPy BLAS: {blas_info()}"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
