@@ -116,6 +116,25 @@ SkSlot* get_sk_slot(int dev, cudaStream_t st, int* rc) {
 }
 }  // namespace
 
+// Library-internal (not part of the public header): stream-K scratch of `stream` for other translation units
+// (lasso.cu).  *partials / *flags are null when no slot is free.
+extern "C" int ipm_internal_sk_slot(void* stream, double** partials, unsigned int** flags, unsigned int* epoch,
+                                    int* num_sms) {
+  int dev = 0, rc = IPM_OK;
+  IPM_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDev) return IPM_ERR_ARG;
+  if (!g_num_sms[dev]) IPM_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev));
+  SkSlot* slot = get_sk_slot(dev, (cudaStream_t)stream, &rc);
+  if (rc) return rc;
+  *partials = slot ? slot->partials : nullptr;
+  *flags = slot ? slot->flags : nullptr;
+  unsigned e = ++g_sk_epoch;
+  if (e == 0) e = ++g_sk_epoch;
+  *epoch = e;
+  *num_sms = g_num_sms[dev];
+  return IPM_OK;
+}
+
 extern "C" int ipm_gemm_tn_f64(const double* A, int lda, const double* B, int ldb, const double* w, double alpha,
                                double beta, double* D, int ldd, int M, int N, int K, int upper, void* stream) {
   if (!A || !B || !D || M <= 0 || N <= 0 || K < 0 || lda < M || ldb < N || ldd < N) return IPM_ERR_ARG;
@@ -158,7 +177,7 @@ extern "C" int ipm_gemm_tn_f64(const double* A, int lda, const double* B, int ld
       const int grid = many ? G : (int)P;
       unsigned epoch = ++g_sk_epoch;
       if (epoch == 0) epoch = ++g_sk_epoch;
-      gemm::StreamK sk{slot->partials, slot->flags, epoch, (int)P};
+      gemm::StreamK sk{slot->partials, slot->flags, epoch, (int)P, 0};
       if (w) {
         auto kern = gemm::gemm_tn_persistent_kernel<true, PlainEpilogue>;
         IPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
@@ -371,7 +390,7 @@ extern "C" int ipm_syrk_scatter_f64(const double* Cm, int ldc, const double* w, 
   if (P < 1) P = 1;
   unsigned sk_epoch = ++g_sk_epoch;
   if (sk_epoch == 0) sk_epoch = ++g_sk_epoch;
-  gemm::StreamK sk{slot->partials, slot->flags, sk_epoch, (int)P};
+  gemm::StreamK sk{slot->partials, slot->flags, sk_epoch, (int)P, 0};
   PeerScatterEpilogue epi;
   for (int r = 0; r < kMaxPeers; ++r) {
     epi.peers.inbox[r] = r < R ? (double*)peer_inbox[r] : nullptr;

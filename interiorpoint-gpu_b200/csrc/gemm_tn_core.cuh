@@ -401,6 +401,7 @@ struct StreamK {
   unsigned int* flags;    // gridDim.x flags; a slot is valid when its flag equals `epoch`
   unsigned int epoch;
   int ctas;               // CTAs 0 .. ctas-1 share the remainder tiles (1 <= ctas <= min(gridDim.x, rem * ktiles))
+  int gemm_ctas;          // 0: every CTA of the grid works on tiles; else CTAs >= gemm_ctas belong to epi.extra()
 };
 
 struct PersistentSchedule {
@@ -429,7 +430,12 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   sch.tiles_m = (M + BM - 1) / BM, sch.tiles_n = (N + BN - 1) / BN, sch.upper = upper;
   const int ntiles = upper ? sch.tiles_n * (sch.tiles_n + 1) / 2 : sch.tiles_m * sch.tiles_n;
   const int ktiles = (K + BK - 1) / BK;
-  const int G = gridDim.x, c = blockIdx.x;
+  const int G = sk.gemm_ctas ? sk.gemm_ctas : gridDim.x, c = blockIdx.x;
+  if (c >= G) {  // CTAs owned by the epilogue functor (Lasso tail rows), co-resident with the tile CTAs
+    pdl_wait();
+    epi.extra(c - G);
+    return;
+  }
   sch.ktiles = ktiles, sch.G = G, sch.c = c, sch.waves = ntiles / G, sch.nseg = 0;
   const int dp_tiles = sch.waves * G, rem = ntiles - dp_tiles;
   const int P = sk.ctas;

@@ -70,7 +70,8 @@ struct LassoEpilogue {
     s.u = warp_sum(s.u);
     if ((threadIdx.x & 31) == 0) {
       double* p = partials + ((long long)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5)) * 4;
-      p[0] = s.r; p[1] = s.d; p[2] = s.a; p[3] = s.u;
+      // += : a persistent CTA handles several tiles (the slots are zeroed before every launch that wants norms)
+      p[0] += s.r; p[1] += s.d; p[2] += s.a; p[3] += s.u;
     }
   }
 
@@ -256,10 +257,14 @@ static inline int lasso_n_main(int n) {
 
 using namespace ipm;
 
+extern "C" int ipm_internal_sk_slot(void* stream, double** partials, unsigned int** flags, unsigned int* epoch,
+                                    int* num_sms);
+
 extern "C" long long ipm_lasso_partials_doubles(int n, int K) {
   const int n_main = lasso_n_main(n);
-  const long long ctas = (long long)ceil_div(n_main, gemm::BM) * ceil_div(K, gemm::BN) +
-                         (n_main < n ? ceil_div(K, TAIL_COLS) : 0);
+  long long ctas = (long long)ceil_div(n_main, gemm::BM) * ceil_div(K, gemm::BN);
+  if (ctas < 256) ctas = 256;  // the stream-K path launches up to one CTA per SM however few tiles there are
+  ctas += n_main < n ? ceil_div(K, TAIL_COLS) : 0;
   return ctas * WARPS_PER_CTA * 4;
 }
 
@@ -287,18 +292,37 @@ extern "C" int ipm_lasso_admm_step_f64(const double* Qt, int ldq, int n, int K, 
   LassoEpilogue epi{bA, eta, alpha, u, z_out, Qt, z_in, ld, ldq, n, K, n_main, k_main, rho, add_bias, positive, want_norms,
                     partials};
   auto kern = gemm::gemm_tn_kernel<false, LassoEpilogue>;
+  auto pkern = gemm::gemm_tn_persistent_kernel<false, LassoEpilogue>;
   static bool attr_set = false;
   if (!attr_set) {
     IPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
+    IPM_CUDA_CHECK(cudaFuncSetAttribute(pkern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
     attr_set = true;
   }
-  const long long nparts = (long long)(tiles + tail_ctas) * WARPS_PER_CTA * 4;
+  // Small batches (a per-GPU shard of K = 512 is 16 tiles on 148 SMs): spread the k-tiles of every tile over all SMs
+  // with the persistent stream-K kernel; the tail-row CTAs stay co-resident behind the tile CTAs.
+  const int ktiles = ceil_div(k_main, gemm::BK);
+  double* sk_partials = nullptr;
+  unsigned int *sk_flags = nullptr, sk_epoch = 0;
+  int sms = 0;
+  rc = ipm_internal_sk_slot(stream, &sk_partials, &sk_flags, &sk_epoch, &sms);
+  if (rc) return rc;
+  const int G = sms - tail_ctas;
+  const bool few = sk_partials && G > 0 && 4 * tiles <= 3 * G && ktiles >= 2;
+  const int grid_ctas = few ? (G < tiles * ktiles ? G : tiles * ktiles) : tiles;
+  const long long nparts = (long long)(grid_ctas + tail_ctas) * WARPS_PER_CTA * 4;
   if (want_norms) IPM_CUDA_CHECK(cudaMemsetAsync(partials, 0, sizeof(double) * nparts, st));
   // M = n_main rows through the DMMA tiles, contraction rows [0, k_main) through the k-tiles
   // programmatic dependent launch: iteration i+1's CTAs are scheduled while iteration i drains (they wait in
   // pdl_wait() before touching z / alpha / u)
-  IPM_CUDA_CHECK(launch_pdl(kern, dim3(tiles + tail_ctas), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, n_main,
-                            K, k_main, (const double*)nullptr, 0, epi));
+  if (few) {
+    gemm::StreamK sk{sk_partials, sk_flags, sk_epoch, grid_ctas, grid_ctas};
+    IPM_CUDA_CHECK(launch_pdl(pkern, dim3(grid_ctas + tail_ctas), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB,
+                              n_main, K, k_main, (const double*)nullptr, 0, epi, sk));
+  } else {
+    IPM_CUDA_CHECK(launch_pdl(kern, dim3(tiles + tail_ctas), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, n_main,
+                              K, k_main, (const double*)nullptr, 0, epi));
+  }
   IPM_LAUNCH_CHECK();
   if (want_norms) {
     lasso_norms_kernel<<<1, 256, 0, st>>>(partials, (int)(nparts / 4), norms_out);
