@@ -215,12 +215,14 @@ static int launch_potf2(double* Akk, long long ld, int nb, int k0, int* info, cu
 // thread, coefficients by 16-byte shared loads).
 // ------------------------------------------------------------------------------------------------
 constexpr int TP_COLS = 64;
+constexpr int US_LD = NB + 4;        // 132 and 68 are 4 (mod 16): the (k = lane & 3, m = lane >> 2) fragment loads of
+constexpr int PS_LD = TP_COLS + 4;   // the DMMA update hit 16 distinct 8-byte banks per half-warp, rows stay 16-byte aligned
 
 __global__ void __launch_bounds__(256, 1) trsm_panel_kernel(const double* __restrict__ U11, long long ldu, int nb,
                                                             double* __restrict__ P, long long ldp, int ncols) {
   extern __shared__ double sm[];
-  double* Us = sm;             // NB x NB
-  double* Ps = sm + NB * NB;   // NB x TP_COLS
+  double* Us = sm;                // NB x NB (ld US_LD)
+  double* Ps = sm + NB * US_LD;   // NB x TP_COLS (ld PS_LD)
   __shared__ double rinv[NB];
   const int tid = threadIdx.x;
   const int c = tid & (TP_COLS - 1), tr = tid >> 6;  // 4 row phases
@@ -236,13 +238,13 @@ __global__ void __launch_bounds__(256, 1) trsm_panel_kernel(const double* __rest
       const int r = idx >> 6, cc = (idx & 63) * 2;
       double2 v = make_double2(0.0, 0.0);
       if (cc + 1 >= r) v = *reinterpret_cast<const double2*>(U11 + (long long)r * ldu + cc);
-      Us[r * NB + cc] = cc >= r ? v.x : 0.0;
-      Us[r * NB + cc + 1] = v.y;
+      Us[r * US_LD + cc] = cc >= r ? v.x : 0.0;
+      Us[r * US_LD + cc + 1] = v.y;
     }
   } else {
     for (int idx = tid; idx < NB * NB; idx += 256) {
       const int r = idx >> 7, cc = idx & 127;
-      Us[idx] = (r < nb && cc >= r && cc < nb) ? U11[(long long)r * ldu + cc] : 0.0;
+      Us[r * US_LD + cc] = (r < nb && cc >= r && cc < nb) ? U11[(long long)r * ldu + cc] : 0.0;
     }
   }
   if (vecP) {
@@ -251,54 +253,65 @@ __global__ void __launch_bounds__(256, 1) trsm_panel_kernel(const double* __rest
       const int idx = tid + 256 * q;  // double2 index: row = idx / 32, col2 = idx % 32
       const int r = idx >> 5, cc = (idx & 31) * 2;
       const double2 v = *reinterpret_cast<const double2*>(P + (long long)r * ldp + col0 + cc);
-      Ps[r * TP_COLS + cc] = v.x;
-      Ps[r * TP_COLS + cc + 1] = v.y;
+      Ps[r * PS_LD + cc] = v.x;
+      Ps[r * PS_LD + cc + 1] = v.y;
     }
   } else {
     for (int idx = tid; idx < NB * TP_COLS; idx += 256) {
       const int r = idx >> 6, cc = idx & 63;
-      Ps[idx] = (r < nb && cc < ncl) ? P[(long long)r * ldp + col0 + cc] : 0.0;
+      Ps[r * PS_LD + cc] = (r < nb && cc < ncl) ? P[(long long)r * ldp + col0 + cc] : 0.0;
     }
   }
   __syncthreads();
-  if (tid < NB) rinv[tid] = tid < nb ? 1.0 / Us[tid * NB + tid] : 1.0;
+  if (tid < NB) rinv[tid] = tid < nb ? 1.0 / Us[tid * US_LD + tid] : 1.0;
   __syncthreads();
   for (int b0 = 0; b0 < nb; b0 += 32) {
     if (tr == 0) {
       // rows beyond nb are zero rows of Us / Ps with rinv = 1: harmless
       double v[32];
 #pragma unroll
-      for (int l = 0; l < 32; ++l) v[l] = Ps[(b0 + l) * TP_COLS + c];
+      for (int l = 0; l < 32; ++l) v[l] = Ps[(b0 + l) * PS_LD + c];
 #pragma unroll
       for (int l = 0; l < 32; ++l) {
         const double x = v[l] * rinv[b0 + l];
         v[l] = x;
-        const double* urow = Us + (b0 + l) * NB + b0;
+        const double* urow = Us + (b0 + l) * US_LD + b0;
 #pragma unroll
         for (int r = l + 1; r < 32; ++r) v[r] = fma(-urow[r], x, v[r]);
       }
 #pragma unroll
-      for (int l = 0; l < 32; ++l) Ps[(b0 + l) * TP_COLS + c] = v[l];
+      for (int l = 0; l < 32; ++l) Ps[(b0 + l) * PS_LD + c] = v[l];
     }
     __syncthreads();
-    const int rest0 = b0 + 32;
-    for (int rb = rest0 + 8 * tr; rb < nb; rb += 32) {
-      double acc[8];
+    // rows below the block:  Ps[rb.., :] -= U[b0..b0+32, rb..]^T X[b0..b0+32, :]  as 8x8 DMMA tiles, K = 32.
+    // Warp w owns the 8 columns 8w .. 8w+7 (its eight B fragments are loaded once), and walks the row blocks four
+    // at a time so that four independent accumulator chains are in flight.
+    {
+      const int lane = tid & 31, wp = tid >> 5, l4 = lane & 3, g8 = lane >> 2;
+      const int rest0 = b0 + 32;  // rows beyond nb are zero rows / zero coefficient columns: harmless
+      double bf[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) acc[q] = Ps[(rb + q) * TP_COLS + c];
-#pragma unroll 4
-      for (int l = 0; l < 32; ++l) {
-        const double xl = Ps[(b0 + l) * TP_COLS + c];
-        const double2* urow = reinterpret_cast<const double2*>(Us + (b0 + l) * NB + rb);
+      for (int kk = 0; kk < 8; ++kk) bf[kk] = Ps[(b0 + 4 * kk + l4) * PS_LD + 8 * wp + g8];
+      for (int r0 = rest0; r0 < NB; r0 += 32) {
+        double2 cacc[4];
+        double af[4][8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const double2 u2 = urow[q];
-          acc[2 * q] = fma(-u2.x, xl, acc[2 * q]);
-          acc[2 * q + 1] = fma(-u2.y, xl, acc[2 * q + 1]);
+        for (int i = 0; i < 4; ++i) {
+          cacc[i] = *reinterpret_cast<const double2*>(Ps + (r0 + 8 * i + g8) * PS_LD + 8 * wp + 2 * l4);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) af[i][kk] = -Us[(b0 + 4 * kk + l4) * US_LD + r0 + 8 * i + g8];
         }
-      }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) Ps[(rb + q) * TP_COLS + c] = acc[q];
+        for (int kk = 0; kk < 8; ++kk)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(cacc[i].x), "+d"(cacc[i].y)
+                         : "d"(af[i][kk]), "d"(bf[kk]));
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<double2*>(Ps + (r0 + 8 * i + g8) * PS_LD + 8 * wp + 2 * l4) = cacc[i];
+      }
     }
     __syncthreads();
   }
@@ -308,12 +321,12 @@ __global__ void __launch_bounds__(256, 1) trsm_panel_kernel(const double* __rest
       const int idx = tid + 256 * q;
       const int r = idx >> 5, cc = (idx & 31) * 2;
       *reinterpret_cast<double2*>(P + (long long)r * ldp + col0 + cc) =
-          make_double2(Ps[r * TP_COLS + cc], Ps[r * TP_COLS + cc + 1]);
+          make_double2(Ps[r * PS_LD + cc], Ps[r * PS_LD + cc + 1]);
     }
   } else {
     for (int idx = tid; idx < NB * TP_COLS; idx += 256) {
       const int r = idx >> 6, cc = idx & 63;
-      if (r < nb && cc < ncl) P[(long long)r * ldp + col0 + cc] = Ps[idx];
+      if (r < nb && cc < ncl) P[(long long)r * ldp + col0 + cc] = Ps[r * PS_LD + cc];
     }
   }
 }
@@ -321,7 +334,7 @@ __global__ void __launch_bounds__(256, 1) trsm_panel_kernel(const double* __rest
 static int launch_trsm_panel(const double* U11, long long ldu, int nb, double* P, long long ldp, int ncols,
                              cudaStream_t st) {
   if (ncols <= 0) return IPM_OK;
-  const int smem = (NB * NB + NB * TP_COLS) * 8;
+  const int smem = (NB * US_LD + NB * PS_LD) * 8;
   static bool attr_set = false;
   if (!attr_set) {
     IPM_CUDA_CHECK(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
