@@ -26,7 +26,7 @@ class QPSolver(BarrierSolverBase):
                  max_outer_iters=20, max_inner_iters=50, phase1_max_inner_iters=500, epsilon=1e-10,
                  inner_epsilon=1e-5, check_cvxpy=True, linear_solve_method="cholesky", max_cg_iters=50, alpha=0.2,
                  beta=0.6, mu=15, suppress_print=False, use_gpu=False, track_loss=False, get_dual_variables=False,
-                 phase1_tol=0, phase1_t0=0.01, x0=None, update_slacks_every=0, shard_rows=False):
+                 phase1_tol=0, phase1_t0=0.01, x0=None, update_slacks_every=0, shard_rows=False, sparse="auto"):
         if P is None:
             raise ValueError("Setting P to None is just an LP! Please use LP solver or set a value to P.")
         self.P, self.q, self.A, self.C, self.b, self.d = P, q, A, C, b, d
@@ -67,7 +67,7 @@ class QPSolver(BarrierSolverBase):
                 lb_loc = ub_loc = None  # bound rows belong to rank 0
             newton_cls = ShardedLinearNewton
         self.data = LinearProblemData(self.n, self.device, P=P, q=q, C=C_loc, d=d_loc, lb=lb_loc, ub=ub_loc, A=A, b=b,
-                                      sparse=False)
+                                      sparse=False if self.sharded else sparse)
         self.x_dev = torch.as_tensor(self.x).to(device=self.device, dtype=F64).clone()
         if C is not None:
             self.phase1_solver = PhaseOneSolver(

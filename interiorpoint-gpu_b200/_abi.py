@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libipm_b200.so")
+LIB_PATH = os.environ.get("IPM_B200_LIB") or os.path.join(_HERE, "lib", "libipm_b200.so")  # override: A/B builds
 
 _dp = C.c_void_p  # device pointer
 _i = C.c_int

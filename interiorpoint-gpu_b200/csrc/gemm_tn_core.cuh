@@ -35,7 +35,7 @@ namespace gemm {
 constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
 constexpr int KGROUPS = BK / 4;        // m8n8k4 k-groups per k-tile
 constexpr int PREFETCH = STAGES - 1;   // k-tiles issued ahead of a warp's own consumption
-constexpr int ISSUE_AT = KGROUPS / 2;  // a warp tops the ring up in the MIDDLE of its k-tile: the slot it refills was
+constexpr int ISSUE_AT = 6;            // a warp tops the ring up late in its k-tile (6 of 8 k-groups; measured best of 2/4/6): the slot it refills was
                                        // released by everybody half a k-tile ago, so the empty-wait rarely spins
 constexpr int CONSUMER_WARPS = 8;
 constexpr int THREADS = CONSUMER_WARPS * 32;

@@ -53,3 +53,32 @@ def test_aflow40b_shaped_stand_in_sparse_equals_dense():
     x = np.asarray(sp.xstar)
     assert np.all(prob["C"] @ x < prob["d"]) and np.all(x > 0) and np.all(x < 1)
     assert np.linalg.norm(prob["A"] @ x - prob["b"]) < 1e-6
+
+
+def test_qp_with_sparse_inequalities_equals_dense():
+    """QPSolver takes the same sparse-rows path (t*P is copied first, the entry-wise C' diag(w) C is added on top)."""
+    from ipm_b200.QPSolver import QPSolver
+
+    rs = np.random.RandomState(5)
+    n, m, p = 320, 400, 24
+    Pp = rs.uniform(-1, 1, (n // 2, n))
+    P = Pp.T @ Pp / n + np.eye(n)
+    C = np.where(rs.rand(m, n) < 0.01, rs.uniform(-2, 2, (m, n)), 0.0)
+    A = rs.uniform(-2, 2, (p, n))
+    x_feas = rs.uniform(-2, 2, n)
+    prob = dict(P=P, q=rs.uniform(-2, 2, n), A=A, b=A @ x_feas, C=C, d=C @ x_feas + rs.uniform(0.1, 1, m),
+                lower_bound=-3, upper_bound=3)
+    sp = QPSolver(**prob, check_cvxpy=False, suppress_print=True, **problems.QP_TEST_SETTINGS)
+    dn = QPSolver(**prob, check_cvxpy=False, suppress_print=True, sparse=False, **problems.QP_TEST_SETTINGS)
+    assert sp.data.sparse is not None and dn.data.sparse is None
+    v_sp, v_dn = sp.solve(), dn.solve()
+    print("sparse", v_sp, sp.inner_iters, "dense", v_dn, dn.inner_iters)
+    assert v_sp == pytest.approx(v_dn, rel=1e-8)
+    assert len(sp.inner_iters) == len(dn.inner_iters)
+    # Same arithmetic up to summation order: counts +-2.  The last centering steps of an equality-constrained solve
+    # stop on a residual that is close to its own rounding noise (SURVEY 7.4-1; on this instance the reference's
+    # NumPy arm needs 12 Newton steps in the last centering, the dense device path 16, the sparse one 11), so one
+    # step may differ by more -- optimum and iterate must not.
+    diffs = [abs(a - b) for a, b in zip(sp.inner_iters, dn.inner_iters)]
+    assert sum(d > 2 for d in diffs) <= 1 and max(diffs) <= 6, (sp.inner_iters, dn.inner_iters)
+    assert np.linalg.norm(np.asarray(sp.xstar) - np.asarray(dn.xstar)) <= 1e-6 * (1 + np.linalg.norm(dn.xstar))
