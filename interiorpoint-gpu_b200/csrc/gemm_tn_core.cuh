@@ -35,8 +35,11 @@ namespace gemm {
 constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
 constexpr int KGROUPS = BK / 4;        // m8n8k4 k-groups per k-tile
 constexpr int PREFETCH = STAGES - 1;   // k-tiles issued ahead of a warp's own consumption
-constexpr int ISSUE_AT = 6;            // a warp tops the ring up late in its k-tile (6 of 8 k-groups; measured best of 2/4/6): the slot it refills was
-                                       // released by everybody half a k-tile ago, so the empty-wait rarely spins
+// k-group at which a warp tops the ring up (refills the slot everybody released during the previous k-tile).  The
+// later, the less the empty-wait spins: measured on the persistent Hessian kernel 2 / 4 / 6 / 7 -> 33.0 / 33.0 / 32.7 /
+// 32.4 ms (issuing at the start of the NEXT k-tile with one k-tile of prefetch: 32.5).  The one-CTA-per-tile kernel
+// has short k loops (Lasso: 16 k-tiles) and prefers the data earlier: 4 -> 95.3 us, 7 -> 96.5 us per ADMM iteration.
+constexpr int ISSUE_AT_PERSISTENT = 7, ISSUE_AT_ONE_TILE = 4;
 constexpr int CONSUMER_WARPS = 8;
 constexpr int THREADS = CONSUMER_WARPS * 32;
 constexpr int CHUNK_BYTES = BK * 128;               // one TMA box: BK rows x 128 B
@@ -271,7 +274,7 @@ __device__ __forceinline__ void load_weights(double (&wk)[4], const double* __re
 // acc += sum over k-tiles [kt_begin, kt_end).  Software pipelined: the fragments of k-group j+1 (and the row
 // weights of the next k-tile) are in flight while the 32 DMMAs of group j issue; warp 0 tops the TMA ring up by
 // one k-tile per consumed k-tile (each warp its own two boxes).
-template <bool HAS_W, class S, class Prod>
+template <bool HAS_W, class S, int ISSUE_AT, class Prod>
 __device__ __forceinline__ void consume_ktiles(double (&acc)[S::MI][S::NI][2], const Ring& ring, const LaneMap& lm,
                                                const double* __restrict__ w, int K, int kt_begin, int kt_end,
                                                uint32_t& it, int warp, int lane, Prod& prod) {
@@ -382,7 +385,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   double acc[S::MI][S::NI][2];
   zero_acc(acc);
   uint32_t it = 0;
-  if (sch.ktiles > 0) consume_ktiles<HAS_W, S>(acc, ring, lm, w, K, 0, sch.ktiles, it, warp, lane, prod);
+  if (sch.ktiles > 0)
+    consume_ktiles<HAS_W, S, ISSUE_AT_ONE_TILE>(acc, ring, lm, w, K, 0, sch.ktiles, it, warp, lane, prod);
   epi.tile(acc, sch.m0 + lm.wm * (S::MI * 8), sch.n0 + lm.wn * (S::NI * 8), lm.g8, lm.l4);
   epi.after_tile(ti, tiles_m, sch.n0, TN);
 }
@@ -463,7 +467,7 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     sch.segment(sg, m0, n0, k0, k1);
     const bool is_sk = sg < sch.nseg;
     zero_acc(acc);
-    consume_ktiles<HAS_W, S>(acc, ring, lm, w, K, k0, k1, it, warp, lane, prod);
+    consume_ktiles<HAS_W, S, ISSUE_AT_PERSISTENT>(acc, ring, lm, w, K, k0, k1, it, warp, lane, prod);
     if (is_sk && k0 != 0) {
       // partial of a tile owned by a lower CTA
       double* slot = sk.partials + (size_t)c * (BM * BN) + tid;
