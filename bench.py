@@ -105,13 +105,13 @@ class ClockSampler:
 
 def hessian_dram_traffic(n, m):
     """DRAM bytes (read + write) per launch of the Hessian kernel from the committed `ncu --set full` capture
-    (profiles/syrk_hessian_ncu_r01c.csv, taken at the default cfg-2 shape); None for any other shape."""
+    (profiles/syrk_hessian_ncu_r01d.csv, taken at the default cfg-2 shape); None for any other shape."""
     if (n, m) != (8192, 16384):
         return None
     try:
         import csv
 
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "syrk_hessian_ncu_r01c.csv"))))
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "syrk_hessian_ncu_r01d.csv"))))
         h, units, first = rows[0], rows[1], rows[2]
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
         rd = float(first[h.index("dram__bytes_read.sum")]) * scale[units[h.index("dram__bytes_read.sum")]]

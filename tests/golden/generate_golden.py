@@ -159,7 +159,29 @@ def standalone_phase_one():
     return out
 
 
+def method_cases():
+    """Newton-class dispatch (LPSolver.py:371-448, QPSolver.py:385-455): the reference's alternative
+    ``linear_solve_method``s on the first test_LP / test_QP instance (both have equality constraints, so "kkt" is
+    admissible).  The device engine maps all of them onto its Cholesky kernels; this pins that the outcome is the same."""
+    out = []
+    for method in ("np_solve", "np_lstsq", "direct", "kkt"):
+        for cls, gen, settings, tag in ((LPSolver, "lp_testsolver", problems.LP_TEST_SETTINGS, "lp"),
+                                        (QPSolver, "qp_testsolver", problems.QP_TEST_SETTINGS, "qp")):
+            name = f"{tag}_seed1_n100_0_{method}"
+            try:
+                out.append(run_barrier(cls, gen, dict(seed=1, n=100, m=80, k=20, count=1), 0,
+                                       dict(settings, linear_solve_method=method), name))
+            except Exception as e:  # noqa: BLE001 -- some of the reference's own Newton classes crash on the NumPy arm
+                print(name, "REFERENCE FAILED:", type(e).__name__, e)
+                out.append(dict(name=name, solver=cls.__name__, reference_error=f"{type(e).__name__}: {e}"))
+    with open(os.path.join(HERE, "method_cases.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 def main():
+    if "--methods-only" in sys.argv:
+        method_cases()
+        return
     barrier = []
     for i in range(3):
         barrier.append(run_barrier(LPSolver, "lp_testsolver", dict(seed=1, n=100, m=80, k=20, count=3), i,
@@ -192,6 +214,7 @@ def main():
                                problems.SOCP_TEST_SETTINGS, "socp_n96_warm"))
     with open(os.path.join(HERE, "barrier_cases.json"), "w") as f:
         json.dump(barrier, f, indent=1)
+    method_cases()
     with open(os.path.join(HERE, "socp_group_lasso.json"), "w") as f:
         json.dump(group_lasso_socp(), f, indent=1)
     lasso = [

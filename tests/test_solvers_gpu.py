@@ -120,3 +120,30 @@ def test_socp_group_lasso_fstar():
     assert free == {10, 11}
     assert_iters_close(s.inner_iters, g["inner_iters"], cap=s.max_inner_iters, free=free)
     assert_iters_close(s.phase1_solver.inner_iters, g["phase1_inner_iters"])
+
+
+METHODS = load_golden("method_cases.json")
+
+
+@pytest.mark.parametrize("case", METHODS, ids=[c["name"] for c in METHODS])
+def test_linear_solve_method_variants(case):
+    """Newton-class dispatch (LPSolver.py:371-448): the reference's ``np_solve`` / ``np_lstsq`` / ``direct`` / ``kkt``
+    classes solve the same Newton system with different LAPACK routines; the device engine maps all of them onto its
+    Cholesky kernels.  Goldens from the real reference per method; its ``kkt`` classes crash on the NumPy arm
+    (``except cp.linalg.LinAlgError`` with CuPy absent, NewtonSolverInfeasibleStart.py:165), so for ``kkt`` the bar is
+    the reference's default-method optimum."""
+    cls = _solver_class(case["solver"])
+    if "reference_error" in case:
+        base = {c["name"]: c for c in BARRIER}[case["name"].rsplit("_kkt", 1)[0]]
+        prob = build_problem(base)
+        s = cls(**prob, check_cvxpy=False, suppress_print=True, **dict(base["settings"], linear_solve_method="kkt"))
+        assert s.solve() == pytest.approx(base["value"], rel=1e-6)
+        return
+    prob = build_problem(case)
+    s = cls(**prob, check_cvxpy=False, suppress_print=True, **case["settings"])
+    val = s.solve()
+    print(case["name"], val, case["value"], s.inner_iters, case["inner_iters"])
+    assert val == pytest.approx(case["value"], rel=1e-6, abs=1e-9)
+    assert_iters_close(s.inner_iters, case["inner_iters"], cap=s.max_inner_iters,
+                       noisy=noise_dominated_steps(case, prob, case["settings"]))
+    assert_iters_close(s.phase1_solver.inner_iters, case["phase1_inner_iters"])
