@@ -104,11 +104,12 @@ int ipm_scale_shift_f64(const double* in, int ldi, double* out, int ldo, int row
 
 /* ---- factorisation and triangular solves ---------------------------------------------------------------- */
 /* In-place H = U^T U on the upper triangle; *info_dev (device int) = 0 or the 1-based index of the first
- * non-positive pivot.  scipy.linalg.cho_factor / cp.linalg.cholesky NewtonSolver.py:286,303;
+ * non-positive pivot.  Uses a library-owned high-priority side stream for the panel chain (joined before return).  scipy.linalg.cho_factor / cp.linalg.cholesky NewtonSolver.py:286,303;
  * NewtonSolverInfeasibleStart.py:398,426,455,473,780,795; LassoSolver.py:160,178. */
 int ipm_potrf_upper_f64(double* H, int ld, int n, int* info_dev, void* stream);
-/* b <- U^{-T} b (trans = 1) or U^{-1} b (trans = 0); ws: n doubles.  cho_solve / solve_triangular
- * NewtonSolver.py:287-313. */
+/* b <- U^{-T} b (trans = 1) or U^{-1} b (trans = 0), in place; ws is unused (kept for ABI stability, may be NULL).
+ * One persistent launch; not re-entrant per device (two concurrent solves on different streams of one device would
+ * share the block flags).  cho_solve / solve_triangular NewtonSolver.py:287-313. */
 int ipm_trsv_upper_f64(const double* U, int ld, int n, double* b, int trans, double* ws, void* stream);
 /* B <- U^{-T} B, B: n x p.  cho_solve(L1, A.T) NewtonSolverInfeasibleStart.py:399-411,460-465;
  * cho_solve(L, I) LassoSolver.py:163-188. */
