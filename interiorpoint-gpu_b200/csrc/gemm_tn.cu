@@ -1,4 +1,6 @@
 // ipm_gemm_tn_f64: D = beta*D + alpha * A^T diag(w) B   (FP64, TMA + DMMA, see gemm_tn_core.cuh)
+#include <stdlib.h>
+
 #include <atomic>
 #include <mutex>
 
@@ -17,26 +19,27 @@ struct PlainEpilogue {
 
   template <int MI, int NI>
   __device__ __forceinline__ void tile(const double (&acc)[MI][NI][2], int m_base, int n_base, int g8, int l4) const {
-    static_assert(MI == 8 && NI == 4, "PlainEpilogue is written for the 128x128 CTA tile");
+    static_assert(MI % 2 == 0, "rows are processed two 8-row groups at a time");
     const bool vec_ok = ((ldd & 1) == 0) && ((((uintptr_t)D) & 15) == 0);
     // fast path: the warp tile is fully inside the matrix, fully on/above the diagonal, 16-byte aligned
-    const bool interior = vec_ok && (m_base + 64 <= M) && (n_base + 32 <= N) && (!tri || n_base >= m_base + 63);
+    const bool interior = vec_ok && (m_base + MI * 8 <= M) && (n_base + NI * 8 <= N) &&
+                          (!tri || n_base >= m_base + MI * 8 - 1);
     if (interior) {
 #pragma unroll
-      for (int ib = 0; ib < 8; ib += 2) {
-        double2 old[2][4];
+      for (int ib = 0; ib < MI; ib += 2) {
+        double2 old[2][NI];
         if (beta != 0.0) {
 #pragma unroll
           for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int jn = 0; jn < 4; ++jn)
+            for (int jn = 0; jn < NI; ++jn)
               old[i][jn] = *reinterpret_cast<const double2*>(D + (long long)(m_base + (ib + i) * 8 + g8) * ldd +
                                                              n_base + jn * 8 + 2 * l4);
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
-          for (int jn = 0; jn < 4; ++jn) {
+          for (int jn = 0; jn < NI; ++jn) {
             double2 v;
             if (beta != 0.0) {
               v.x = fma(alpha, acc[ib + i][jn][0], beta * old[i][jn].x);
@@ -52,10 +55,10 @@ struct PlainEpilogue {
       return;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < MI; ++i) {
       const int row = m_base + i * 8 + g8;
 #pragma unroll
-      for (int jn = 0; jn < 4; ++jn) {
+      for (int jn = 0; jn < NI; ++jn) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int col = n_base + jn * 8 + 2 * l4 + e;
@@ -178,7 +181,17 @@ extern "C" int ipm_gemm_tn_f64(const double* A, int lda, const double* B, int ld
       unsigned epoch = ++g_sk_epoch;
       if (epoch == 0) epoch = ++g_sk_epoch;
       gemm::StreamK sk{slot->partials, slot->flags, epoch, (int)P, 0};
-      if (w) {
+      static const bool warps16 = [] {
+        const char* e = getenv("IPM_GEMM_WARPS16");
+        return e && e[0] == '1';
+      }();
+      if (w && many && warps16) {
+        // 16-warp variant (4 warps per SM sub-partition) for the long-K contraction; see gemm_tn_core.cuh
+        auto kern = gemm::gemm_tn_persistent16_kernel<true, PlainEpilogue>;
+        IPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
+        IPM_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(gemm::THREADS16), gemm::SMEM_BYTES, st, tmA, tmB, M, N, K, w,
+                                  tri_tiles, epi, sk));
+      } else if (w) {
         auto kern = gemm::gemm_tn_persistent_kernel<true, PlainEpilogue>;
         IPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
         IPM_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, M, N, K, w,
