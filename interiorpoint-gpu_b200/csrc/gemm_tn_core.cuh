@@ -601,31 +601,39 @@ gemm_tn_persistent16_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       uint32_t s = it % STAGES;
       mbar_wait(ring.full0 + 8 * s, (it / STAGES) & 1);
       uint32_t st = ring.tiles0 + s * STAGE_BYTES;
+      double a[2][S::MI], b[2][S::NI];
+      load_frags<S>(a[0], b[0], st, lm, 0);
       for (int kt = k0; kt < k1; ++kt) {
+        const bool has_next = kt + 1 < k1;
+        uint32_t s_next = s, st_next = st;
+        double wk[4];
 #pragma unroll
         for (int j = 0; j < KGROUPS; ++j) {
-          double wk[4];
+          const int cur = j & 1, nxt = cur ^ 1;
           if (HAS_W && (j & 3) == 0) load_weights(wk, w, 2 * kt + (j >> 2), K, lm.l4);
           if (j == ISSUE_AT_PERSISTENT) prod.issue(warp, lane);
-          double a[S::MI], b[S::NI];
-          load_frags<S>(a, b, st, lm, j);
+          if (j < KGROUPS - 1) {
+            load_frags<S>(a[nxt], b[nxt], st, lm, j + 1);
+          } else if (has_next) {
+            s_next = (it + 1) % STAGES;
+            mbar_wait(ring.full0 + 8 * s_next, ((it + 1) / STAGES) & 1);
+            st_next = ring.tiles0 + s_next * STAGE_BYTES;
+            load_frags<S>(a[nxt], b[nxt], st_next, lm, 0);
+          }
           if (HAS_W) {
 #pragma unroll
-            for (int i = 0; i < S::NI; ++i) b[i] *= wk[j & 3];
+            for (int i = 0; i < S::NI; ++i) b[cur][i] *= wk[j & 3];
           }
 #pragma unroll
           for (int i = 0; i < S::MI; ++i)
 #pragma unroll
-            for (int jn = 0; jn < S::NI; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], a[i], b[jn]);
+            for (int jn = 0; jn < S::NI; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], a[cur][i], b[cur][jn]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(ring.empty0 + 8 * s);
         ++it;
-        if (kt + 1 < k1) {
-          s = it % STAGES;
-          mbar_wait(ring.full0 + 8 * s, (it / STAGES) & 1);
-          st = ring.tiles0 + s * STAGE_BYTES;
-        }
+        s = s_next;
+        st = st_next;
       }
     }
     if (is_sk && k0 != 0) {
