@@ -1,6 +1,4 @@
 // ipm_gemm_tn_f64: D = beta*D + alpha * A^T diag(w) B   (FP64, TMA + DMMA, see gemm_tn_core.cuh)
-#include <stdlib.h>
-
 #include <atomic>
 #include <mutex>
 
@@ -181,17 +179,7 @@ extern "C" int ipm_gemm_tn_f64(const double* A, int lda, const double* B, int ld
       unsigned epoch = ++g_sk_epoch;
       if (epoch == 0) epoch = ++g_sk_epoch;
       gemm::StreamK sk{slot->partials, slot->flags, epoch, (int)P, 0};
-      static const bool warps16 = [] {
-        const char* e = getenv("IPM_GEMM_WARPS16");
-        return e && e[0] == '1';
-      }();
-      if (w && many && warps16) {
-        // 16-warp variant (4 warps per SM sub-partition) for the long-K contraction; see gemm_tn_core.cuh
-        auto kern = gemm::gemm_tn_persistent16_kernel<true, PlainEpilogue>;
-        IPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
-        IPM_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(gemm::THREADS16), gemm::SMEM_BYTES, st, tmA, tmB, M, N, K, w,
-                                  tri_tiles, epi, sk));
-      } else if (w) {
+      if (w) {
         auto kern = gemm::gemm_tn_persistent_kernel<true, PlainEpilogue>;
         IPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
         IPM_CUDA_CHECK(launch_pdl(kern, dim3(grid), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB, M, N, K, w,

@@ -508,171 +508,5 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// 16-warp variant of the persistent kernel (long-K contractions only): warp grid 4 x 4, warp tile 32 x 32, the same
-// 16 K accumulators spread over twice the warps.  Four warps per SM sub-partition instead of two: while one warp
-// is at a k-tile hand-off (barrier wait, TMA issue, fragment loads) three others can keep the DMMA pipe busy.  512
-// threads cap the kernel at 128 registers per thread, so fragments and weights are single-buffered (the other warps
-// hide their latency).  Warp c < 8 issues column chunk c of A, warp c >= 8 chunk c - 8 of B.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int WARPS16 = 16, THREADS16 = WARPS16 * 32;
-struct Shape16 {
-  static constexpr int WM = 4, MI = 4, NI = 4;
-};
-
-template <class Schedule>
-struct Producer16 {
-  const Schedule& sch;
-  const CUtensorMap *tmA, *tmB;
-  Ring ring;
-  int sg, kt, k1, m0, n0;
-  uint32_t it;
-  __device__ __forceinline__ Producer16(const Schedule& s, const CUtensorMap* a, const CUtensorMap* b, const Ring& r)
-      : sch(s), tmA(a), tmB(b), ring(r), sg(-1), kt(0), k1(0), m0(0), n0(0), it(0) {
-    next_segment();
-  }
-  __device__ __forceinline__ void next_segment() {
-    ++sg;
-    if (sg < sch.count()) sch.segment(sg, m0, n0, kt, k1);
-  }
-  __device__ __forceinline__ void issue(int wp, int lane) {
-    if (sg >= sch.count()) return;
-    if (lane == 0) {
-      const uint32_t s = it % STAGES;
-      if (it >= STAGES) mbar_wait(ring.empty0 + 8 * s, ((it / STAGES) - 1) & 1);
-      const uint32_t full = ring.full0 + 8 * s;
-      mbar_expect_tx(full, CHUNK_BYTES);
-      const uint32_t base = ring.tiles0 + s * STAGE_BYTES;
-      if (wp < 8) tma_load_2d(base + wp * CHUNK_BYTES, tmA, m0 + wp * 16, kt * BK, full);
-      else tma_load_2d(base + OPERAND_BYTES + (wp - 8) * CHUNK_BYTES, tmB, n0 + (wp - 8) * 16, kt * BK, full);
-    }
-    __syncwarp();
-    ++it;
-    if (++kt >= k1) next_segment();
-  }
-};
-
-template <bool HAS_W, class Epilogue>
-__global__ void __launch_bounds__(THREADS16, 1)
-gemm_tn_persistent16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M,
-                            int N, int K, const double* __restrict__ w, int upper, Epilogue epi, StreamK sk) {
-  extern __shared__ uint8_t smem_raw[];
-  using S = Shape16;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  PersistentSchedule sch;
-  sch.tiles_m = (M + BM - 1) / BM, sch.tiles_n = (N + BN - 1) / BN, sch.upper = upper;
-  const int ntiles = upper ? sch.tiles_n * (sch.tiles_n + 1) / 2 : sch.tiles_m * sch.tiles_n;
-  const int ktiles = (K + BK - 1) / BK;
-  const int G = gridDim.x, c = blockIdx.x;
-  sch.ktiles = ktiles, sch.G = G, sch.c = c, sch.waves = ntiles / G, sch.nseg = 0;
-  const int dp_tiles = sch.waves * G, rem = ntiles - dp_tiles;
-  const int P = sk.ctas;
-  const long long U = (long long)rem * ktiles;
-  const long long u0 = c < P ? U * c / P : 0, u1 = c < P ? U * (c + 1) / P : 0;
-  sch.seg_tile[0] = sch.seg_tile[1] = sch.seg_k0[0] = sch.seg_k0[1] = sch.seg_k1[0] = sch.seg_k1[1] = 0;
-  if (u1 > u0) {
-    const int ta = (int)(u0 / ktiles), ka = (int)(u0 - (long long)ta * ktiles);
-    const int len = (int)(u1 - u0);
-    const int first = min(len, ktiles - ka);
-    sch.seg_tile[0] = dp_tiles + ta, sch.seg_k0[0] = ka, sch.seg_k1[0] = ka + first, sch.nseg = 1;
-    if (len > first) sch.seg_tile[1] = dp_tiles + ta + 1, sch.seg_k0[1] = 0, sch.seg_k1[1] = len - first, sch.nseg = 2;
-  }
-  const Ring ring = setup_ring(smem_raw, WARPS16);
-  pdl_wait();
-  Producer16<PersistentSchedule> prod(sch, &tmA, &tmB, ring);
-  for (int p = 0; p < PREFETCH; ++p) prod.issue(warp, lane);
-  LaneMap lm;
-  lm.l4 = lane & 3, lm.g8 = lane >> 2, lm.wm = warp >> 2, lm.wn = warp & 3;
-  lm.a_blk0 = lm.wm * S::MI, lm.b_blk0 = lm.wn * S::NI;  // both even: block parity == index parity
-#pragma unroll
-  for (int e = 0; e < 2; ++e)
-#pragma unroll
-    for (int jb = 0; jb < 2; ++jb)
-      lm.a_off[e][jb] = lm.b_off[e][jb] =
-          (uint32_t)((((e * 4) + (lm.g8 >> 1)) ^ (2 * lm.l4 + jb)) << 4) + (lm.g8 & 1) * 8;
-  uint32_t it = 0;
-  double acc[S::MI][S::NI][2];
-  for (int sg = 0; sg < sch.count(); ++sg) {
-    int m0, n0, k0, k1;
-    sch.segment(sg, m0, n0, k0, k1);
-    const bool is_sk = sg < sch.nseg;
-    zero_acc(acc);
-    {
-      uint32_t s = it % STAGES;
-      mbar_wait(ring.full0 + 8 * s, (it / STAGES) & 1);
-      uint32_t st = ring.tiles0 + s * STAGE_BYTES;
-      double a[2][S::MI], b[2][S::NI];
-      load_frags<S>(a[0], b[0], st, lm, 0);
-      for (int kt = k0; kt < k1; ++kt) {
-        const bool has_next = kt + 1 < k1;
-        uint32_t s_next = s, st_next = st;
-        double wk[4];
-#pragma unroll
-        for (int j = 0; j < KGROUPS; ++j) {
-          const int cur = j & 1, nxt = cur ^ 1;
-          if (HAS_W && (j & 3) == 0) load_weights(wk, w, 2 * kt + (j >> 2), K, lm.l4);
-          if (j == ISSUE_AT_PERSISTENT) prod.issue(warp, lane);
-          if (j < KGROUPS - 1) {
-            load_frags<S>(a[nxt], b[nxt], st, lm, j + 1);
-          } else if (has_next) {
-            s_next = (it + 1) % STAGES;
-            mbar_wait(ring.full0 + 8 * s_next, ((it + 1) / STAGES) & 1);
-            st_next = ring.tiles0 + s_next * STAGE_BYTES;
-            load_frags<S>(a[nxt], b[nxt], st_next, lm, 0);
-          }
-          if (HAS_W) {
-#pragma unroll
-            for (int i = 0; i < S::NI; ++i) b[cur][i] *= wk[j & 3];
-          }
-#pragma unroll
-          for (int i = 0; i < S::MI; ++i)
-#pragma unroll
-            for (int jn = 0; jn < S::NI; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], a[cur][i], b[cur][jn]);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(ring.empty0 + 8 * s);
-        ++it;
-        s = s_next;
-        st = st_next;
-      }
-    }
-    if (is_sk && k0 != 0) {
-      double* slot = sk.partials + (size_t)c * (BM * BN) + tid;
-#pragma unroll
-      for (int i = 0; i < S::MI; ++i)
-#pragma unroll
-        for (int j = 0; j < S::NI; ++j) {
-          __stcg(slot + ((i * S::NI + j) * 2 + 0) * THREADS16, acc[i][j][0]);
-          __stcg(slot + ((i * S::NI + j) * 2 + 1) * THREADS16, acc[i][j][1]);
-        }
-      __threadfence();
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(sk.flags + c), "r"(sk.epoch) : "memory");
-      continue;
-    }
-    if (is_sk && k1 < ktiles) {
-      const long long tile_end = (long long)(sch.seg_tile[sg] - dp_tiles + 1) * ktiles;
-      for (int c2 = c + 1; c2 < P && U * c2 / P < tile_end; ++c2) {
-        if (tid == 0) {
-          unsigned v;
-          do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sk.flags + c2) : "memory");
-          } while (v != sk.epoch);
-        }
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        const double* slot = sk.partials + (size_t)c2 * (BM * BN) + tid;
-#pragma unroll
-        for (int i = 0; i < S::MI; ++i)
-#pragma unroll
-          for (int j = 0; j < S::NI; ++j) {
-            acc[i][j][0] += __ldcg(slot + ((i * S::NI + j) * 2 + 0) * THREADS16);
-            acc[i][j][1] += __ldcg(slot + ((i * S::NI + j) * 2 + 1) * THREADS16);
-          }
-      }
-    }
-    epi.tile(acc, m0 + lm.wm * (S::MI * 8), n0 + lm.wn * (S::NI * 8), lm.g8, lm.l4);
-  }
-}
-
 }  // namespace gemm
 }  // namespace ipm
