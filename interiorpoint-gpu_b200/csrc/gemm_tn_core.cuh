@@ -1,7 +1,7 @@
 // FP64 "TN" contraction core for sm_100a:   acc[m][n] = sum_k  w[k] * A[k][m] * B[k][n]
 //
 // A is K x M and B is K x N, both row-major (the contracted index k is the ROW index, so a tile
-// [16 k-rows] x [128 contiguous columns] is what both operands look like in HBM).  That one flavour
+// [32 k-rows] x [128 contiguous columns] is what both operands look like in HBM).  That one flavour
 // serves every dense contraction of the interior-point path:
 //   * Hessian         H = C^T diag(w) C              (A = B = C, upper tiles only)
 //   * Cholesky update A22 -= U12^T U12               (A = B = U12, alpha = -1, beta = 1)
@@ -47,14 +47,12 @@ constexpr int OPERAND_BYTES = (BM / 16) * CHUNK_BYTES;  // 32 KiB
 constexpr int STAGE_BYTES = 2 * OPERAND_BYTES;      // A + B
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES * 8;
 
-// CTA tile shapes: 8 warps as a WM x (8 / WM) grid, each warp MI x NI blocks of 8 x 8 (MI * NI * 2 accumulators per
-// thread).  BM is always 128; BN = 112 exists because 4096 / 112 = 36.6 -> 37 column tiles x 4 row tiles = 148 CTAs,
-// exactly one wave on a B200, where the 128-wide tile leaves 20 SMs idle (Lasso batch, K = 4096 problems).
+// CTA tile shape: 8 warps as a WM x (8 / WM) grid, each warp MI x NI blocks of 8 x 8 (MI * NI * 2 accumulators per
+// thread).  The pipeline pieces below are written against the shape so that other warp grids can be tried; the two
+// that were (128 x 112 as 4 x 2 warps for a one-wave Lasso grid, and 16 warps of 32 x 32) measured slower and are not
+// kept (negative results).
 struct Shape128x128 {
   static constexpr int WM = 2, MI = 8, NI = 4;
-};
-struct Shape128x112 {
-  static constexpr int WM = 4, MI = 4, NI = 7;
 };
 template <class S>
 struct ShapeTraits {
@@ -218,7 +216,7 @@ struct Producer {
 
 // Per-lane constants of a consumer warp.  Column block b (8 columns) of an operand lives in chunk b >> 1 at
 // 16-byte unit ((b & 1) * 4 + (g8 >> 1)) ^ (2 * l4 + jb) of row (.., jb = row parity); the warp's first block may be
-// odd (128x112: b_blk0 = 7 wn), so its parity is folded into the two offset tables.
+// odd for shapes with odd NI, so its parity is folded into the two offset tables.
 struct LaneMap {
   uint32_t a_off[2][2], b_off[2][2];  // [block index parity relative to the warp's first block][row parity]
   int a_blk0, b_blk0;
@@ -272,8 +270,8 @@ __device__ __forceinline__ void load_weights(double (&wk)[4], const double* __re
 }
 
 // acc += sum over k-tiles [kt_begin, kt_end).  Software pipelined: the fragments of k-group j+1 (and the row
-// weights of the next k-tile) are in flight while the 32 DMMAs of group j issue; warp 0 tops the TMA ring up by
-// one k-tile per consumed k-tile (each warp its own two boxes).
+// weights of the next k-tile) are in flight while the 32 DMMAs of group j issue; every warp tops the TMA ring up by
+// its own two boxes per consumed k-tile (prod.issue at k-group ISSUE_AT).
 template <bool HAS_W, class S, int ISSUE_AT, class Prod>
 __device__ __forceinline__ void consume_ktiles(double (&acc)[S::MI][S::NI][2], const Ring& ring, const LaneMap& lm,
                                                const double* __restrict__ w, int K, int kt_begin, int kt_end,
