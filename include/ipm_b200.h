@@ -107,6 +107,10 @@ int ipm_scale_shift_f64(const double* in, int ldi, double* out, int ldo, int row
  * non-positive pivot.  Uses a library-owned high-priority side stream for the panel chain (joined before return).  scipy.linalg.cho_factor / cp.linalg.cholesky NewtonSolver.py:286,303;
  * NewtonSolverInfeasibleStart.py:398,426,455,473,780,795; LassoSolver.py:160,178. */
 int ipm_potrf_upper_f64(double* H, int ld, int n, int* info_dev, void* stream);
+/* Same contract, ONE persistent launch: left-looking tile DAG with device-side flags (csrc/chol.cu, namespace dag).
+ * Used by ipm_potrf_upper_f64 itself when the environment has IPM_POTRF_DAG=1; sizes it does not cover
+ * (n <= 256, n > 32768) go through the stream-ordered code.  One factorisation at a time per stream. */
+int ipm_potrf_upper_dag_f64(double* H, int ld, int n, int* info_dev, void* stream);
 /* b <- U^{-T} b (trans = 1) or U^{-1} b (trans = 0), in place; ws is unused (kept for ABI stability, may be NULL).
  * One persistent launch; not re-entrant per device (two concurrent solves on different streams of one device would
  * share the block flags).  cho_solve / solve_triangular NewtonSolver.py:287-313. */

@@ -37,6 +37,7 @@ SIGNATURES = {
     "ipm_dots_f64": (_i, [_i, C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_i), _dp, _dp]),
     "ipm_axpy_dev_f64": (_i, [_i, _dp, _dp, _dp, _dp]),
     "ipm_potrf_upper_f64": (_i, [_dp, _i, _i, _dp, _dp]),
+    "ipm_potrf_upper_dag_f64": (_i, [_dp, _i, _i, _dp, _dp]),
     "ipm_trsm_upper_t_f64": (_i, [_dp, _i, _i, _dp, _i, _i, _dp]),
     "ipm_trsv_upper_f64": (_i, [_dp, _i, _i, _dp, _i, _dp, _dp]),
     "ipm_lin_barrier_ws_doubles": (_ll, []),

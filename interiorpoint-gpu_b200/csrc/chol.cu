@@ -7,7 +7,14 @@
 // so the DMMA/TMA core does the n^3/3 flops; the per-panel pieces below (128x128 diagonal factor, 128-row
 // triangular panel solve) are the serial O(n^2 NB) remainder.  Two-level blocking: the trailing update uses
 // K = 384 (three 128-row panels) so that each output tile is read/written a third as often.
+#include <stdlib.h>
+
+#include <atomic>
+#include <mutex>
+
 #include "common.cuh"
+#include "gemm_tn_core.cuh"
+#include "tensormap.cuh"
 
 using namespace ipm;
 
@@ -83,13 +90,23 @@ __device__ __forceinline__ void potf2_trailing_update(double* __restrict__ S, in
   }
 }
 
-__global__ void __launch_bounds__(PF_THREADS, 1) potf2_kernel(double* __restrict__ A, long long ld, int nb, int k0,
-                                                              int* __restrict__ info) {
-  extern __shared__ double S[];  // NB x PF_LD; identity beyond nb, garbage-tolerant strict lower triangle
-  __shared__ double rs[32];      // rsqrt of the current sub-block's pivots
+// Loads of tile data: CG = true reads through L2 only (ld.global.cg) -- for tiles another CTA of the SAME kernel has
+// just published (the persistent tile-DAG factorisation); the stand-alone kernels use plain loads.
+template <bool CG>
+__device__ __forceinline__ double2 tile_ld2(const double* p) {
+  return CG ? __ldcg(reinterpret_cast<const double2*>(p)) : *reinterpret_cast<const double2*>(p);
+}
+template <bool CG>
+__device__ __forceinline__ double tile_ld1(const double* p) {
+  return CG ? __ldcg(p) : *p;
+}
+
+// Body of potf2_kernel for one CTA of PF_THREADS threads: S = NB x PF_LD doubles of shared memory, rs = 32 doubles.
+template <bool CG>
+__device__ __forceinline__ void potf2_tile(double* __restrict__ S, double* __restrict__ rs, double* __restrict__ A,
+                                           long long ld, int nb, int k0, int* __restrict__ info) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool vec = !(ld & 1) && !(((uintptr_t)A) & 15);
-  pdl_wait();
   if (vec) {
 #pragma unroll 16
     for (int q = 0; q < NB * NB / 2 / PF_THREADS; ++q) {
@@ -98,9 +115,9 @@ __global__ void __launch_bounds__(PF_THREADS, 1) potf2_kernel(double* __restrict
       double2 v = make_double2(r == c ? 1.0 : 0.0, r == c + 1 ? 1.0 : 0.0);
       if (r < nb && c + 1 >= r) {
         if (c + 1 < nb) {
-          v = *reinterpret_cast<const double2*>(A + (long long)r * ld + c);
+          v = tile_ld2<CG>(A + (long long)r * ld + c);
         } else if (c < nb) {
-          v.x = A[(long long)r * ld + c];
+          v.x = tile_ld1<CG>(A + (long long)r * ld + c);
         }
       }
       S[r * PF_LD + c] = v.x;
@@ -109,7 +126,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) potf2_kernel(double* __restrict
   } else {
     for (int idx = tid; idx < NB * NB; idx += PF_THREADS) {
       const int r = idx >> 7, c = idx & 127;
-      S[r * PF_LD + c] = (r < nb && c < nb && c >= r) ? A[(long long)r * ld + c] : (r == c ? 1.0 : 0.0);
+      S[r * PF_LD + c] = (r < nb && c < nb && c >= r) ? tile_ld1<CG>(A + (long long)r * ld + c) : (r == c ? 1.0 : 0.0);
     }
   }
   IPM_PHASE_MARK(0);
@@ -196,6 +213,15 @@ __global__ void __launch_bounds__(PF_THREADS, 1) potf2_kernel(double* __restrict
   IPM_PHASE_MARK(21);
 }
 
+
+__global__ void __launch_bounds__(PF_THREADS, 1) potf2_kernel(double* __restrict__ A, long long ld, int nb, int k0,
+                                                              int* __restrict__ info) {
+  extern __shared__ double S[];  // NB x PF_LD; identity beyond nb, garbage-tolerant strict lower triangle
+  __shared__ double rs[32];      // rsqrt of the current sub-block's pivots
+  pdl_wait();
+  potf2_tile<false>(S, rs, A, ld, nb, k0, info);
+}
+
 static int launch_potf2(double* Akk, long long ld, int nb, int k0, int* info, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -218,53 +244,76 @@ constexpr int TP_COLS = 64;
 constexpr int US_LD = NB + 4;        // 132 and 68 are 4 (mod 16): the (k = lane & 3, m = lane >> 2) fragment loads of
 constexpr int PS_LD = TP_COLS + 4;   // the DMMA update hit 16 distinct 8-byte banks per half-warp, rows stay 16-byte aligned
 
-__global__ void __launch_bounds__(256, 1) trsm_panel_kernel(const double* __restrict__ U11, long long ldu, int nb,
-                                                            double* __restrict__ P, long long ldp, int ncols) {
-  extern __shared__ double sm[];
-  double* Us = sm;                // NB x NB (ld US_LD)
-  double* Ps = sm + NB * US_LD;   // NB x TP_COLS (ld PS_LD)
-  __shared__ double rinv[NB];
+// Pieces of the panel solve for one CTA of 256 threads (Us: NB x US_LD, Ps: NB x PS_LD, rinv: NB doubles, all shared).
+template <bool CG>
+__device__ __forceinline__ void trsm_load_u(double* __restrict__ Us, const double* __restrict__ U11, long long ldu,
+                                            int nb) {
   const int tid = threadIdx.x;
-  const int c = tid & (TP_COLS - 1), tr = tid >> 6;  // 4 row phases
-  const int col0 = blockIdx.x * TP_COLS;
-  const int ncl = min(TP_COLS, ncols - col0);
   const bool vecU = (nb == NB) && !(ldu & 1) && !(((uintptr_t)U11) & 15);
-  const bool vecP = (nb == NB) && (ncl == TP_COLS) && !(ldp & 1) && !(((uintptr_t)(P + col0)) & 15);
-  pdl_wait();
   if (vecU) {
 #pragma unroll 16
     for (int q = 0; q < 32; ++q) {
       const int idx = tid + 256 * q;  // double2 index
       const int r = idx >> 6, cc = (idx & 63) * 2;
       double2 v = make_double2(0.0, 0.0);
-      if (cc + 1 >= r) v = *reinterpret_cast<const double2*>(U11 + (long long)r * ldu + cc);
+      if (cc + 1 >= r) v = tile_ld2<CG>(U11 + (long long)r * ldu + cc);
       Us[r * US_LD + cc] = cc >= r ? v.x : 0.0;
       Us[r * US_LD + cc + 1] = v.y;
     }
   } else {
     for (int idx = tid; idx < NB * NB; idx += 256) {
       const int r = idx >> 7, cc = idx & 127;
-      Us[r * US_LD + cc] = (r < nb && cc >= r && cc < nb) ? U11[(long long)r * ldu + cc] : 0.0;
+      Us[r * US_LD + cc] = (r < nb && cc >= r && cc < nb) ? tile_ld1<CG>(U11 + (long long)r * ldu + cc) : 0.0;
     }
   }
+}
+
+// vecP: nb == NB, ncl == TP_COLS, even ldp, 16-byte aligned P + col0
+template <bool CG>
+__device__ __forceinline__ void trsm_load_p(double* __restrict__ Ps, const double* __restrict__ P, long long ldp,
+                                            int nb, int col0, int ncl, bool vecP) {
+  const int tid = threadIdx.x;
   if (vecP) {
 #pragma unroll 16
     for (int q = 0; q < 16; ++q) {
       const int idx = tid + 256 * q;  // double2 index: row = idx / 32, col2 = idx % 32
       const int r = idx >> 5, cc = (idx & 31) * 2;
-      const double2 v = *reinterpret_cast<const double2*>(P + (long long)r * ldp + col0 + cc);
+      const double2 v = tile_ld2<CG>(P + (long long)r * ldp + col0 + cc);
       Ps[r * PS_LD + cc] = v.x;
       Ps[r * PS_LD + cc + 1] = v.y;
     }
   } else {
     for (int idx = tid; idx < NB * TP_COLS; idx += 256) {
       const int r = idx >> 6, cc = idx & 63;
-      Ps[r * PS_LD + cc] = (r < nb && cc < ncl) ? P[(long long)r * ldp + col0 + cc] : 0.0;
+      Ps[r * PS_LD + cc] = (r < nb && cc < ncl) ? tile_ld1<CG>(P + (long long)r * ldp + col0 + cc) : 0.0;
     }
   }
-  __syncthreads();
-  if (tid < NB) rinv[tid] = tid < nb ? 1.0 / Us[tid * US_LD + tid] : 1.0;
-  __syncthreads();
+}
+
+__device__ __forceinline__ void trsm_store_p(const double* __restrict__ Ps, double* __restrict__ P, long long ldp,
+                                             int nb, int col0, int ncl, bool vecP) {
+  const int tid = threadIdx.x;
+  if (vecP) {
+#pragma unroll 8
+    for (int q = 0; q < 16; ++q) {
+      const int idx = tid + 256 * q;
+      const int r = idx >> 5, cc = (idx & 31) * 2;
+      *reinterpret_cast<double2*>(P + (long long)r * ldp + col0 + cc) =
+          make_double2(Ps[r * PS_LD + cc], Ps[r * PS_LD + cc + 1]);
+    }
+  } else {
+    for (int idx = tid; idx < NB * TP_COLS; idx += 256) {
+      const int r = idx >> 6, cc = idx & 63;
+      if (r < nb && cc < ncl) P[(long long)r * ldp + col0 + cc] = Ps[r * PS_LD + cc];
+    }
+  }
+}
+
+// Substitution of the TP_COLS columns held in Ps (in place); ends with a CTA barrier.
+__device__ __forceinline__ void trsm_solve(const double* __restrict__ Us, double* __restrict__ Ps,
+                                           const double* __restrict__ rinv, int nb) {
+  const int tid = threadIdx.x;
+  const int c = tid & (TP_COLS - 1), tr = tid >> 6;  // 4 row phases
   for (int b0 = 0; b0 < nb; b0 += 32) {
     if (tr == 0) {
       // rows beyond nb are zero rows of Us / Ps with rinv = 1: harmless
@@ -315,20 +364,26 @@ __global__ void __launch_bounds__(256, 1) trsm_panel_kernel(const double* __rest
     }
     __syncthreads();
   }
-  if (vecP) {
-#pragma unroll 8
-    for (int q = 0; q < 16; ++q) {
-      const int idx = tid + 256 * q;
-      const int r = idx >> 5, cc = (idx & 31) * 2;
-      *reinterpret_cast<double2*>(P + (long long)r * ldp + col0 + cc) =
-          make_double2(Ps[r * PS_LD + cc], Ps[r * PS_LD + cc + 1]);
-    }
-  } else {
-    for (int idx = tid; idx < NB * TP_COLS; idx += 256) {
-      const int r = idx >> 6, cc = idx & 63;
-      if (r < nb && cc < ncl) P[(long long)r * ldp + col0 + cc] = Ps[r * PS_LD + cc];
-    }
-  }
+}
+
+__global__ void __launch_bounds__(256, 1) trsm_panel_kernel(const double* __restrict__ U11, long long ldu, int nb,
+                                                            double* __restrict__ P, long long ldp, int ncols) {
+  extern __shared__ double sm[];
+  double* Us = sm;                // NB x NB (ld US_LD)
+  double* Ps = sm + NB * US_LD;   // NB x TP_COLS (ld PS_LD)
+  __shared__ double rinv[NB];
+  const int tid = threadIdx.x;
+  const int col0 = blockIdx.x * TP_COLS;
+  const int ncl = min(TP_COLS, ncols - col0);
+  const bool vecP = (nb == NB) && (ncl == TP_COLS) && !(ldp & 1) && !(((uintptr_t)(P + col0)) & 15);
+  pdl_wait();
+  trsm_load_u<false>(Us, U11, ldu, nb);
+  trsm_load_p<false>(Ps, P, ldp, nb, col0, ncl, vecP);
+  __syncthreads();
+  if (tid < NB) rinv[tid] = tid < nb ? 1.0 / Us[tid * US_LD + tid] : 1.0;
+  __syncthreads();
+  trsm_solve(Us, Ps, rinv, nb);
+  trsm_store_p(Ps, P, ldp, nb, col0, ncl, vecP);
 }
 
 static int launch_trsm_panel(const double* U11, long long ldu, int nb, double* P, long long ldp, int ncols,
@@ -345,6 +400,255 @@ static int launch_trsm_panel(const double* U11, long long ldu, int nb, double* P
   IPM_LAUNCH_CHECK();
   return IPM_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Persistent tile-DAG factorisation (left-looking), ONE launch for the whole matrix.  Opt-in (IPM_POTRF_DAG=1).
+//
+// Task (i, j), i <= j, owns the 128 x 128 tile U(i, j):
+//     acc = sum_{k < i} U(k, i)^T U(k, j)       the TN contraction of gemm_tn_core.cuh over the 128 i rows above the
+//                                               tile (TMA ring + DMMA, accumulators in registers for the whole K)
+//     B   = A(i, j) - acc                       written back in place
+//     i == j:  U(i, i) = chol(B)  (potf2_tile)      i < j:  U(i, j) = U(i, i)^{-T} B  (trsm pieces, two 64-column halves)
+// and then publishes the tile with a release store on flag[i][j] (epoch-stamped, never reset).  Tasks are numbered
+// row-major over the upper triangle, CTA c runs tasks c, c + G, c + 2G, ... in that order.  Every dependency of a task
+// (the tiles above it in its two block columns, and the diagonal tile of its row) has a smaller number, and all G <=
+// #SMs CTAs are resident (one per SM by shared memory), so the lowest-numbered unfinished task can always proceed:
+// no deadlock.  The producer lanes wait for flag[k][i] and flag[k][j] right before they issue the TMA loads of row
+// block k, so a task starts accumulating as soon as the first rows above it exist and only its LAST row block sits on
+// the critical path (look-ahead falls out of the schedule instead of being arranged with streams).
+//
+// Compared with the stream-ordered right-looking code below, the dependent chain per 128 columns is potf2 -> one
+// tile solve -> one K = 128 accumulation, with no kernel boundary in between, and every tile is written once.
+// ------------------------------------------------------------------------------------------------
+namespace dag {
+using namespace ipm::gemm;
+
+constexpr int KT_PER_BLOCK = NB / BK;                                  // k-tiles per 128-row block
+constexpr int SCRATCH_BYTES = (NB * US_LD + NB * PS_LD) * 8;            // tile-solve scratch (>= potf2's, >= the ring)
+static_assert(SCRATCH_BYTES >= STAGES * STAGE_BYTES && SCRATCH_BYTES >= PF_SMEM, "scratch aliases the TMA ring");
+constexpr int SMEM = 1024 /*align slack*/ + SCRATCH_BYTES + 2 * STAGES * 8;
+constexpr int MAX_T = 256;                                             // n <= 32768
+
+__device__ __forceinline__ void wait_flag(const unsigned* f, unsigned epoch) {
+  unsigned v;
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+  } while (v != epoch);
+}
+
+// Producer cursor of one task (every warp keeps a copy; lane 0 issues column chunk `wp` of both operands).
+struct Producer {
+  const CUtensorMap* tm;
+  Ring ring;
+  const unsigned* flags;
+  unsigned epoch;
+  int T, ti, tj, kt, k1;
+  uint32_t it;
+  __device__ __forceinline__ void begin(int i, int j) { ti = i, tj = j, kt = 0, k1 = i * KT_PER_BLOCK; }
+  __device__ __forceinline__ void issue(int wp, int lane) {
+    if (kt >= k1) return;
+    if (lane == 0) {
+      if ((kt % KT_PER_BLOCK) == 0) {
+        const int kb = kt / KT_PER_BLOCK;
+        wait_flag(flags + kb * T + ti, epoch);
+        if (tj != ti) wait_flag(flags + kb * T + tj, epoch);
+        asm volatile("fence.proxy.async;" ::: "memory");  // the tiles were written through the generic proxy
+      }
+      const uint32_t s = it % STAGES;
+      if (it >= STAGES) mbar_wait(ring.empty0 + 8 * s, ((it / STAGES) - 1) & 1);
+      const uint32_t full = ring.full0 + 8 * s;
+      mbar_expect_tx(full, 2 * CHUNK_BYTES);
+      const uint32_t dstA = ring.tiles0 + s * STAGE_BYTES + wp * CHUNK_BYTES;
+      tma_load_2d(dstA, tm, ti * BM + wp * 16, kt * BK, full);
+      tma_load_2d(dstA + OPERAND_BYTES, tm, tj * BN + wp * 16, kt * BK, full);
+    }
+    __syncwarp();
+    ++it;
+    ++kt;
+  }
+};
+
+// H(tile) -= acc for the warp's 64 x 32 piece (rows / columns beyond n and, on diagonal tiles, col < row skipped).
+__device__ __forceinline__ void subtract_acc(double* __restrict__ H, long long ld, int n, bool diag,
+                                             const double (&acc)[8][4][2], int m_base, int n_base, int g8, int l4) {
+  const bool interior = !(ld & 1) && !(((uintptr_t)H) & 15) && (m_base + 64 <= n) && (n_base + 32 <= n) &&
+                        (!diag || n_base >= m_base + 63);
+  if (interior) {
+#pragma unroll
+    for (int ib = 0; ib < 8; ib += 2) {
+      double2 old[2][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn)
+          old[i][jn] = __ldcg(reinterpret_cast<const double2*>(H + (long long)(m_base + (ib + i) * 8 + g8) * ld +
+                                                               n_base + jn * 8 + 2 * l4));
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn)
+          *reinterpret_cast<double2*>(H + (long long)(m_base + (ib + i) * 8 + g8) * ld + n_base + jn * 8 + 2 * l4) =
+              make_double2(old[i][jn].x - acc[ib + i][jn][0], old[i][jn].y - acc[ib + i][jn][1]);
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = m_base + i * 8 + g8;
+#pragma unroll
+    for (int jn = 0; jn < 4; ++jn)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = n_base + jn * 8 + 2 * l4 + e;
+        if (row < n && col < n && !(diag && col < row)) {
+          double* p = H + (long long)row * ld + col;
+          *p = __ldcg(p) - acc[i][jn][e];
+        }
+      }
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+potrf_dag_kernel(const __grid_constant__ CUtensorMap tm, double* __restrict__ H, long long ld, int n, int T,
+                 int* __restrict__ info, unsigned* __restrict__ flags, unsigned epoch) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ double rinv[NB];
+  __shared__ double rs[32];
+  using S = Shape128x128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  double* scratch = reinterpret_cast<double*>(smem);  // the TMA ring during the contraction, tile scratch after it
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SCRATCH_BYTES);
+  const Ring ring{smem_u32(bars), smem_u32(bars + STAGES), smem_u32(smem)};
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(ring.full0 + 8 * s, CONSUMER_WARPS);
+      mbar_init(ring.empty0 + 8 * s, CONSUMER_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  pdl_wait();
+  const LaneMap lm = make_lane_map<S>(warp, lane);
+  Producer prod{&tm, ring, flags, epoch, T, 0, 0, 0, 0, 0u};
+  uint32_t it = 0;
+  const int ntasks = T * (T + 1) / 2;
+  for (int lin = blockIdx.x; lin < ntasks; lin += gridDim.x) {
+    int ti, tj;
+    decode_tile(lin, T, T, true, ti, tj);
+    const bool diag = ti == tj;
+    double acc[S::MI][S::NI][2];
+    zero_acc(acc);
+    if (ti > 0) {
+      prod.begin(ti, tj);
+      for (int p = 0; p < PREFETCH; ++p) prod.issue(warp, lane);
+      consume_ktiles<false, S, ISSUE_AT_ONE_TILE>(acc, ring, lm, nullptr, ti * NB, 0, ti * KT_PER_BLOCK, it, warp, lane,
+                                                  prod);
+      subtract_acc(H, ld, n, diag, acc, ti * BM + lm.wm * 64, tj * BN + lm.wn * 32, lm.g8, lm.l4);
+    }
+    if (!diag && tid == 0) wait_flag(flags + ti * T + ti, epoch);
+    __syncthreads();  // ring drained by every warp, B = A - acc visible to the CTA, U(i, i) published
+    const int k0 = ti * NB, nb = min(NB, n - k0);
+    if (diag) {
+      potf2_tile<true>(scratch, rs, H + (long long)k0 * ld + k0, ld, nb, k0, info);
+    } else {
+      const int c0 = tj * NB, ncols = min(NB, n - c0);
+      double* Us = scratch;
+      double* Ps = scratch + NB * US_LD;
+      double* P = H + (long long)k0 * ld + c0;
+      trsm_load_u<true>(Us, H + (long long)k0 * ld + k0, ld, nb);
+      for (int col0 = 0; col0 < ncols; col0 += TP_COLS) {
+        const int ncl = min(TP_COLS, ncols - col0);
+        const bool vecP = (nb == NB) && (ncl == TP_COLS) && !(ld & 1) && !(((uintptr_t)(P + col0)) & 15);
+        trsm_load_p<true>(Ps, P, ld, nb, col0, ncl, vecP);
+        __syncthreads();
+        if (col0 == 0) {
+          if (tid < NB) rinv[tid] = tid < nb ? 1.0 / Us[tid * US_LD + tid] : 1.0;
+          __syncthreads();
+        }
+        trsm_solve(Us, Ps, rinv, nb);
+        trsm_store_p(Ps, P, ld, nb, col0, ncl, vecP);
+        __syncthreads();  // Ps is reloaded by the next half
+      }
+    }
+    // publish: tile data -> device scope (and the async proxy of the CTAs that will TMA-load it), then the flag;
+    // the same fence orders this task's generic accesses to the scratch before the next task's TMA writes to it
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + ti * T + tj), "r"(epoch) : "memory");
+  }
+}
+
+struct Slot {
+  cudaStream_t stream;
+  unsigned* flags;
+  bool used;
+};
+constexpr int kMaxDev = 16, kSlotsPerDev = 4;
+Slot g_slots[kMaxDev][kSlotsPerDev];
+int g_sms[kMaxDev];
+std::mutex g_mutex;
+std::atomic<unsigned> g_epoch{0};
+
+// flag storage of (device, stream); nullptr when all slots belong to other streams (caller takes the stream-ordered path)
+unsigned* get_flags(int dev, cudaStream_t st, int* rc) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  *rc = IPM_OK;
+  for (int i = 0; i < kSlotsPerDev; ++i)
+    if (g_slots[dev][i].used && g_slots[dev][i].stream == st) return g_slots[dev][i].flags;
+  for (int i = 0; i < kSlotsPerDev; ++i) {
+    Slot* s = &g_slots[dev][i];
+    if (s->used) continue;
+    if (cudaMalloc(&s->flags, MAX_T * MAX_T * sizeof(unsigned)) != cudaSuccess ||
+        cudaMemset(s->flags, 0, MAX_T * MAX_T * sizeof(unsigned)) != cudaSuccess) {
+      *rc = ipm_set_cuda_error(cudaGetLastError());
+      return nullptr;
+    }
+    s->stream = st;
+    s->used = true;
+    return s->flags;
+  }
+  return nullptr;
+}
+
+bool enabled() {
+  static const bool on = [] {
+    const char* e = getenv("IPM_POTRF_DAG");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+
+// returns 1 when the problem is not handled here (caller falls through to the stream-ordered factorisation)
+int potrf(double* H, int ld, int n, int* info_dev, cudaStream_t st) {
+  const int T = ceil_div(n, NB);
+  if (T < 3 || T > MAX_T) return 1;
+  int dev = 0, rc = IPM_OK;
+  IPM_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDev) return 1;
+  if (!g_sms[dev]) IPM_CUDA_CHECK(cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev));
+  unsigned* flags = get_flags(dev, st, &rc);
+  if (rc) return rc;
+  if (!flags) return 1;
+  CUtensorMap tm;
+  if (make_operand_map(&tm, H, ld, n, n)) return 1;  // unaligned base: the stream-ordered path reports it
+  unsigned epoch = ++g_epoch;
+  if (epoch == 0) epoch = ++g_epoch;  // never 0 (the flags' initial value)
+  static bool attr_set = false;
+  if (!attr_set) {
+    IPM_CUDA_CHECK(cudaFuncSetAttribute(potrf_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_set = true;
+  }
+  const int ntasks = T * (T + 1) / 2;
+  const int grid = ntasks < g_sms[dev] ? ntasks : g_sms[dev];
+  IPM_CUDA_CHECK(launch_pdl(potrf_dag_kernel, dim3(grid), dim3(THREADS), SMEM, st, tm, H, (long long)ld, n, T, info_dev,
+                            flags, epoch));
+  IPM_LAUNCH_CHECK();
+  return IPM_OK;
+}
+}  // namespace dag
 
 // Library-owned side stream + events for the look-ahead (one set per device, created on first use).
 struct SideStream {
@@ -383,10 +687,30 @@ static int get_side_stream(SideStream** out) {
 // for each outer block of NBO = 384 rows:   [ potf2(128) ; trsm of its 128-row panel ; K=128 update of the block's
 // remaining rows ] x 3 panels, then ONE K=384 DMMA update of the trailing matrix.
 // ------------------------------------------------------------------------------------------------
+static int potrf_stream_ordered(double* H, int ld, int n, int* info_dev, void* stream);
+
 extern "C" int ipm_potrf_upper_f64(double* H, int ld, int n, int* info_dev, void* stream) {
   if (!H || !info_dev || n < 0 || ld < n || (ld & 1)) return IPM_ERR_ARG;
+  IPM_CUDA_CHECK(cudaMemsetAsync(info_dev, 0, sizeof(int), (cudaStream_t)stream));
+  if (dag::enabled()) {
+    const int rc = dag::potrf(H, ld, n, info_dev, (cudaStream_t)stream);
+    if (rc <= 0) return rc;  // done or failed; 1 = not handled there
+  }
+  return potrf_stream_ordered(H, ld, n, info_dev, stream);
+}
+
+// Same contract as ipm_potrf_upper_f64, always through the single-launch tile-DAG kernel when the size allows it
+// (256 <= n <= 32768 and a free flag slot for the stream), else the stream-ordered code.
+extern "C" int ipm_potrf_upper_dag_f64(double* H, int ld, int n, int* info_dev, void* stream) {
+  if (!H || !info_dev || n < 0 || ld < n || (ld & 1)) return IPM_ERR_ARG;
+  IPM_CUDA_CHECK(cudaMemsetAsync(info_dev, 0, sizeof(int), (cudaStream_t)stream));
+  const int rc = dag::potrf(H, ld, n, info_dev, (cudaStream_t)stream);
+  if (rc <= 0) return rc;
+  return potrf_stream_ordered(H, ld, n, info_dev, stream);
+}
+
+static int potrf_stream_ordered(double* H, int ld, int n, int* info_dev, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  IPM_CUDA_CHECK(cudaMemsetAsync(info_dev, 0, sizeof(int), st));
   // Look-ahead: the serial panel chain of outer block o+1 (two potf2 + two panel solves, single-CTA latency
   // bound) runs on a side stream concurrently with the bulk trailing update of block o on the caller's stream.
   //   side : chain(0), U1(0), chain(1), [wait U2(0)] U1(1), chain(2), ...
