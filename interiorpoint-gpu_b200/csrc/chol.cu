@@ -309,11 +309,32 @@ __device__ __forceinline__ void trsm_store_p(const double* __restrict__ Ps, doub
   }
 }
 
+#ifdef IPM_DAG_TIMING
+namespace dag {
+__device__ long long g_dag_t[256 * 16];  // per-CTA cycle counters, see the slot list at DAG_ADD
+}
+#define TRSM_MARK(slot, t0)                                                              \
+  do {                                                                                   \
+    if (threadIdx.x == 0) dag::g_dag_t[blockIdx.x * 16 + (slot)] += clock64() - (t0);    \
+    (t0) = clock64();                                                                    \
+  } while (0)
+#else
+#define TRSM_MARK(slot, t0) \
+  do {                      \
+  } while (0)
+#endif
+
 // Substitution of the TP_COLS columns held in Ps (in place); ends with a CTA barrier.
 __device__ __forceinline__ void trsm_solve(const double* __restrict__ Us, double* __restrict__ Ps,
                                            const double* __restrict__ rinv, int nb) {
   const int tid = threadIdx.x;
   const int c = tid & (TP_COLS - 1), tr = tid >> 6;  // 4 row phases
+#ifdef IPM_DAG_TIMING
+  long long tm0 = clock64();
+#endif
+  // one copy of the (fully unrolled, ~14 KB) block substitution: unrolled over b0 -- and over the two column halves of
+  // the tile-DAG kernel -- it becomes 8 copies that are each executed once per tile and run ~4x slower
+#pragma unroll 1
   for (int b0 = 0; b0 < nb; b0 += 32) {
     if (tr == 0) {
       // rows beyond nb are zero rows of Us / Ps with rinv = 1: harmless
@@ -332,6 +353,7 @@ __device__ __forceinline__ void trsm_solve(const double* __restrict__ Us, double
       for (int l = 0; l < 32; ++l) Ps[(b0 + l) * PS_LD + c] = v[l];
     }
     __syncthreads();
+    TRSM_MARK(10, tm0);
     // rows below the block:  Ps[rb.., :] -= U[b0..b0+32, rb..]^T X[b0..b0+32, :]  as 8x8 DMMA tiles, K = 32.
     // Warp w owns the 8 columns 8w .. 8w+7 (its eight B fragments are loaded once), and walks the row blocks four
     // at a time so that four independent accumulator chains are in flight.
@@ -363,6 +385,7 @@ __device__ __forceinline__ void trsm_solve(const double* __restrict__ Us, double
       }
     }
     __syncthreads();
+    TRSM_MARK(11, tm0);
   }
 }
 
@@ -409,13 +432,16 @@ static int launch_trsm_panel(const double* U11, long long ldu, int nb, double* P
 //                                               tile (TMA ring + DMMA, accumulators in registers for the whole K)
 //     B   = A(i, j) - acc                       written back in place
 //     i == j:  U(i, i) = chol(B)  (potf2_tile)      i < j:  U(i, j) = U(i, i)^{-T} B  (trsm pieces, two 64-column halves)
-// and then publishes the tile with a release store on flag[i][j] (epoch-stamped, never reset).  Tasks are numbered
-// row-major over the upper triangle, CTA c runs tasks c, c + G, c + 2G, ... in that order.  Every dependency of a task
-// (the tiles above it in its two block columns, and the diagonal tile of its row) has a smaller number, and all G <=
-// #SMs CTAs are resident (one per SM by shared memory), so the lowest-numbered unfinished task can always proceed:
-// no deadlock.  The producer lanes wait for flag[k][i] and flag[k][j] right before they issue the TMA loads of row
-// block k, so a task starts accumulating as soon as the first rows above it exist and only its LAST row block sits on
-// the critical path (look-ahead falls out of the schedule instead of being arranged with streams).
+// and then publishes the tile.  Tile (i, j) needs tile (i - 1, j), so the tiles of a block column are published top
+// down and ONE counter per block column is enough: done[j] = (epoch << 32) | (number of finished row blocks of column
+// j), written with a release store (epoch-stamped, never reset).  Tasks are numbered row-major over the upper
+// triangle, CTA c runs tasks c, c + G, c + 2G, ... in that order.  Every dependency of a task (the tiles above it in
+// its two block columns, and the diagonal tile of its row) has a smaller number, and all G <= #SMs CTAs are resident
+// (one per SM by shared memory), so the lowest-numbered unfinished task can always proceed: no deadlock.  The
+// producer lanes check done[i] and done[j] right before they issue the TMA loads of row block k -- and remember the
+// counts, so a task whose inputs were finished long ago polls once -- hence a task starts accumulating as soon as
+// the first rows above it exist and only its LAST row block sits on the critical path (look-ahead falls out of the
+// schedule instead of being arranged with streams).
 //
 // Compared with the stream-ordered right-looking code below, the dependent chain per 128 columns is potf2 -> one
 // tile solve -> one K = 128 accumulation, with no kernel boundary in between, and every tile is written once.
@@ -429,30 +455,69 @@ static_assert(SCRATCH_BYTES >= STAGES * STAGE_BYTES && SCRATCH_BYTES >= PF_SMEM,
 constexpr int SMEM = 1024 /*align slack*/ + SCRATCH_BYTES + 2 * STAGES * 8;
 constexpr int MAX_T = 256;                                             // n <= 32768
 
-__device__ __forceinline__ void wait_flag(const unsigned* f, unsigned epoch) {
-  unsigned v;
+#ifdef IPM_DAG_TIMING
+// per CTA: [0] whole kernel, [1] contraction, [2] wait for the row's diagonal tile, [3] potf2, [4] tile solves,
+// [5] publish, [6] tasks, [7] polling of the progress counters by warp 0 (inside [1]); inside [4]: [8] load U,
+// [9] load P, [10] substitution (2 warps), [11] DMMA update of the rows below, [12] store, [13] subtract_acc (in [1])
+// (clock64 cycles)
+#define DAG_MARK(slot, t0) TRSM_MARK(slot, t0)
+#define DAG_CLOCK() clock64()
+#define DAG_ADD(slot, t0)                                                         \
+  do {                                                                            \
+    if (threadIdx.x == 0) g_dag_t[blockIdx.x * 16 + (slot)] += clock64() - (t0);   \
+  } while (0)
+#else
+#define DAG_MARK(slot, t0) \
+  do {                     \
+    (void)(t0);            \
+  } while (0)
+#define DAG_CLOCK() 0ll
+#define DAG_ADD(slot, t0) \
+  do {                    \
+    (void)(t0);           \
+  } while (0)
+#endif
+
+// number of published row blocks of a block column (0 while the counter still carries another call's epoch)
+__device__ __forceinline__ int column_progress(const unsigned long long* p, unsigned epoch) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return (unsigned)(v >> 32) == epoch ? (int)(unsigned)v : 0;
+}
+__device__ __forceinline__ int wait_column(const unsigned long long* p, unsigned epoch, int need) {
+  int r;
   do {
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-  } while (v != epoch);
+    r = column_progress(p, epoch);
+  } while (r < need);
+  return r;
 }
 
 // Producer cursor of one task (every warp keeps a copy; lane 0 issues column chunk `wp` of both operands).
 struct Producer {
   const CUtensorMap* tm;
   Ring ring;
-  const unsigned* flags;
+  const unsigned long long* done;
   unsigned epoch;
-  int T, ti, tj, kt, k1;
+  int ti, tj, kt, k1, ready_i, ready_j;  // ready_*: row blocks of columns ti / tj known to be published
   uint32_t it;
-  __device__ __forceinline__ void begin(int i, int j) { ti = i, tj = j, kt = 0, k1 = i * KT_PER_BLOCK; }
+  __device__ __forceinline__ void begin(int i, int j) {
+    ti = i, tj = j, kt = 0, k1 = i * KT_PER_BLOCK, ready_i = ready_j = 0;
+  }
   __device__ __forceinline__ void issue(int wp, int lane) {
     if (kt >= k1) return;
     if (lane == 0) {
-      if ((kt % KT_PER_BLOCK) == 0) {
-        const int kb = kt / KT_PER_BLOCK;
-        wait_flag(flags + kb * T + ti, epoch);
-        if (tj != ti) wait_flag(flags + kb * T + tj, epoch);
+      const int need = kt / KT_PER_BLOCK + 1;
+      if ((kt % KT_PER_BLOCK) == 0 && (ready_i < need || ready_j < need)) {
+#ifdef IPM_DAG_TIMING
+        const long long t0 = clock64();
+#endif
+        if (ready_i < need) ready_i = wait_column(done + ti, epoch, need);
+        if (tj == ti) ready_j = ready_i;
+        if (ready_j < need) ready_j = wait_column(done + tj, epoch, need);
         asm volatile("fence.proxy.async;" ::: "memory");  // the tiles were written through the generic proxy
+#ifdef IPM_DAG_TIMING
+        if (wp == 0) g_dag_t[blockIdx.x * 16 + 7] += clock64() - t0;
+#endif
       }
       const uint32_t s = it % STAGES;
       if (it >= STAGES) mbar_wait(ring.empty0 + 8 * s, ((it / STAGES) - 1) & 1);
@@ -510,13 +575,15 @@ __device__ __forceinline__ void subtract_acc(double* __restrict__ H, long long l
 
 __global__ void __launch_bounds__(THREADS, 1)
 potrf_dag_kernel(const __grid_constant__ CUtensorMap tm, double* __restrict__ H, long long ld, int n, int T,
-                 int* __restrict__ info, unsigned* __restrict__ flags, unsigned epoch) {
+                 int* __restrict__ info, unsigned long long* __restrict__ done, unsigned epoch) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ double rinv[NB];
   __shared__ double rs[32];
   using S = Shape128x128;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment (128B swizzle) as an OFFSET into the shared array: arithmetic on the integer value of the
+  // pointer would make every scratch access a generic LD/ST instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   double* scratch = reinterpret_cast<double*>(smem);  // the TMA ring during the contraction, tile scratch after it
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SCRATCH_BYTES);
   const Ring ring{smem_u32(bars), smem_u32(bars + STAGES), smem_u32(smem)};
@@ -531,59 +598,100 @@ potrf_dag_kernel(const __grid_constant__ CUtensorMap tm, double* __restrict__ H,
   __syncthreads();
   pdl_wait();
   const LaneMap lm = make_lane_map<S>(warp, lane);
-  Producer prod{&tm, ring, flags, epoch, T, 0, 0, 0, 0, 0u};
+  Producer prod{&tm, ring, done, epoch, 0, 0, 0, 0, 0, 0, 0u};
   uint32_t it = 0;
   const int ntasks = T * (T + 1) / 2;
+  const long long t_kernel = DAG_CLOCK();
   for (int lin = blockIdx.x; lin < ntasks; lin += gridDim.x) {
     int ti, tj;
     decode_tile(lin, T, T, true, ti, tj);
     const bool diag = ti == tj;
     double acc[S::MI][S::NI][2];
     zero_acc(acc);
+    long long t0 = DAG_CLOCK();
     if (ti > 0) {
       prod.begin(ti, tj);
       for (int p = 0; p < PREFETCH; ++p) prod.issue(warp, lane);
       consume_ktiles<false, S, ISSUE_AT_ONE_TILE>(acc, ring, lm, nullptr, ti * NB, 0, ti * KT_PER_BLOCK, it, warp, lane,
                                                   prod);
+      long long t1 = DAG_CLOCK();
       subtract_acc(H, ld, n, diag, acc, ti * BM + lm.wm * 64, tj * BN + lm.wn * 32, lm.g8, lm.l4);
+      DAG_MARK(13, t1);
     }
-    if (!diag && tid == 0) wait_flag(flags + ti * T + ti, epoch);
+    DAG_ADD(1, t0);
+    t0 = DAG_CLOCK();
+    if (!diag && tid == 0) wait_column(done + ti, epoch, ti + 1);
     __syncthreads();  // ring drained by every warp, B = A - acc visible to the CTA, U(i, i) published
+    DAG_ADD(2, t0);
+    t0 = DAG_CLOCK();
     const int k0 = ti * NB, nb = min(NB, n - k0);
     if (diag) {
       potf2_tile<true>(scratch, rs, H + (long long)k0 * ld + k0, ld, nb, k0, info);
+      __syncthreads();
+      DAG_ADD(3, t0);
     } else {
       const int c0 = tj * NB, ncols = min(NB, n - c0);
       double* Us = scratch;
       double* Ps = scratch + NB * US_LD;
       double* P = H + (long long)k0 * ld + c0;
+      long long t1 = DAG_CLOCK();
       trsm_load_u<true>(Us, H + (long long)k0 * ld + k0, ld, nb);
+      DAG_MARK(8, t1);
+#pragma unroll 1
       for (int col0 = 0; col0 < ncols; col0 += TP_COLS) {
         const int ncl = min(TP_COLS, ncols - col0);
         const bool vecP = (nb == NB) && (ncl == TP_COLS) && !(ld & 1) && !(((uintptr_t)(P + col0)) & 15);
+        t1 = DAG_CLOCK();
         trsm_load_p<true>(Ps, P, ld, nb, col0, ncl, vecP);
         __syncthreads();
         if (col0 == 0) {
           if (tid < NB) rinv[tid] = tid < nb ? 1.0 / Us[tid * US_LD + tid] : 1.0;
           __syncthreads();
         }
+        DAG_MARK(9, t1);
         trsm_solve(Us, Ps, rinv, nb);
+        t1 = DAG_CLOCK();
         trsm_store_p(Ps, P, ld, nb, col0, ncl, vecP);
         __syncthreads();  // Ps is reloaded by the next half
+        DAG_MARK(12, t1);
       }
+      DAG_ADD(4, t0);
     }
+    t0 = DAG_CLOCK();
     // publish: tile data -> device scope (and the async proxy of the CTAs that will TMA-load it), then the flag;
     // the same fence orders this task's generic accesses to the scratch before the next task's TMA writes to it
     __threadfence();
     asm volatile("fence.proxy.async;" ::: "memory");
     __syncthreads();
-    if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + ti * T + tj), "r"(epoch) : "memory");
+    if (tid == 0) {
+      const unsigned long long v = ((unsigned long long)epoch << 32) | (unsigned)(ti + 1);
+      asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(done + tj), "l"(v) : "memory");
+    }
+    DAG_ADD(5, t0);
+#ifdef IPM_DAG_TIMING
+    if (tid == 0) g_dag_t[blockIdx.x * 16 + 6] += 1;
+#endif
   }
+  DAG_ADD(0, t_kernel);
 }
+
+#ifdef IPM_DAG_TIMING
+}  // namespace dag
+// variant builds only: copies the per-CTA cycle counters to the host and clears them
+extern "C" int ipm_internal_dag_timing(long long* out, int count) {
+  static long long zero[256 * 16];
+  if (count > 256 * 16) count = 256 * 16;
+  IPM_CUDA_CHECK(cudaDeviceSynchronize());
+  IPM_CUDA_CHECK(cudaMemcpyFromSymbol(out, dag::g_dag_t, count * sizeof(long long)));
+  IPM_CUDA_CHECK(cudaMemcpyToSymbol(dag::g_dag_t, zero, sizeof(zero)));
+  return IPM_OK;
+}
+namespace dag {
+#endif
 
 struct Slot {
   cudaStream_t stream;
-  unsigned* flags;
+  unsigned long long* done;  // MAX_T progress counters
   bool used;
 };
 constexpr int kMaxDev = 16, kSlotsPerDev = 4;
@@ -592,23 +700,24 @@ int g_sms[kMaxDev];
 std::mutex g_mutex;
 std::atomic<unsigned> g_epoch{0};
 
-// flag storage of (device, stream); nullptr when all slots belong to other streams (caller takes the stream-ordered path)
-unsigned* get_flags(int dev, cudaStream_t st, int* rc) {
+// progress counters of (device, stream); nullptr when all slots belong to other streams (caller takes the
+// stream-ordered path)
+unsigned long long* get_counters(int dev, cudaStream_t st, int* rc) {
   std::lock_guard<std::mutex> lock(g_mutex);
   *rc = IPM_OK;
   for (int i = 0; i < kSlotsPerDev; ++i)
-    if (g_slots[dev][i].used && g_slots[dev][i].stream == st) return g_slots[dev][i].flags;
+    if (g_slots[dev][i].used && g_slots[dev][i].stream == st) return g_slots[dev][i].done;
   for (int i = 0; i < kSlotsPerDev; ++i) {
     Slot* s = &g_slots[dev][i];
     if (s->used) continue;
-    if (cudaMalloc(&s->flags, MAX_T * MAX_T * sizeof(unsigned)) != cudaSuccess ||
-        cudaMemset(s->flags, 0, MAX_T * MAX_T * sizeof(unsigned)) != cudaSuccess) {
+    if (cudaMalloc(&s->done, MAX_T * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(s->done, 0, MAX_T * sizeof(unsigned long long)) != cudaSuccess) {
       *rc = ipm_set_cuda_error(cudaGetLastError());
       return nullptr;
     }
     s->stream = st;
     s->used = true;
-    return s->flags;
+    return s->done;
   }
   return nullptr;
 }
@@ -629,13 +738,13 @@ int potrf(double* H, int ld, int n, int* info_dev, cudaStream_t st) {
   IPM_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= kMaxDev) return 1;
   if (!g_sms[dev]) IPM_CUDA_CHECK(cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev));
-  unsigned* flags = get_flags(dev, st, &rc);
+  unsigned long long* done = get_counters(dev, st, &rc);
   if (rc) return rc;
-  if (!flags) return 1;
+  if (!done) return 1;
   CUtensorMap tm;
   if (make_operand_map(&tm, H, ld, n, n)) return 1;  // unaligned base: the stream-ordered path reports it
   unsigned epoch = ++g_epoch;
-  if (epoch == 0) epoch = ++g_epoch;  // never 0 (the flags' initial value)
+  if (epoch == 0) epoch = ++g_epoch;  // never 0 (the counters' initial value)
   static bool attr_set = false;
   if (!attr_set) {
     IPM_CUDA_CHECK(cudaFuncSetAttribute(potrf_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -644,7 +753,7 @@ int potrf(double* H, int ld, int n, int* info_dev, cudaStream_t st) {
   const int ntasks = T * (T + 1) / 2;
   const int grid = ntasks < g_sms[dev] ? ntasks : g_sms[dev];
   IPM_CUDA_CHECK(launch_pdl(potrf_dag_kernel, dim3(grid), dim3(THREADS), SMEM, st, tm, H, (long long)ld, n, T, info_dev,
-                            flags, epoch));
+                            done, epoch));
   IPM_LAUNCH_CHECK();
   return IPM_OK;
 }
