@@ -215,6 +215,35 @@ def test_trsv_more_blocks_than_sms():
         assert float(res.max()) < 1e-13
 
 
+@pytest.mark.parametrize("n", [200, 385, 1024, 2500])
+def test_potrf_tile_dag(n):
+    """Single-launch tile-DAG factorisation (csrc/chol.cu, namespace dag): ragged last tile (385 = 3 * 128 + 1), more tasks
+    than SMs (2500: 210 tiles), and a size it hands to the stream-ordered code (200: two tiles)."""
+    H = spd(n, n + 7)
+    Hd, ld = padded(H)
+    low_before = torch.tril(Hd[:, :n], -1).clone()
+    info = torch.full((1,), -7, dtype=torch.int32, device="cuda")
+    for _ in range(2):  # second call: the progress counters carry the previous call's epoch
+        Hd[:, :n] = torch.as_tensor(H, device="cuda")
+        _abi.call("ipm_potrf_upper_dag_f64", Hd.data_ptr(), ld, n, info.data_ptr(), None)
+        torch.cuda.synchronize()
+        assert int(info.item()) == 0
+        U = torch.triu(Hd[:, :n]).cpu().numpy()
+        assert np.max(np.abs(U.T @ U - H)) / np.max(np.abs(H)) < 1e-13
+        assert torch.equal(torch.tril(Hd[:, :n], -1), low_before)
+
+
+def test_potrf_tile_dag_reports_first_bad_pivot():
+    n = 700
+    H = spd(n, 5, cond_pow=1)
+    H[600, 600] = -1.0
+    Hd, ld = padded(H)
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    _abi.call("ipm_potrf_upper_dag_f64", Hd.data_ptr(), ld, n, info.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert int(info.item()) == 601
+
+
 def test_potrf_reports_first_bad_pivot():
     n = 200
     H = spd(n, 3, cond_pow=1)
