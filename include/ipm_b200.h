@@ -12,7 +12,10 @@
  *     16-byte aligned base and an even leading dimension (TMA row stride); the engine pads ld to 16 doubles.
  *   - symmetric matrices: only the UPPER triangle (col >= row) is read / written.  Cholesky is H = U^T U.
  *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream); nothing here
- *     synchronises, allocates device memory, or throws.  Workspace comes from the caller (*_ws_doubles()).
+ *     synchronises or throws.  Workspace comes from the caller (*_ws_doubles()); the only device memory the library
+ *     owns is small per-(device, stream) scratch allocated on first use and kept for the life of the process: the
+ *     stream-K partials of ipm_gemm_tn_f64 (#SMs x 128 KB), the progress counters of the persistent solves and of
+ *     ipm_potrf_upper_dag_f64 (a few KB).  So the FIRST call on a stream must not happen inside a CUDA graph capture.
  *   - return value: IPM_OK, or a negative status.  Numerical failure is NOT a status: ipm_potrf_upper_f64 writes
  *     LAPACK-style `info` to device memory, the line searches write a `stuck` flag (the reference signals these
  *     with LinAlgError / success_flag=False, NewtonSolver.py:130-131,314-330).
