@@ -137,3 +137,35 @@ def test_miplib_loader_validates_shapes(tmp_path):
     miplib.save_lp(f, **bad)
     with pytest.raises(ValueError):
         miplib.load_lp(f)
+
+
+@pytest.mark.parametrize("T,G", [(3, 6), (4, 3), (20, 148), (33, 16), (64, 148)])
+def test_tile_dag_schedule_cannot_deadlock(T, G):
+    """Model of the tile-DAG Cholesky's schedule (csrc/chol.cu, namespace dag): tasks (i, j), i <= j, numbered row-major,
+    CTA c runs tasks c, c + G, ... in order and blocks on ONE progress counter per block column.  Whatever the timing,
+    the lowest-numbered unfinished task is always runnable, every column is published top-down, and all tasks finish."""
+    tasks = [(i, j) for i in range(T) for j in range(i, T)]
+    queues = [tasks[c::G] for c in range(G)]
+    pos = [0] * G
+    done = [0] * T  # published row blocks per block column
+    rng = np.random.RandomState(T * 1000 + G)
+    finished = 0
+    while finished < len(tasks):
+        runnable = []
+        for c in range(G):
+            if pos[c] == len(queues[c]):
+                continue
+            i, j = queues[c][pos[c]]
+            # inputs: U(k, i), U(k, j) for k < i (counters >= i), and U(i, i) for an off-diagonal tile (done[i] >= i + 1)
+            if done[i] >= i and done[j] >= i and (i == j or done[i] >= i + 1):
+                runnable.append(c)
+        assert runnable, "deadlock"
+        lowest = min(tasks.index(queues[c][pos[c]]) for c in range(G) if pos[c] < len(queues[c]))
+        assert lowest in [tasks.index(queues[c][pos[c]]) for c in runnable]
+        c = runnable[rng.randint(len(runnable))]  # an arbitrary runnable CTA finishes next
+        i, j = queues[c][pos[c]]
+        assert done[j] == i  # top-down: the counter of column j goes i -> i + 1
+        done[j] = i + 1
+        pos[c] += 1
+        finished += 1
+    assert done == list(range(1, T + 1))
