@@ -54,12 +54,10 @@ class Launcher:
         self.timed_ops = None  # {"op name": [(start_event, end_event, tag), ...]} when bench.py profiles live
         self.tag = None
         self.stream = None     # raw cudaStream_t handed to every call (None = legacy default stream = torch's default)
-        self.graph_launches = 0  # kernels replayed through CUDA graphs (the library's host-side counter misses them)
 
     def kernel_launches(self):
-        """Kernels launched by libipm_b200 since this launcher was created (process-wide counter) plus the kernels
-        replayed through captured graphs."""
-        return int(_abi.lib().ipm_launch_count() - self._base) + self.graph_launches
+        """Kernels launched by libipm_b200 since this launcher was created (process-wide counter)."""
+        return int(_abi.lib().ipm_launch_count() - self._base)
 
     def timed_range(self, tag):
         """Context manager: CUDA events around a group of launches/collectives (only while bench.py profiles)."""
