@@ -608,13 +608,13 @@ potrf_dag_kernel(const __grid_constant__ CUtensorMap tm, double* __restrict__ H,
     const bool diag = ti == tj;
     double acc[S::MI][S::NI][2];
     zero_acc(acc);
-    long long t0 = DAG_CLOCK();
+    [[maybe_unused]] long long t0 = DAG_CLOCK();
     if (ti > 0) {
       prod.begin(ti, tj);
       for (int p = 0; p < PREFETCH; ++p) prod.issue(warp, lane);
       consume_ktiles<false, S, ISSUE_AT_ONE_TILE>(acc, ring, lm, nullptr, ti * NB, 0, ti * KT_PER_BLOCK, it, warp, lane,
                                                   prod);
-      long long t1 = DAG_CLOCK();
+      [[maybe_unused]] long long t1 = DAG_CLOCK();
       subtract_acc(H, ld, n, diag, acc, ti * BM + lm.wm * 64, tj * BN + lm.wn * 32, lm.g8, lm.l4);
       DAG_MARK(13, t1);
     }
@@ -634,7 +634,7 @@ potrf_dag_kernel(const __grid_constant__ CUtensorMap tm, double* __restrict__ H,
       double* Us = scratch;
       double* Ps = scratch + NB * US_LD;
       double* P = H + (long long)k0 * ld + c0;
-      long long t1 = DAG_CLOCK();
+      [[maybe_unused]] long long t1 = DAG_CLOCK();
       trsm_load_u<true>(Us, H + (long long)k0 * ld + k0, ld, nb);
       DAG_MARK(8, t1);
 #pragma unroll 1
