@@ -60,7 +60,47 @@ def parse():
                     help="lp: BASELINE configs[1] (the headline); socp: configs[3] (n=16384, 256 cones of 64 rows, "
                          "test_SOCP settings) -- use with --shard rows for the cone-sharded Hessian scaling numbers")
     ap.add_argument("--cones", type=int, default=256)
+    ap.add_argument("--factorisation", action="store_true",
+                    help="N = 1: also time the n x n Cholesky alone, stream-ordered and single-launch tile-DAG, and add a "
+                         "'factorisation' object (roofline against the FP64 tensor peak) to the JSON line")
     return ap.parse_args()
+
+
+def factorisation_section(n, reps=5):
+    """ipm_potrf_upper_f64 (stream-ordered) and ipm_potrf_upper_dag_f64 (one persistent launch) on an SPD matrix with
+    the Hessian's structure (C' diag(w) C + I), L2 flushed before every factorisation; n^3 / 3 flop."""
+    from ipm_b200 import _abi
+
+    g = torch.Generator(device="cuda").manual_seed(n)
+    C_ = torch.rand((2 * n, n), dtype=torch.float64, device="cuda", generator=g) * 4 - 2
+    w = torch.rand(2 * n, dtype=torch.float64, device="cuda", generator=g) + 0.5
+    H = torch.zeros((n, n), dtype=torch.float64, device="cuda")
+    _abi.call("ipm_gemm_tn_f64", C_.data_ptr(), n, C_.data_ptr(), n, w.data_ptr(), 1.0, 0.0, H.data_ptr(), n, n, n,
+              2 * n, 1, None)
+    H.diagonal().add_(1.0)
+    del C_
+    work = torch.empty_like(H)
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
+    out = {"n": n, "flop": n ** 3 / 3.0, "l2": "256 MB written between repetitions"}
+    for key, name in (("stream_ordered", "ipm_potrf_upper_f64"), ("tile_dag", "ipm_potrf_upper_dag_f64")):
+        ts = []
+        for _ in range(reps + 1):
+            work.copy_(H)
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            _abi.call(name, work.data_ptr(), n, n, info.data_ptr(), None)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        assert int(info.item()) == 0
+        ms = float(np.median(ts[1:]))
+        tf = out["flop"] / (ms * 1e-3) / 1e12
+        out[key] = {"ms": ms, "achieved": tf, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
+                    "frac": tf / FP64_TENSOR_PEAK_TFLOPS, "entry_point": name}
+    return out
 
 
 class ClockSampler:
@@ -426,6 +466,8 @@ def main():
                          "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s per GPU",
                          "frac": lasso["flop"] / (lasso["ms"] * 1e-3) / 1e12 / world / FP64_TENSOR_PEAK_TFLOPS,
                          "note": "2 n^2 K flop per ADMM iteration over the whole solve() incl. stop checks"}}
+    if args.factorisation and world == 1:
+        line["factorisation"] = factorisation_section(n)
     if not args.no_cpu_baseline and world == 1:
         k, dt = cpu_sample(prob, args.cpu_newton_steps)
         line["cpu_baseline"] = {"value": k / dt, "unit": "Newton steps/s", "cores": blas_threads(), "kind": "port",
