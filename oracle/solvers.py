@@ -139,6 +139,17 @@ class _BarrierSolver:
         self.t_final = t
         return self.value
 
+    def dual_variables(self):
+        """(lam_star, v_star) of LPSolver.py:641-646 / QPSolver.py:626-631: 1 / (t slacks(x*)) in the slack layout
+        [C rows | upper bounds | lower bounds] and v / t, both with the LAST t of the outer loop (already multiplied by
+        mu when the loop ran out of iterations instead of meeting the gap test)."""
+        lam = None
+        if self.num_constraints > 0:
+            self.fm.move(self.xstar)
+            lam = 1 / (self.t_final * self.fm.slacks)
+        nu = None if self.E is None else self.v / self.t_final
+        return lam, nu
+
 
 class OracleLP(_BarrierSolver):
     eq_tol_scale_n = True

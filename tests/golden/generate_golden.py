@@ -178,9 +178,40 @@ def method_cases():
         json.dump(out, f, indent=1)
 
 
+def dual_cases():
+    """``get_dual_variables=True`` / ``track_loss=True`` outputs (LPSolver.py:608-609,641-646, QPSolver.py:593-594,
+    626-631): lam_star = 1 / (t slacks(x*)) in the slack layout [C rows | upper bounds | lower bounds], v_star = v / t
+    with the LAST t of the outer loop, objective_vals per accepted centering step."""
+    out = []
+    for cls, gen, gen_kwargs, settings, name in (
+            (LPSolver, "lp_testsolver", dict(seed=1, n=100, m=80, k=20, count=1), problems.LP_TEST_SETTINGS,
+             "lp_seed1_n100_0_duals"),
+            (QPSolver, "qp_testsolver", dict(seed=1, n=100, m=80, k=20, count=1), problems.QP_TEST_SETTINGS,
+             "qp_seed1_n100_0_duals"),
+            (LPSolver, "lp_dense_family", dict(seed=0, n=64, warm=True), {}, "lp_dense_n64_warm_duals")):
+        prob = getattr(problems, gen)(**gen_kwargs)
+        if isinstance(prob, list):
+            prob = prob[0]
+        np.random.seed(0)
+        s = cls(**prob, check_cvxpy=False, suppress_print=True, get_dual_variables=True, track_loss=True, **settings)
+        val = s.solve()
+        rec = dict(name=name, solver=cls.__name__, generator=gen, generator_kwargs=gen_kwargs, settings=settings,
+                   value=float(val), objective_vals=[float(v) for v in s.objective_vals],
+                   lam_star=[float(v) for v in np.asarray(s.lam_star).ravel()] if hasattr(s, "lam_star") else None,
+                   v_star=[float(v) for v in np.asarray(s.v_star).ravel()] if hasattr(s, "v_star") else None)
+        print(name, rec["value"], len(rec["objective_vals"]), None if rec["lam_star"] is None else len(rec["lam_star"]),
+              None if rec["v_star"] is None else len(rec["v_star"]))
+        out.append(rec)
+    with open(os.path.join(HERE, "dual_cases.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 def main():
     if "--methods-only" in sys.argv:
         method_cases()
+        return
+    if "--duals-only" in sys.argv:
+        dual_cases()
         return
     barrier = []
     for i in range(3):
