@@ -206,7 +206,32 @@ def dual_cases():
         json.dump(out, f, indent=1)
 
 
+def behaviour_cases():
+    """Control-flow behaviour of solve(): the phase-I failure on an empty feasible set (LPSolver.py:553-558) and a second
+    solve() on the same object (quirk Q7: the iterate was updated in place, LPSolver.py:544, so the second run
+    starts from the first one's end point)."""
+    out = []
+    prob = problems.lp_small_polytope(infeasible=True)
+    try:
+        LPSolver(**prob, check_cvxpy=False, suppress_print=True).solve()
+        out.append(dict(name="lp_empty_set", error=None))
+    except Exception as e:  # noqa: BLE001
+        out.append(dict(name="lp_empty_set", error=type(e).__name__, message=str(e)))
+    s = LPSolver(**problems.lp_small_polytope(), check_cvxpy=False, suppress_print=True)
+    v1 = float(s.solve())
+    it1 = [int(k) for k in s.inner_iters]
+    v2 = float(s.solve())
+    it2 = [int(k) for k in s.inner_iters]
+    out.append(dict(name="lp_solve_twice", first=dict(value=v1, inner_iters=it1), second=dict(value=v2, inner_iters=it2)))
+    print(out)
+    with open(os.path.join(HERE, "behaviour_cases.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 def main():
+    if "--behaviour-only" in sys.argv:
+        behaviour_cases()
+        return
     if "--methods-only" in sys.argv:
         method_cases()
         return

@@ -118,3 +118,17 @@ def lp_bounds_only(seed, n, p=0):
         A = rs.uniform(-2, 2, (p, n))
         out.update(A=A, b=A @ rs.uniform(-2, 2, n))
     return out
+
+
+def lp_small_polytope(seed=3, n=12, infeasible=False):
+    """Small LP over random half-spaces and the box [-3, 3]^n; `infeasible` adds  sum x <= 1  and  sum x >= 2  (empty set:
+    the phase-I ValueError of LPSolver.py:553-558).  Without them the default x0 (box midpoint 0) is strictly feasible
+    (d >= 1), phase-I is skipped, and the main loop updates the solver's own iterate in place."""
+    rs = np.random.RandomState(seed)
+    C = rs.uniform(-1, 1, (6, n))
+    d = rs.uniform(1, 2, 6)
+    c = rs.uniform(-1, 1, n)
+    if infeasible:
+        C = np.vstack([C, np.ones((1, n)), -np.ones((1, n))])
+        d = np.concatenate([d, [1.0], [-2.0]])
+    return dict(c=c, C=C, d=d, lower_bound=-3, upper_bound=3)

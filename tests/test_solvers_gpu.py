@@ -174,3 +174,19 @@ def test_dual_variables_and_loss_trace(case):
     if case["v_star"] is not None:
         v, v_ref = np.asarray(s.v_star, dtype=float).ravel(), np.array(case["v_star"])
         assert np.linalg.norm(v - v_ref) <= 1e-2 * (1e-12 + np.linalg.norm(v_ref))
+
+
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent; not yet run on a device")
+def test_control_flow_behaviour():
+    """Phase-I failure on an empty feasible set (LPSolver.py:553-558) and a second solve() on the same object (quirk Q7)."""
+    cases = {c["name"]: c for c in load_golden("behaviour_cases.json")}
+    cls = _solver_class("LPSolver")
+    g = cases["lp_empty_set"]
+    with pytest.raises(ValueError, match=g["message"]):
+        cls(**problems.lp_small_polytope(infeasible=True), check_cvxpy=False, suppress_print=True).solve()
+    g = cases["lp_solve_twice"]
+    s = cls(**problems.lp_small_polytope(), check_cvxpy=False, suppress_print=True)
+    for key in ("first", "second"):
+        val = s.solve()
+        assert val == pytest.approx(g[key]["value"], rel=1e-6, abs=1e-9)
+        assert_iters_close(s.inner_iters, g[key]["inner_iters"])
