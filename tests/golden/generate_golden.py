@@ -228,7 +228,29 @@ def behaviour_cases():
         json.dump(out, f, indent=1)
 
 
+def option_cases():
+    """Constructor options outside the defaults: try_diag=False on a bounds-only LP (dense Cholesky of a diagonal Hessian,
+    LPSolver.py:436-446), update_slacks_every > 0 (slacks refreshed inside the Armijo loop, NewtonSolver.py:196-202),
+    use_psd_condition=True (SOCPSolver.py:20-54).  Same problems as barrier_cases.json."""
+    with open(os.path.join(HERE, "barrier_cases.json")) as f:
+        base = {c["name"]: c for c in json.load(f)}
+    out = []
+    for src, extra, cls in (("lp_bounds_only_n50", dict(try_diag=False), LPSolver),
+                            ("lp_dense_n64_warm", dict(update_slacks_every=3), LPSolver),
+                            ("lp_dense_n64_cold", dict(update_slacks_every=2), LPSolver),
+                            ("socp_n48_warm", dict(use_psd_condition=True), SOCPSolver)):
+        b = base[src]
+        tag = "_".join(f"{k}_{v}" for k, v in extra.items())
+        out.append(run_barrier(cls, b["generator"], b["generator_kwargs"], b["index"], dict(b["settings"], **extra),
+                               f"{src}__{tag}"))
+    with open(os.path.join(HERE, "option_cases.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 def main():
+    if "--options-only" in sys.argv:
+        option_cases()
+        return
     if "--behaviour-only" in sys.argv:
         behaviour_cases()
         return
