@@ -7,14 +7,12 @@ import torch
 import torch.distributed as tdist
 
 try:
-    from . import _abi
     from ._solver_base import BarrierSolverBase, as_bound, check_bounds, check_pair, default_x0, HostArray
     from .engine import F64, Launcher, LinearNewton, LinearProblemData
     from .PhaseOneSolver import PhaseOneSolver
     from .dist import row_range
     from .sharded_engine import ShardedLinearNewton
 except ImportError:  # flat-module use
-    import _abi
     from _solver_base import BarrierSolverBase, as_bound, check_bounds, check_pair, default_x0, HostArray
     from engine import F64, Launcher, LinearNewton, LinearProblemData
     from PhaseOneSolver import PhaseOneSolver

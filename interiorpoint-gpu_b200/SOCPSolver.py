@@ -11,7 +11,6 @@ import torch
 import torch.distributed as tdist
 
 try:
-    from . import _abi
     from ._solver_base import BarrierSolverBase, as_bound, check_bounds, default_x0, HostArray
     from .cone_engine import ConeNewton, ConeProblemData
     from .dist import row_range
@@ -19,7 +18,6 @@ try:
     from .PhaseOneSolver import PhaseOneSolver
     from .sharded_engine import ShardedConeNewton
 except ImportError:  # flat-module use
-    import _abi
     from _solver_base import BarrierSolverBase, as_bound, check_bounds, default_x0, HostArray
     from cone_engine import ConeNewton, ConeProblemData
     from dist import row_range

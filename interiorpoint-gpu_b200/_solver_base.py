@@ -7,7 +7,10 @@ device engine.  Only scalars cross the PCIe bus inside ``solve()``.
 import numpy as np
 import torch
 
-from . import _abi
+try:
+    from . import _abi
+except ImportError:  # flat-module use
+    import _abi
 
 
 class HostArray(np.ndarray):

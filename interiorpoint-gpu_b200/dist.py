@@ -11,7 +11,6 @@ Two partitionings exist on this path:
 """
 
 import numpy as np
-import torch
 import torch.distributed as dist
 
 

@@ -2,7 +2,6 @@
 symbol include/ipm_b200.h declares, the ctypes table agrees with the header, and the product path fails loudly
 (no CPU fallback) when no B200 is visible."""
 
-import ctypes
 import os
 import re
 

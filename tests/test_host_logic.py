@@ -169,3 +169,21 @@ def test_tile_dag_schedule_cannot_deadlock(T, G):
         pos[c] += 1
         finished += 1
     assert done == list(range(1, T + 1))
+
+
+def test_flat_module_layout_imports_like_the_reference():
+    """with interiorpoint-gpu_b200/ on sys.path the reference's flat module names work
+    (`from LPSolver import LPSolver`, ...).  Fresh interpreter, so the package import of this test session cannot mask
+    a missing flat-import fallback."""
+    import os
+    import subprocess
+    import sys
+
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "interiorpoint-gpu_b200")
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from LPSolver import LPSolver\nfrom QPSolver import QPSolver\nfrom SOCPSolver import SOCPSolver\n"
+            "from LassoSolver import LassoSolver\nfrom PhaseOneSolver import PhaseOneSolver\nimport PhaseOne, harness, miplib\n"
+            "print(LPSolver.__name__, QPSolver.__name__, SOCPSolver.__name__, LassoSolver.__name__)\n" % pkg)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == ["LPSolver", "QPSolver", "SOCPSolver", "LassoSolver"]

@@ -1,7 +1,6 @@
 """BASELINE cfg-5: LassoSolver ADMM batch, A 2048x512 (+bias), K problems (default 4096).  Prints JSON."""
 import json
 import sys
-import time
 
 import numpy as np
 import torch
