@@ -91,3 +91,42 @@ def test_product_path_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_every_call_site_passes_the_declared_number_of_arguments():
+    """Static check of the host code: every `L("ipm_...", ...)` (Launcher call: the stream is appended) and
+    `_abi.call("ipm_...", ...)` in the package passes as many positional arguments as the ctypes table declares.
+    ctypes only complains at run time on a GPU box; this catches arity slips on the CPU."""
+    import ast
+    import glob
+    import os
+
+    from ipm_b200 import _abi
+
+    pkg = os.path.dirname(_abi.__file__)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(pkg, "*.py")) + glob.glob(os.path.join(root, "tools", "*.py")) + glob.glob(
+        os.path.join(root, "tests", "*.py")) + [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")]
+    checked = 0
+    for path in sorted(files):
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            if not isinstance(node, ast.Call) or not node.args:
+                continue
+            first = node.args[0]
+            if not (isinstance(first, ast.Constant) and isinstance(first.value, str) and first.value.startswith("ipm_")):
+                continue
+            if any(isinstance(a, ast.Starred) for a in node.args):
+                continue  # forwarded argument lists are checked where they are built
+            name = first.value
+            f = node.func
+            is_abi_call = isinstance(f, ast.Attribute) and f.attr == "call"
+            is_launcher = (isinstance(f, ast.Name) and f.id == "L") or (isinstance(f, ast.Attribute) and f.attr == "L")
+            if not (is_abi_call or is_launcher):
+                continue  # some other function that happens to take an "ipm_..." string
+            assert name in _abi.SIGNATURES, f"{path}:{node.lineno}: {name} is not in the ctypes table"
+            want = len(_abi.SIGNATURES[name][1]) - (0 if is_abi_call else 1)
+            got = len(node.args) - 1
+            assert got == want, f"{path}:{node.lineno}: {name} takes {want} arguments here, {got} given"
+            checked += 1
+    assert checked > 40
