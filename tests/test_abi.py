@@ -130,3 +130,35 @@ def test_every_call_site_passes_the_declared_number_of_arguments():
             assert got == want, f"{path}:{node.lineno}: {name} takes {want} arguments here, {got} given"
             checked += 1
     assert checked > 40
+
+
+def test_definitions_match_the_header():
+    """The .cu files do not include the public header (they are compiled as C++ with their own helpers), so nothing
+    but this test ties the parameter list of every `extern "C"` definition to its prototype in include/ipm_b200.h:
+    same number of parameters, same parameter types in the same order."""
+    import glob
+    import os
+
+    def norm(params):
+        out = []
+        for p in params.split(","):
+            p = re.sub(r"\b(const|__restrict__)\b", " ", p)
+            p = re.sub(r"\s+", " ", p).strip()
+            m = re.match(r"^(.*?)(\w+)$", p)  # drop the parameter name
+            out.append(re.sub(r"\s+", "", m.group(1)) if m and m.group(1).strip() else re.sub(r"\s+", "", p))
+        return out
+
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    protos = {m.group(1): norm(m.group(2)) for m in re.finditer(r"\b(ipm_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+              if m.group(2).strip() not in ("", "void")}
+    csrc = os.path.join(os.path.dirname(HEADER), "..", "interiorpoint-gpu_b200", "csrc")
+    seen = set()
+    for path in glob.glob(os.path.join(csrc, "*.cu")):
+        src = re.sub(r"//[^\n]*", "", open(path).read())
+        for m in re.finditer(r'extern "C"\s+[\w\s\*]*?\b(ipm_\w+)\s*\(([^{;]*?)\)\s*\{', src, flags=re.S):
+            name, params = m.group(1), m.group(2)
+            if name not in protos:
+                continue  # library-internal helpers are not in the header
+            assert norm(params) == protos[name], f"{os.path.basename(path)}: {name}: {norm(params)} vs header {protos[name]}"
+            seen.add(name)
+    assert seen == set(protos), sorted(set(protos) - seen)
