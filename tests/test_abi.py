@@ -162,3 +162,33 @@ def test_definitions_match_the_header():
             assert norm(params) == protos[name], f"{os.path.basename(path)}: {name}: {norm(params)} vs header {protos[name]}"
             seen.add(name)
     assert seen == set(protos), sorted(set(protos) - seen)
+
+
+def test_ctypes_argument_types_match_the_header():
+    """Same table, types this time: a c_int where the prototype says long long (or a double passed as an int) would be
+    silently misread on the device side."""
+    import ctypes as C
+
+    from ipm_b200 import _abi
+
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    scalars = {"int": C.c_int, "double": C.c_double, "longlong": C.c_longlong, "unsignedlonglong": C.c_ulonglong,
+               "unsignedint": C.c_uint, "unsigned": C.c_uint}
+    for m in re.finditer(r"\b(ipm_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        name, params = m.group(1), m.group(2).strip()
+        if params in ("", "void"):
+            continue
+        argtypes = _abi.SIGNATURES[name][1]
+        for k, p in enumerate(params.split(",")):
+            p = re.sub(r"\bconst\b", " ", p)
+            mm = re.match(r"^(.*?)(\w+)\s*$", p.strip())
+            ctype = re.sub(r"\s+", "", mm.group(1))
+            got = argtypes[k]
+            if ctype.endswith("**"):
+                want = {C.POINTER(C.c_void_p)}
+            elif ctype.endswith("*"):
+                # scalar outputs on the HOST are bound as typed pointers, device pointers as void*
+                want = {C.c_void_p, C.POINTER(scalars.get(ctype[:-1], C.c_void_p))}
+            else:
+                want = {scalars[ctype]}
+            assert got in want, f"{name} argument {k} ({p.strip()}): ctypes {got}, header {ctype}"
