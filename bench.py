@@ -257,10 +257,23 @@ def lasso_section(K, rank, world):
                 flop=2.0 * n1 * n1 * len(cols) * its, h2d=s2.h2d_bytes, d2h=int(X2.nbytes))
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank, which would time the CPU arm on ONE core.  The CPU arm runs on
+    rank 0 alone (the other ranks exit), so it may -- and per the contract must -- use every core of the host."""
+    try:
+        import scipy.linalg  # noqa: F401  (SciPy ships its own OpenBLAS; it must be loaded before the limit is raised)
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=len(os.sched_getaffinity(0)), user_api="blas")
+    except Exception:
+        pass
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    use_all_host_threads()
     prob, m = workload(args, 0)
     times, steps = [], 0
     for i in range(args.warmup + args.steps):
@@ -469,6 +482,7 @@ def main():
     if args.factorisation and world == 1:
         line["factorisation"] = factorisation_section(n)
     if not args.no_cpu_baseline and world == 1:
+        use_all_host_threads()
         k, dt = cpu_sample(prob, args.cpu_newton_steps)
         line["cpu_baseline"] = {"value": k / dt, "unit": "Newton steps/s", "cores": blas_threads(), "kind": "port",
                                 "sample": f"{k} full-size Newton iterations (first centering step) of the oracle, "
