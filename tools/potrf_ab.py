@@ -9,6 +9,13 @@ sys.path.insert(0, ".")
 from ipm_b200 import _abi  # noqa: E402
 
 _abi.require_device()
+NAMES = ["ipm_potrf_upper_f64", "ipm_potrf_upper_dag_f64"]
+if hasattr(_abi.lib(), "ipm_internal_potrf_dag2_f64"):  # pipelined variant while it is being validated
+    import ctypes as C
+
+    fn = _abi.lib().ipm_internal_potrf_dag2_f64
+    fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    NAMES.append("ipm_internal_potrf_dag2_f64")
 
 
 def spd(n, seed):
@@ -33,7 +40,7 @@ for n in (385, 1024, 2500, 4097):
     H = spd(n, n)
     ld = (n + 15) // 16 * 16
     out = {}
-    for name in ("ipm_potrf_upper_f64", "ipm_potrf_upper_dag_f64"):
+    for name in NAMES:
         Hd, info = factor(name, H, n, ld)
         U = torch.triu(Hd[:, :n])
         err = float(((U.T @ U - H).abs().max() / H.abs().max()).item())
@@ -47,7 +54,7 @@ for n in (385, 1024, 2500, 4097):
 n = 700
 H = spd(n, 7)
 H[600, 600] = -1.0
-for name in ("ipm_potrf_upper_f64", "ipm_potrf_upper_dag_f64"):
+for name in NAMES:
     _, info = factor(name, H, n, 704)
     print(name, "bad pivot info =", info, flush=True)
     assert info == 601
@@ -57,7 +64,7 @@ for n in [int(a) for a in sys.argv[1:]] or [8192]:
     H = spd(n, 1)
     work = torch.empty_like(H)
     info = torch.zeros(1, dtype=torch.int32, device="cuda")
-    for name in ("ipm_potrf_upper_f64", "ipm_potrf_upper_dag_f64"):
+    for name in NAMES:
         ts = []
         for rep in range(6):
             work.copy_(H)
