@@ -4,13 +4,14 @@
 # 1. the late tests that are in the suite as non-strict xfails (duals / loss trace, constructor options, control flow)
 # 2. the whole -m gpu suite with the tile-DAG Cholesky as the factorisation (IPM_POTRF_DAG=1)
 # 3. bench.py --factorisation (both Cholesky entry points inside the bench harness)
-# 4. the pipelined tile-DAG variant: build it as a variant library from the patch, check and time all three entry points
+# 4. the pipelined tile-DAG variant, check and time all three entry points.  Build the variant library BEFORE the call
+#    (built .so files travel to the box):
+#      git apply tools/experiments/dag_pipelined.patch && python interiorpoint-gpu_b200/build.py --variant dag2 \
+#        && git checkout interiorpoint-gpu_b200/csrc/chol.cu && python interiorpoint-gpu_b200/build.py --force
 set -x
 cd "$(dirname "$0")/../.."
 timeout 300 python -m pytest tests/test_solvers_gpu.py -q --runxfail -k "dual or options or control_flow" 2>&1 | tail -15
 IPM_POTRF_DAG=1 timeout 400 python -m pytest tests -q -x -m gpu 2>&1 | tail -5
 timeout 400 python bench.py --steps 1 --warmup 3 --factorisation --no-e2e --lasso-k 0 --no-cpu-baseline 2>&1 | tail -1 \
   | python -c "import sys, json; print(json.dumps(json.loads(sys.stdin.read())['factorisation'], indent=1))"
-git apply tools/experiments/dag_pipelined.patch && python interiorpoint-gpu_b200/build.py --variant dag2 \
-  && IPM_B200_LIB=$PWD/interiorpoint-gpu_b200/lib/variants/libdag2.so timeout -s KILL 120 python tools/potrf_ab.py 2048 4096 8192 16384
-git checkout interiorpoint-gpu_b200/csrc/chol.cu tools/potrf_ab.py
+IPM_B200_LIB=$PWD/interiorpoint-gpu_b200/lib/variants/libdag2.so timeout -s KILL 120 python tools/potrf_ab.py 2048 4096 8192 16384
