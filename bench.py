@@ -83,7 +83,14 @@ def factorisation_section(n, reps=5):
     info = torch.zeros(1, dtype=torch.int32, device="cuda")
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
     out = {"n": n, "flop": n ** 3 / 3.0, "l2": "256 MB written between repetitions"}
-    for key, name in (("stream_ordered", "ipm_potrf_upper_f64"), ("tile_dag", "ipm_potrf_upper_dag_f64")):
+    import ctypes as C
+
+    lib = _abi.lib()
+    for nm in ("ipm_internal_potrf_stream_f64", "ipm_internal_potrf_dag2_f64"):  # library-internal A/B entry points
+        getattr(lib, nm).restype, getattr(lib, nm).argtypes = C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                                                         C.c_void_p]
+    for key, name in (("default", "ipm_potrf_upper_f64"), ("stream_ordered", "ipm_internal_potrf_stream_f64"),
+                      ("tile_dag", "ipm_potrf_upper_dag_f64"), ("tile_dag_pipelined", "ipm_internal_potrf_dag2_f64")):
         ts = []
         for _ in range(reps + 1):
             work.copy_(H)
@@ -91,7 +98,7 @@ def factorisation_section(n, reps=5):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             e0.record()
-            _abi.call(name, work.data_ptr(), n, n, info.data_ptr(), None)
+            _abi.check(getattr(lib, name)(work.data_ptr(), n, n, info.data_ptr(), None), name)
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))

@@ -37,6 +37,15 @@ int ipm_abi_version(void);
 int ipm_device_ok(void);                       /* IPM_OK iff the current device is compute capability 10.x */
 const char* ipm_last_cuda_error(void);
 unsigned long long ipm_launch_count(void);     /* kernels launched by this library in this process */
+/* Watchdog of the device-side spin waits (persistent kernels whose CTAs -- or whose peers on other GPUs -- wait for
+ * each other: tile-DAG Cholesky, stream-K GEMM, triangular solves, the peer-memory Hessian exchange).  A wait that
+ * exceeds the limit records a code (1 potrf-dag, 2 stream-K, 3/4 peer Hessian, 5 trsv, 6 lasso, 7 peer potrf), every
+ * other wait of the process then returns at once, the kernels finish on garbage in bounded time, and potrf reports
+ * info = -1.  Read it after synchronising the stream; 0 = no fault.  The reference has no counterpart (a failed CuPy
+ * kernel raises on the next call). */
+unsigned int ipm_device_fault(void);
+void ipm_clear_device_fault(void);
+unsigned int ipm_set_spin_limit(unsigned int mcycles);  /* limit in units of 2^20 SM cycles; returns the old value */
 
 /* ---- dense contraction core (TMA + FP64 DMMA) ----------------------------------------------------------- */
 /* D = beta*D + alpha * A^T diag(w) B.   A: K x M (lda), B: K x N (ldb), w: K or NULL, D: M x N (ldd).
@@ -111,7 +120,7 @@ int ipm_scale_shift_f64(const double* in, int ldi, double* out, int ldo, int row
  * NewtonSolverInfeasibleStart.py:398,426,455,473,780,795; LassoSolver.py:160,178. */
 int ipm_potrf_upper_f64(double* H, int ld, int n, int* info_dev, void* stream);
 /* Same contract, ONE persistent launch: left-looking tile DAG with device-side flags (csrc/chol.cu, namespace dag).
- * Used by ipm_potrf_upper_f64 itself when the environment has IPM_POTRF_DAG=1; sizes it does not cover
+ * Used by ipm_potrf_upper_f64 itself for n >= 6144 (IPM_POTRF_DAG=1: every admissible size, =0: never); sizes it does not cover
  * (n <= 256, n > 32768) go through the stream-ordered code.  One factorisation at a time per stream. */
 int ipm_potrf_upper_dag_f64(double* H, int ld, int n, int* info_dev, void* stream);
 /* b <- U^{-T} b (trans = 1) or U^{-1} b (trans = 0), in place; ws is unused (kept for ABI stability, may be NULL).

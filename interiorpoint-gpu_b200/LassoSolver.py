@@ -166,6 +166,7 @@ class LassoSolver:
             if check:
                 host.copy_(norms, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
+                _abi.check_device_fault()
                 r_norm, d_norm, a_norm, u_norm = (float(np.sqrt(v)) for v in host.tolist())
                 tol_primal = stop_mult + self.EPS_REL * a_norm
                 tol_dual = stop_mult + self.EPS_REL * self.rho * u_norm

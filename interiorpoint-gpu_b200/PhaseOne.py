@@ -34,7 +34,7 @@ class PhaseOneSolver:
         m, n = G.shape
         self.m, self.n = m, n
         device = torch.device("cuda", torch.cuda.current_device())
-        self.data = LinearProblemData(n, device, C=G, d=h)
+        self.data = LinearProblemData(n, device, C=G, d=np.asarray(h, dtype=np.float64).ravel())
         self.ns = LinearNewton(self.data, phase1=True, max_iters=max_iter_newton, epsilon=eps, alpha=0.2, beta=0.7)
         self.ns.shift = 0.01  # "some conditioning", PhaseOne.py:123-127
         self.z = torch.zeros(n + 1, dtype=F64, device=device)
@@ -51,6 +51,43 @@ class PhaseOneSolver:
     @property
     def s(self):
         return float(self.z[self.n])
+
+    # ---- the reference's public pieces (exercised by its known-answer tests, AutomatedTestsPhaseOne.py:15-232) ----
+    def phase_one_objective(self, x, s, t):
+        """t s - sum log(s + h - G x) at the GIVEN point (PhaseOne.py:171-185)."""
+        ns, ws = self.ns, self.ns.ws
+        z = torch.empty(self.n + 1, dtype=F64, device=self.z.device)
+        z[: self.n].copy_(torch.as_tensor(np.asarray(x, dtype=np.float64)))
+        z[self.n] = float(s)
+        ns._eval(z, ws.tri)
+        return float(t) * float(s) - float(ws.tri.red[0])
+
+    def phase_one_check_feasibility(self, x, s):
+        """max(G x - h) < s (PhaseOne.py:220-238)."""
+        z = torch.zeros(self.n + 1, dtype=F64, device=self.z.device)
+        z[: self.n].copy_(torch.as_tensor(np.asarray(x, dtype=np.float64)))
+        return bool(-self.ns.min_slack(z) < float(s))
+
+    def phase_one_gradient(self, t):
+        """[sum_i g_i / f_i ; t - sum_i 1 / f_i] at the current (x, s) (PhaseOne.py:240-272)."""
+        ns, ws = self.ns, self.ns.ws
+        ns.set_t(t)
+        ns._eval(self.z, ws.cur)
+        ns._gradient(float(t), None, ws.cur, ws.g, want_border=True)
+        return HostArray(ws.g[: self.n + 1].cpu().numpy())
+
+    def phase_one_hessian(self):
+        """Full symmetric (n+1) x (n+1) Hessian WITHOUT the 0.01 I conditioning (PhaseOne.py:274-328)."""
+        ns, ws = self.ns, self.ns.ws
+        ns._eval(self.z, ws.cur)
+        ns._gradient(ns.t, None, ws.cur, ws.g, want_border=True)
+        shift, ns.shift = ns.shift, 0.0
+        try:
+            ns._hessian(ns.t)
+        finally:
+            ns.shift = shift
+        U = torch.triu(ws.H[: ns.nz, : ns.nz])
+        return HostArray((U + torch.triu(U, 1).T).cpu().numpy())
 
     def phase_one_newtons_method(self, t):
         """PhaseOne.py:109-162.  Returns True if the Newton iteration cap was reached."""

@@ -23,6 +23,9 @@ SIGNATURES = {
     "ipm_device_ok": (_i, []),
     "ipm_last_cuda_error": (C.c_char_p, []),
     "ipm_launch_count": (C.c_ulonglong, []),
+    "ipm_device_fault": (C.c_uint, []),
+    "ipm_clear_device_fault": (None, []),
+    "ipm_set_spin_limit": (C.c_uint, [C.c_uint]),
     "ipm_gemm_tn_f64": (_i, [_dp, _i, _dp, _i, _dp, _d, _d, _dp, _i, _i, _i, _i, _i, _dp]),
     "ipm_gemv_n_f64": (_i, [_dp, _i, _i, _i, _dp, _dp, _d, _d, _dp]),
     "ipm_gemv_t_ws_doubles": (_ll, [_i, _i, _i]),
@@ -105,6 +108,23 @@ def check(rc, what=""):
     if rc == IPM_ERR_NO_DEVICE:
         raise IpmError(f"{what}: no sm_100 device / driver entry point")
     raise IpmError(f"{what}: status {rc}")
+
+
+FAULTS = {1: "tile-DAG Cholesky: a column-progress counter never arrived",
+          2: "persistent GEMM: a stream-K partial never arrived",
+          3: "row-sharded Hessian: a peer's partial tile never arrived",
+          4: "row-sharded Hessian: the owners' final tiles never arrived",
+          5: "triangular solve: a solution block was never published",
+          6: "persistent ADMM kernel: a neighbour panel never arrived",
+          7: "distributed Cholesky: a peer's tiles never arrived"}
+
+
+def check_device_fault():
+    """Raise if a device-side wait gave up (include/ipm_b200.h: ipm_device_fault).  Call after a stream sync."""
+    code = lib().ipm_device_fault()
+    if code:
+        lib().ipm_clear_device_fault()
+        raise IpmError(f"device watchdog fired (code {code}): {FAULTS.get(code, 'unknown wait')}")
 
 
 def ptr(t):

@@ -191,6 +191,7 @@ class BarrierSolverBase:
             t = t * self.mu
             ns.set_t(t)
         self.xstar_device = best_x
+        self.t_final = t  # the t the dual variables are formed with (LPSolver.py:641-646)
         self.xstar = HostArray(best_x.cpu().numpy())
         if self.get_dual_variables:
             self._dual_variables(best_x, t)

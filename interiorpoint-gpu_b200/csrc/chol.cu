@@ -223,11 +223,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) potf2_kernel(double* __restrict
 }
 
 static int launch_potf2(double* Akk, long long ld, int nb, int k0, int* info, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    IPM_CUDA_CHECK(cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM));
-    attr_set = true;
-  }
+  static bool attr_set[kMaxDevices];
+  IPM_CUDA_CHECK(ensure_dynamic_smem(potf2_kernel, PF_SMEM, attr_set));
   IPM_CUDA_CHECK(launch_pdl(potf2_kernel, dim3(1), dim3(PF_THREADS), PF_SMEM, st, Akk, ld, nb, k0, info));
   IPM_LAUNCH_CHECK();
   return IPM_OK;
@@ -413,11 +410,8 @@ static int launch_trsm_panel(const double* U11, long long ldu, int nb, double* P
                              cudaStream_t st) {
   if (ncols <= 0) return IPM_OK;
   const int smem = (NB * US_LD + NB * PS_LD) * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
-    IPM_CUDA_CHECK(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  static bool attr_set[kMaxDevices];
+  IPM_CUDA_CHECK(ensure_dynamic_smem(trsm_panel_kernel, smem, attr_set));
   IPM_CUDA_CHECK(launch_pdl(trsm_panel_kernel, dim3(ceil_div(ncols, TP_COLS)), dim3(256), smem, st, U11, ldu, nb, P, ldp,
                             ncols));
   IPM_LAUNCH_CHECK();
@@ -484,11 +478,15 @@ __device__ __forceinline__ int column_progress(const unsigned long long* p, unsi
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return (unsigned)(v >> 32) == epoch ? (int)(unsigned)v : 0;
 }
-__device__ __forceinline__ int wait_column(const unsigned long long* p, unsigned epoch, int need) {
-  int r;
-  do {
-    r = column_progress(p, epoch);
-  } while (r < need);
+// Bounded (common.cuh: spin_wait).  When the watchdog fires, info becomes -1 and the wait reports the column as
+// complete, so that the task -- and with it the whole grid -- finishes on garbage instead of hanging.
+__device__ __forceinline__ int wait_column(const unsigned long long* p, unsigned epoch, int need, unsigned int* fault,
+                                           int* info) {
+  int r = 0;
+  if (!spin_wait([&] { return (r = column_progress(p, epoch)) >= need; }, fault, IPM_FAULT_POTRF_DAG)) {
+    atomicCAS(info, 0, -1);
+    r = MAX_T;
+  }
   return r;
 }
 
@@ -498,6 +496,8 @@ struct Producer {
   Ring ring;
   const unsigned long long* done;
   unsigned epoch;
+  unsigned int* fault;
+  int* info;
   int ti, tj, kt, k1, ready_i, ready_j;  // ready_*: row blocks of columns ti / tj known to be published
   uint32_t it;
   __device__ __forceinline__ void begin(int i, int j) {
@@ -511,9 +511,9 @@ struct Producer {
 #ifdef IPM_DAG_TIMING
         const long long t0 = clock64();
 #endif
-        if (ready_i < need) ready_i = wait_column(done + ti, epoch, need);
+        if (ready_i < need) ready_i = wait_column(done + ti, epoch, need, fault, info);
         if (tj == ti) ready_j = ready_i;
-        if (ready_j < need) ready_j = wait_column(done + tj, epoch, need);
+        if (ready_j < need) ready_j = wait_column(done + tj, epoch, need, fault, info);
         asm volatile("fence.proxy.async;" ::: "memory");  // the tiles were written through the generic proxy
 #ifdef IPM_DAG_TIMING
         if (wp == 0) g_dag_t[blockIdx.x * 16 + 7] += clock64() - t0;
@@ -575,7 +575,8 @@ __device__ __forceinline__ void subtract_acc(double* __restrict__ H, long long l
 
 __global__ void __launch_bounds__(THREADS, 1)
 potrf_dag_kernel(const __grid_constant__ CUtensorMap tm, double* __restrict__ H, long long ld, int n, int T,
-                 int* __restrict__ info, unsigned long long* __restrict__ done, unsigned epoch) {
+                 int* __restrict__ info, unsigned long long* __restrict__ done, unsigned epoch,
+                 unsigned int* __restrict__ fault) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ double rinv[NB];
   __shared__ double rs[32];
@@ -598,7 +599,7 @@ potrf_dag_kernel(const __grid_constant__ CUtensorMap tm, double* __restrict__ H,
   __syncthreads();
   pdl_wait();
   const LaneMap lm = make_lane_map<S>(warp, lane);
-  Producer prod{&tm, ring, done, epoch, 0, 0, 0, 0, 0, 0, 0u};
+  Producer prod{&tm, ring, done, epoch, fault, info, 0, 0, 0, 0, 0, 0, 0u};
   uint32_t it = 0;
   const int ntasks = T * (T + 1) / 2;
   const long long t_kernel = DAG_CLOCK();
@@ -620,7 +621,7 @@ potrf_dag_kernel(const __grid_constant__ CUtensorMap tm, double* __restrict__ H,
     }
     DAG_ADD(1, t0);
     t0 = DAG_CLOCK();
-    if (!diag && tid == 0) wait_column(done + ti, epoch, ti + 1);
+    if (!diag && tid == 0) wait_column(done + ti, epoch, ti + 1, fault, info);
     __syncthreads();  // ring drained by every warp, B = A - acc visible to the CTA, U(i, i) published
     DAG_ADD(2, t0);
     t0 = DAG_CLOCK();
@@ -689,14 +690,347 @@ extern "C" int ipm_internal_dag_timing(long long* out, int count) {
 namespace dag {
 #endif
 
+// ------------------------------------------------------------------------------------------------
+// Pipelined variant (potrf_dag2_kernel): same tasks, same schedule, dependencies tracked per 32 ROWS instead of per
+// 128-row tile, so that the three stages of the dependent chain of a block row
+//     potf2 of U(i, i)   ->   tile solve U(i, i+1) = U(i, i)^{-T} B   ->   last 128 rows of the contraction of (i+1, i+1)
+// overlap: the solve consumes U(i, i) one 32-row step behind the factorisation, and the contraction consumes
+// U(i, i+1) one k-tile (32 rows) behind the solve.  Chain per block row: potf2 + one solve step + one k-tile + three
+// flag hops, instead of potf2 + whole solve + four k-tiles.
+//   prog[c]          (c < MAX_T)  : 32-row groups of the OFF-diagonal tiles of block column c that are final
+//                                   (4 per tile, published top-down: tile (k, c) step g -> 4 k + g + 1)
+//   prog[MAX_T + c]               : 32-row steps of the diagonal tile (c, c) that are final (0 .. 4)
+// The tile solve handles all 128 columns at once (B tile in shared memory, U(i, i) streamed through a 32-row slab),
+// and B = A - acc goes from the accumulators straight to shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int TILE_LD = NB + 4;  // 132: the potf2 / solve tile in shared memory
+constexpr int SLAB_ROWS = 32;
+constexpr int SCRATCH2_BYTES = STAGES * STAGE_BYTES;  // ring (192 KiB) >= tile (132 KiB) + slab (33 KiB)
+static_assert(SCRATCH2_BYTES >= (NB + SLAB_ROWS) * TILE_LD * 8, "tile + slab alias the TMA ring");
+constexpr int SMEM2 = 1024 + SCRATCH2_BYTES + 2 * STAGES * 8;
+
+// Spins until prog[idx] >= need (bounded by the watchdog, common.cuh: spin_wait; on a fault info becomes -1 and the wait
+// reports success so that the kernel drains on garbage instead of hanging).
+__device__ __forceinline__ int wait_progress(unsigned long long* prog, int idx, unsigned epoch, int need, int* info,
+                                             unsigned int* fault) {
+  int r = 0;
+  if (!spin_wait([&] { return (r = column_progress(prog + idx, epoch)) >= need; }, fault, IPM_FAULT_POTRF_DAG)) {
+    atomicCAS(info, 0, -1);
+    r = 4 * MAX_T;
+  }
+  return r;
+}
+__device__ __forceinline__ void publish(unsigned long long* p, unsigned epoch, int count) {
+  const unsigned long long v = ((unsigned long long)epoch << 32) | (unsigned)count;
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+struct Producer2 {
+  const CUtensorMap* tm;
+  Ring ring;
+  unsigned long long* prog;
+  int* info;
+  unsigned int* fault;
+  unsigned epoch;
+  int ti, tj, kt, k1, ready_i, ready_j;  // ready_*: 32-row groups of columns ti / tj known to be final
+  uint32_t it;
+  __device__ __forceinline__ void begin(int i, int j) {
+    ti = i, tj = j, kt = 0, k1 = i * KT_PER_BLOCK, ready_i = ready_j = 0;
+  }
+  __device__ __forceinline__ void issue(int wp, int lane) {
+    if (kt >= k1) return;
+    if (lane == 0) {
+      const int need = kt + 1;  // BK == 32 rows == one group
+      if (ready_i < need || ready_j < need) {
+        if (ready_i < need) ready_i = wait_progress(prog, ti, epoch, need, info, fault);
+        if (tj == ti) ready_j = ready_i;
+        if (ready_j < need) ready_j = wait_progress(prog, tj, epoch, need, info, fault);
+        asm volatile("fence.proxy.async;" ::: "memory");  // the rows were written through the generic proxy
+      }
+      const uint32_t s = it % STAGES;
+      if (it >= STAGES) mbar_wait(ring.empty0 + 8 * s, ((it / STAGES) - 1) & 1);
+      const uint32_t full = ring.full0 + 8 * s;
+      mbar_expect_tx(full, 2 * CHUNK_BYTES);
+      const uint32_t dstA = ring.tiles0 + s * STAGE_BYTES + wp * CHUNK_BYTES;
+      tma_load_2d(dstA, tm, ti * BM + wp * 16, kt * BK, full);
+      tma_load_2d(dstA + OPERAND_BYTES, tm, tj * BN + wp * 16, kt * BK, full);
+    }
+    __syncwarp();
+    ++it;
+    ++kt;
+  }
+};
+static_assert(BK == SLAB_ROWS, "one k-tile == one 32-row group");
+
+// Tile (row0.., col0..) of B = A - acc from the accumulators into shared memory S (ld TILE_LD): entries outside the
+// matrix are 0 (1 on the diagonal of a diagonal tile: identity padding), the strict lower triangle of a diagonal tile 0.
+__device__ __forceinline__ void stage_tile(double* __restrict__ S, const double* __restrict__ H, long long ld, int n,
+                                           int row0, int col0, bool diag, const double (&acc)[8][4][2],
+                                           const LaneMap& lm) {
+  const int lr0 = lm.wm * 64, lc0 = lm.wn * 32;
+  const bool interior = !(ld & 1) && !(((uintptr_t)H) & 15) && (row0 + lr0 + 64 <= n) && (col0 + lc0 + 32 <= n) &&
+                        (!diag || lc0 >= lr0 + 63);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int lr = lr0 + i * 8 + lm.g8, row = row0 + lr;
+#pragma unroll
+    for (int jn = 0; jn < 4; ++jn) {
+      const int lc = lc0 + jn * 8 + 2 * lm.l4, col = col0 + lc;
+      double2 v;
+      if (interior) {
+        const double2 a = __ldcg(reinterpret_cast<const double2*>(H + (long long)row * ld + col));
+        v = make_double2(a.x - acc[i][jn][0], a.y - acc[i][jn][1]);
+      } else {
+        const bool in0 = row < n && col < n && !(diag && col < row);
+        const bool in1 = row < n && col + 1 < n && !(diag && col + 1 < row);
+        v.x = in0 ? __ldcg(H + (long long)row * ld + col) - acc[i][jn][0] : ((diag && lr == lc && row >= n) ? 1.0 : 0.0);
+        v.y = in1 ? __ldcg(H + (long long)row * ld + col + 1) - acc[i][jn][1]
+                  : ((diag && lr == lc + 1 && row >= n) ? 1.0 : 0.0);
+      }
+      *reinterpret_cast<double2*>(S + lr * TILE_LD + lc) = v;
+    }
+  }
+}
+
+// Rows [r_begin, r_begin + 32) of the shared tile S -> global tile G (rows < nrows, columns [cmin(row), ncols)).
+template <bool UPPER>
+__device__ __forceinline__ void store_rows(const double* __restrict__ S, double* __restrict__ G, long long ld,
+                                           int r_begin, int nrows, int ncols) {
+  const bool vec = !(ld & 1) && !(((uintptr_t)G) & 15);
+  for (int idx = threadIdx.x; idx < SLAB_ROWS * (NB / 2); idx += THREADS) {
+    const int r = r_begin + (idx >> 6), c = (idx & 63) * 2;
+    if (r >= nrows) continue;
+    const int cmin = UPPER ? r : 0;
+    double* p = G + (long long)r * ld + c;
+    if (vec && c >= cmin && c + 1 < ncols) {
+      *reinterpret_cast<double2*>(p) = make_double2(S[r * TILE_LD + c], S[r * TILE_LD + c + 1]);
+    } else {
+      if (c >= cmin && c < ncols) p[0] = S[r * TILE_LD + c];
+      if (c + 1 >= cmin && c + 1 < ncols) p[1] = S[r * TILE_LD + c + 1];
+    }
+  }
+}
+
+// Diagonal task: potf2 of the tile in S, publishing every 32-row step (rows final after the pivot block and its row
+// panel) before the trailing update of the step.
+__device__ __forceinline__ void potf2_pipelined(double* __restrict__ S, double* __restrict__ rs, double* __restrict__ G,
+                                                long long ld, int nb, int k0, int* __restrict__ info,
+                                                unsigned long long* diag_prog, unsigned epoch) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll 1
+  for (int base = 0; base < nb; base += 32) {
+    if (warp == 0) {
+      double d[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) d[i] = S[(base + i) * TILE_LD + base + lane];
+      int bad = 0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const double piv = __shfl_sync(0xffffffffu, d[j], j);
+        bad = (bad == 0 && !(piv > 0.0)) ? j + 1 : bad;
+        const double r = rsqrt_nobranch(piv);
+        const double u = d[j] * r;
+        d[j] = u;
+        if (lane == j) rs[j] = r;
+#pragma unroll
+        for (int i = j + 1; i < 32; ++i) {
+          const double ui = __shfl_sync(0xffffffffu, u, i);
+          d[i] = fma(-ui, u, d[i]);
+        }
+      }
+      if (bad && lane == 0) atomicCAS(info, 0, k0 + base + bad);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (lane >= i) S[(base + i) * TILE_LD + base + lane] = d[i];
+    }
+    __syncthreads();
+    const int W = NB - base - 32;  // 96, 64, 32, 0
+    if (tid < W) {
+      const int c = base + 32 + tid;
+      double v[32];
+#pragma unroll
+      for (int l = 0; l < 32; ++l) v[l] = S[(base + l) * TILE_LD + c];
+#pragma unroll
+      for (int l = 0; l < 32; ++l) {
+        const double x = v[l] * rs[l];
+        v[l] = x;
+#pragma unroll
+        for (int r = l + 1; r < 32; ++r) v[r] = fma(-S[(base + l) * TILE_LD + base + r], x, v[r]);
+      }
+#pragma unroll
+      for (int l = 0; l < 32; ++l) S[(base + l) * TILE_LD + c] = v[l];
+    }
+    __syncthreads();
+    store_rows<true>(S, G, ld, base, nb, nb);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) publish(diag_prog, epoch, (base >> 5) + 1);
+    if (W > 0) {
+      potf2_trailing_update(S, base, W, warp, lane);
+      __syncthreads();
+    }
+  }
+}
+
+// Off-diagonal task (ti, tj): X = U(ti, ti)^{-T} B for the B tile in Ps (all 128 columns), one 32-row step behind the
+// factorisation of U(ti, ti); every finished step is stored and published.
+__device__ __forceinline__ void solve_pipelined(double* __restrict__ Ps, double* __restrict__ Us,
+                                                double* __restrict__ rinv, const double* __restrict__ Uii,
+                                                double* __restrict__ G, long long ld, int ncols,
+                                                unsigned long long* prog, int ti, int tj, unsigned epoch,
+                                                int* __restrict__ info, unsigned int* fault) {
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5, l4 = lane & 3, g8 = lane >> 2;
+  const bool vecU = !(ld & 1) && !(((uintptr_t)Uii) & 15);
+  int dready = 0;
+#pragma unroll 1
+  for (int b0 = 0; b0 < NB; b0 += 32) {
+    const int g = b0 >> 5;
+    if (tid == 0 && dready < g + 1) dready = wait_progress(prog, MAX_T + ti, epoch, g + 1, info, fault);  // cached by thread 0
+    __syncthreads();  // U rows published (thread 0 acquired); previous step's readers of the slab are done
+    // slab: rows b0 .. b0+31 of U(ti, ti), columns >= row
+    for (int idx = tid; idx < SLAB_ROWS * (NB / 2); idx += THREADS) {
+      const int r = idx >> 6, cc = (idx & 63) * 2, row = b0 + r;
+      double2 v = make_double2(0.0, 0.0);
+      if (cc + 1 >= row) {
+        if (vecU) {
+          v = __ldcg(reinterpret_cast<const double2*>(Uii + (long long)row * ld + cc));
+        } else {
+          v.x = __ldcg(Uii + (long long)row * ld + cc);
+          v.y = __ldcg(Uii + (long long)row * ld + cc + 1);
+        }
+      }
+      Us[r * TILE_LD + cc] = cc >= row ? v.x : 0.0;
+      Us[r * TILE_LD + cc + 1] = v.y;
+    }
+    __syncthreads();
+    if (tid < SLAB_ROWS) rinv[tid] = 1.0 / Us[tid * TILE_LD + b0 + tid];
+    __syncthreads();
+    if (tid < NB) {
+      const int c = tid;
+      double v[32];
+#pragma unroll
+      for (int l = 0; l < 32; ++l) v[l] = Ps[(b0 + l) * TILE_LD + c];
+#pragma unroll
+      for (int l = 0; l < 32; ++l) {
+        const double x = v[l] * rinv[l];
+        v[l] = x;
+        const double* urow = Us + l * TILE_LD + b0;
+#pragma unroll
+        for (int r = l + 1; r < 32; ++r) v[r] = fma(-urow[r], x, v[r]);
+      }
+#pragma unroll
+      for (int l = 0; l < 32; ++l) Ps[(b0 + l) * TILE_LD + c] = v[l];
+    }
+    __syncthreads();
+    store_rows<false>(Ps, G, ld, b0, NB, ncols);  // rows b0 .. b0+31 of X are final
+    // rows below:  Ps[r0.., :] -= U[b0..b0+32, r0..]^T X[b0..b0+32, :]; warp wp owns columns 16 wp .. 16 wp + 15
+    {
+      double bf[2][8];
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) bf[cb][kk] = Ps[(b0 + 4 * kk + l4) * TILE_LD + 16 * wp + 8 * cb + g8];
+      for (int r0 = b0 + 32; r0 < NB; r0 += 32) {
+        double2 cacc[2][4];
+        double af[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int cb = 0; cb < 2; ++cb)
+            cacc[cb][i] =
+                *reinterpret_cast<const double2*>(Ps + (r0 + 8 * i + g8) * TILE_LD + 16 * wp + 8 * cb + 2 * l4);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) af[i][kk] = -Us[(4 * kk + l4) * TILE_LD + r0 + 8 * i + g8];
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int cb = 0; cb < 2; ++cb)
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                           : "+d"(cacc[cb][i].x), "+d"(cacc[cb][i].y)
+                           : "d"(af[i][kk]), "d"(bf[cb][kk]));
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int cb = 0; cb < 2; ++cb)
+            *reinterpret_cast<double2*>(Ps + (r0 + 8 * i + g8) * TILE_LD + 16 * wp + 8 * cb + 2 * l4) = cacc[cb][i];
+      }
+    }
+    __threadfence();
+    asm volatile("fence.proxy.async;" ::: "memory");  // the rows will be read by TMA
+    __syncthreads();
+    if (tid == 0) publish(prog + tj, epoch, 4 * ti + g + 1);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+potrf_dag2_kernel(const __grid_constant__ CUtensorMap tm, double* __restrict__ H, long long ld, int n, int T,
+                  int* __restrict__ info, unsigned long long* __restrict__ prog, unsigned epoch,
+                  unsigned int* __restrict__ fault) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ double rinv[SLAB_ROWS];
+  __shared__ double rs[32];
+  using S = Shape128x128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  double* tile = reinterpret_cast<double*>(smem);   // NB x TILE_LD; aliases the TMA ring
+  double* slab = tile + NB * TILE_LD;               // SLAB_ROWS x TILE_LD
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SCRATCH2_BYTES);
+  const Ring ring{smem_u32(bars), smem_u32(bars + STAGES), smem_u32(smem)};
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(ring.full0 + 8 * s, CONSUMER_WARPS);
+      mbar_init(ring.empty0 + 8 * s, CONSUMER_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  pdl_wait();
+  const LaneMap lm = make_lane_map<S>(warp, lane);
+  Producer2 prod{&tm, ring, prog, info, fault, epoch, 0, 0, 0, 0, 0, 0, 0u};
+  uint32_t it = 0;
+  const int ntasks = T * (T + 1) / 2;
+  for (int lin = blockIdx.x; lin < ntasks; lin += gridDim.x) {
+    int ti, tj;
+    decode_tile(lin, T, T, true, ti, tj);
+    const bool diag = ti == tj;
+    double acc[S::MI][S::NI][2];
+    zero_acc(acc);
+    if (ti > 0) {
+      prod.begin(ti, tj);
+      for (int p = 0; p < PREFETCH; ++p) prod.issue(warp, lane);
+      consume_ktiles<false, S, ISSUE_AT_ONE_TILE>(acc, ring, lm, nullptr, ti * NB, 0, ti * KT_PER_BLOCK, it, warp, lane,
+                                                  prod);
+      __syncthreads();  // every warp is done with the ring before it becomes the tile
+    }
+    stage_tile(tile, H, ld, n, ti * NB, tj * NB, diag, acc, lm);
+    __syncthreads();
+    const int k0 = ti * NB;
+    if (diag) {
+      potf2_pipelined(tile, rs, H + (long long)k0 * ld + k0, ld, min(NB, n - k0), k0, info, prog + MAX_T + ti, epoch);
+      if (tid == 0) publish(prog + MAX_T + ti, epoch, 4);  // a ragged last tile has fewer than four steps
+    } else {
+      const int c0 = tj * NB;
+      solve_pipelined(tile, slab, rinv, H + (long long)k0 * ld + k0, H + (long long)k0 * ld + c0, ld, min(NB, n - c0),
+                      prog, ti, tj, epoch, info, fault);
+    }
+    // this task's generic accesses to the tile / slab precede the next task's TMA writes into the same bytes
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+  }
+}
+
 struct Slot {
   cudaStream_t stream;
-  unsigned long long* done;  // MAX_T progress counters
+  unsigned long long* done;  // progress counters: MAX_T per block column + MAX_T per diagonal tile (pipelined kernel)
   bool used;
 };
-constexpr int kMaxDev = 16, kSlotsPerDev = 4;
+constexpr int kMaxDev = kMaxDevices, kSlotsPerDev = 4;
 Slot g_slots[kMaxDev][kSlotsPerDev];
-int g_sms[kMaxDev];
+int g_sms[kMaxDev];   // CTAs of potrf_dag_kernel that can be resident at once on the device (occupancy x SM count)
 std::mutex g_mutex;
 std::atomic<unsigned> g_epoch{0};
 
@@ -710,8 +1044,8 @@ unsigned long long* get_counters(int dev, cudaStream_t st, int* rc) {
   for (int i = 0; i < kSlotsPerDev; ++i) {
     Slot* s = &g_slots[dev][i];
     if (s->used) continue;
-    if (cudaMalloc(&s->done, MAX_T * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(s->done, 0, MAX_T * sizeof(unsigned long long)) != cudaSuccess) {
+    if (cudaMalloc(&s->done, (2 * MAX_T + 1) * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(s->done, 0, (2 * MAX_T + 1) * sizeof(unsigned long long)) != cudaSuccess) {
       *rc = ipm_set_cuda_error(cudaGetLastError());
       return nullptr;
     }
@@ -722,22 +1056,35 @@ unsigned long long* get_counters(int dev, cudaStream_t st, int* rc) {
   return nullptr;
 }
 
-bool enabled() {
-  static const bool on = [] {
+// Which sizes ipm_potrf_upper_f64 sends through the single-launch tile-DAG kernel.  Default: n >= 6144 (measured on
+// B200: 7.64 vs 9.00 ms at n = 8192 and 44.7 vs 51.3 ms at 16384, but 3.30 vs 2.91 ms at 4096 where the dependent chain
+// per block row is longer than a block row's share of the work).  IPM_POTRF_DAG=1 forces it for every admissible size
+// (the test suite runs once that way), IPM_POTRF_DAG=0 switches it off.
+constexpr int kAutoMinN = 6144;
+bool enabled(int n) {
+  static const int mode = [] {
     const char* e = getenv("IPM_POTRF_DAG");
-    return e && e[0] == '1';
+    return !e ? -1 : (e[0] == '1' ? 1 : (e[0] == '0' ? 0 : -1));
   }();
-  return on;
+  return mode == 1 || (mode == -1 && n >= kAutoMinN);
 }
 
 // returns 1 when the problem is not handled here (caller falls through to the stream-ordered factorisation)
-int potrf(double* H, int ld, int n, int* info_dev, cudaStream_t st) {
+int potrf(double* H, int ld, int n, int* info_dev, cudaStream_t st, bool pipelined = false) {
   const int T = ceil_div(n, NB);
   if (T < 3 || T > MAX_T) return 1;
   int dev = 0, rc = IPM_OK;
   IPM_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= kMaxDev) return 1;
-  if (!g_sms[dev]) IPM_CUDA_CHECK(cudaDeviceGetAttribute(&g_sms[dev], cudaDevAttrMultiProcessorCount, dev));
+  static bool attr_set[kMaxDevices];
+  IPM_CUDA_CHECK(ensure_dynamic_smem(potrf_dag_kernel, SMEM, attr_set));
+  if (!g_sms[dev]) {
+    int sms = 0, per_sm = 0;
+    IPM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    IPM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, potrf_dag_kernel, THREADS, SMEM));
+    if (per_sm < 1) return 1;
+    g_sms[dev] = sms * per_sm;
+  }
   unsigned long long* done = get_counters(dev, st, &rc);
   if (rc) return rc;
   if (!done) return 1;
@@ -745,15 +1092,20 @@ int potrf(double* H, int ld, int n, int* info_dev, cudaStream_t st) {
   if (make_operand_map(&tm, H, ld, n, n)) return 1;  // unaligned base: the stream-ordered path reports it
   unsigned epoch = ++g_epoch;
   if (epoch == 0) epoch = ++g_epoch;  // never 0 (the counters' initial value)
-  static bool attr_set = false;
-  if (!attr_set) {
-    IPM_CUDA_CHECK(cudaFuncSetAttribute(potrf_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
-  }
   const int ntasks = T * (T + 1) / 2;
   const int grid = ntasks < g_sms[dev] ? ntasks : g_sms[dev];
-  IPM_CUDA_CHECK(launch_pdl(potrf_dag_kernel, dim3(grid), dim3(THREADS), SMEM, st, tm, H, (long long)ld, n, T, info_dev,
-                            done, epoch));
+  // cooperative: the CTAs wait for each other's tiles, so all of them must be resident (a second persistent kernel on
+  // another stream, MPS SM limits or green contexts would otherwise leave round >= 1 tasks waiting for CTAs that are
+  // never scheduled); every wait is additionally bounded by the watchdog
+  if (pipelined) {
+    static bool attr2_set[kMaxDevices];
+    IPM_CUDA_CHECK(ensure_dynamic_smem(potrf_dag2_kernel, SMEM2, attr2_set));
+    IPM_CUDA_CHECK(launch_cooperative(potrf_dag2_kernel, dim3(grid), dim3(THREADS), SMEM2, st, tm, H, (long long)ld, n,
+                                      T, info_dev, done, epoch, ipm_internal_fault_word()));
+  } else {
+    IPM_CUDA_CHECK(launch_cooperative(potrf_dag_kernel, dim3(grid), dim3(THREADS), SMEM, st, tm, H, (long long)ld, n, T,
+                                      info_dev, done, epoch, ipm_internal_fault_word()));
+  }
   IPM_LAUNCH_CHECK();
   return IPM_OK;
 }
@@ -766,12 +1118,14 @@ struct SideStream {
   bool ready;
 };
 static SideStream g_side[16];
+static std::mutex g_side_mutex;  // creation only; the look-ahead itself is per (device, caller) stream-ordered
 
 static int get_side_stream(SideStream** out) {
   int dev = 0;
   IPM_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 16) return IPM_ERR_ARG;
   SideStream* s = &g_side[dev];
+  std::lock_guard<std::mutex> lock(g_side_mutex);
   if (!s->ready) {
     // highest priority: the single-CTA panel chain must get the next free SM while the bulk trailing update of
     // the previous block still has CTAs queued on the caller's stream
@@ -801,7 +1155,7 @@ static int potrf_stream_ordered(double* H, int ld, int n, int* info_dev, void* s
 extern "C" int ipm_potrf_upper_f64(double* H, int ld, int n, int* info_dev, void* stream) {
   if (!H || !info_dev || n < 0 || ld < n || (ld & 1)) return IPM_ERR_ARG;
   IPM_CUDA_CHECK(cudaMemsetAsync(info_dev, 0, sizeof(int), (cudaStream_t)stream));
-  if (dag::enabled()) {
+  if (dag::enabled(n)) {
     const int rc = dag::potrf(H, ld, n, info_dev, (cudaStream_t)stream);
     if (rc <= 0) return rc;  // done or failed; 1 = not handled there
   }
@@ -814,6 +1168,22 @@ extern "C" int ipm_potrf_upper_dag_f64(double* H, int ld, int n, int* info_dev, 
   if (!H || !info_dev || n < 0 || ld < n || (ld & 1)) return IPM_ERR_ARG;
   IPM_CUDA_CHECK(cudaMemsetAsync(info_dev, 0, sizeof(int), (cudaStream_t)stream));
   const int rc = dag::potrf(H, ld, n, info_dev, (cudaStream_t)stream);
+  if (rc <= 0) return rc;
+  return potrf_stream_ordered(H, ld, n, info_dev, stream);
+}
+
+// Library-internal (A/B timing in tools/ and bench.py --factorisation): always the stream-ordered code.
+extern "C" int ipm_internal_potrf_stream_f64(double* H, int ld, int n, int* info_dev, void* stream) {
+  if (!H || !info_dev || n < 0 || ld < n || (ld & 1)) return IPM_ERR_ARG;
+  IPM_CUDA_CHECK(cudaMemsetAsync(info_dev, 0, sizeof(int), (cudaStream_t)stream));
+  return potrf_stream_ordered(H, ld, n, info_dev, stream);
+}
+
+// Library-internal while it is being validated: the pipelined tile-DAG kernel (32-row dependency tracking).
+extern "C" int ipm_internal_potrf_dag2_f64(double* H, int ld, int n, int* info_dev, void* stream) {
+  if (!H || !info_dev || n < 0 || ld < n || (ld & 1)) return IPM_ERR_ARG;
+  IPM_CUDA_CHECK(cudaMemsetAsync(info_dev, 0, sizeof(int), (cudaStream_t)stream));
+  const int rc = dag::potrf(H, ld, n, info_dev, (cudaStream_t)stream, true);
   if (rc <= 0) return rc;
   return potrf_stream_ordered(H, ld, n, info_dev, stream);
 }

@@ -81,7 +81,7 @@ using namespace ipm;
 // long-K contraction (allocated once, never per call).  Calls on one stream serialise, so a slot is never shared
 // by two kernels in flight.
 namespace {
-constexpr int kMaxDev = 16, kSlotsPerDev = 4;
+constexpr int kMaxDev = kMaxDevices, kSlotsPerDev = 4;
 struct SkSlot {
   cudaStream_t stream;
   double* partials;
@@ -178,7 +178,7 @@ extern "C" int ipm_gemm_tn_f64(const double* A, int lda, const double* B, int ld
       const int grid = many ? G : (int)P;
       unsigned epoch = ++g_sk_epoch;
       if (epoch == 0) epoch = ++g_sk_epoch;
-      gemm::StreamK sk{slot->partials, slot->flags, epoch, (int)P, 0};
+      gemm::StreamK sk{slot->partials, slot->flags, epoch, (int)P, 0, ipm_internal_fault_word()};
       if (w) {
         auto kern = gemm::gemm_tn_persistent_kernel<true, PlainEpilogue>;
         IPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
@@ -285,7 +285,8 @@ __global__ void __launch_bounds__(256) hess_reduce_bcast_kernel(const double* __
                                                                 const unsigned int* __restrict__ flags, PeerHs out,
                                                                 long long ldh, int n, int T, int me, int R, int slots,
                                                                 unsigned int epoch, const double* __restrict__ P,
-                                                                long long ldp, double tP) {
+                                                                long long ldp, double tP,
+                                                                unsigned int* __restrict__ fault) {
   const int ntiles = T * (T + 1) / 2;
   for (int slot = blockIdx.x; slot < slots; slot += gridDim.x) {
     const int t = slot * R + me;
@@ -296,10 +297,13 @@ __global__ void __launch_bounds__(256) hess_reduce_bcast_kernel(const double* __
     const int tj = ti + (t - first);
     if (threadIdx.x < R) {
       const unsigned int* f = flags + (size_t)slot * R + threadIdx.x;
-      unsigned v;
-      do {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-      } while (v != epoch);
+      spin_wait(
+          [&] {
+            unsigned v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            return v == epoch;
+          },
+          fault, IPM_FAULT_PEER_REDUCE);  // a late or failed peer: carry on with what is there, the host sees the fault
     }
     __syncthreads();
     // thread -> 32 double2 of the tile: idx2 = threadIdx.x + 256 q  (row = idx2 / 64, col = 2 (idx2 % 64))
@@ -351,11 +355,14 @@ __global__ void __launch_bounds__(256) hess_reduce_bcast_kernel(const double* __
   }
 }
 
-__global__ void hess_wait_kernel(const unsigned int* done, unsigned int target) {
-  unsigned v;
-  do {
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(done) : "memory");
-  } while ((int)(v - target) < 0);  // wrap-safe "v >= target"
+__global__ void hess_wait_kernel(const unsigned int* done, unsigned int target, unsigned int* fault) {
+  spin_wait(
+      [&] {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(done) : "memory");
+        return (int)(v - target) >= 0;  // wrap-safe "v >= target"
+      },
+      fault, IPM_FAULT_PEER_WAIT);
 }
 
 }  // namespace ipm
@@ -391,7 +398,7 @@ extern "C" int ipm_syrk_scatter_f64(const double* Cm, int ldc, const double* w, 
   if (P < 1) P = 1;
   unsigned sk_epoch = ++g_sk_epoch;
   if (sk_epoch == 0) sk_epoch = ++g_sk_epoch;
-  gemm::StreamK sk{slot->partials, slot->flags, sk_epoch, (int)P, 0};
+  gemm::StreamK sk{slot->partials, slot->flags, sk_epoch, (int)P, 0, ipm_internal_fault_word()};
   PeerScatterEpilogue epi;
   for (int r = 0; r < kMaxPeers; ++r) {
     epi.peers.inbox[r] = r < R ? (double*)peer_inbox[r] : nullptr;
@@ -425,9 +432,10 @@ extern "C" int ipm_hess_reduce_bcast_f64(const double* inbox, const unsigned int
   const int T = ceil_div(n, gemm::BN);
   int grid = slots < 296 ? slots : 296;
   if (grid < 1) grid = 1;
-  hess_reduce_bcast_kernel<<<grid, 256, 0, st>>>(inbox, flags, out, ldh, n, T, me, R, slots, epoch, P, ldp, tP);
+  hess_reduce_bcast_kernel<<<grid, 256, 0, st>>>(inbox, flags, out, ldh, n, T, me, R, slots, epoch, P, ldp, tP,
+                                                 ipm_internal_fault_word());
   IPM_LAUNCH_CHECK();
-  hess_wait_kernel<<<1, 1, 0, st>>>((const unsigned int*)peer_done[me], done_target);
+  hess_wait_kernel<<<1, 1, 0, st>>>((const unsigned int*)peer_done[me], done_target, ipm_internal_fault_word());
   IPM_LAUNCH_CHECK();
   return IPM_OK;
 }

@@ -404,6 +404,7 @@ struct StreamK {
   unsigned int epoch;
   int ctas;               // CTAs 0 .. ctas-1 share the remainder tiles (1 <= ctas <= min(gridDim.x, rem * ktiles))
   int gemm_ctas;          // 0: every CTA of the grid works on tiles; else CTAs >= gemm_ctas belong to epi.extra()
+  unsigned int* fault;    // watchdog word of the owner's wait (common.cuh: spin_wait); may be null
 };
 
 struct PersistentSchedule {
@@ -486,10 +487,14 @@ gemm_tn_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       const long long tile_end = (long long)(sch.seg_tile[sg] - dp_tiles + 1) * ktiles;
       for (int c2 = c + 1; c2 < P && U * c2 / P < tile_end; ++c2) {
         if (tid == 0) {
-          unsigned v;
-          do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sk.flags + c2) : "memory");
-          } while (v != sk.epoch);
+          const unsigned int* flag = sk.flags + c2;
+          spin_wait(
+              [&] {
+                unsigned v;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                return v == sk.epoch;
+              },
+              sk.fault, IPM_FAULT_STREAMK);
         }
         cta_barrier_1();
         const double* slot = sk.partials + (size_t)c2 * (BM * BN) + tid;

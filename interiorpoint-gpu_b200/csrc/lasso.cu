@@ -293,12 +293,9 @@ extern "C" int ipm_lasso_admm_step_f64(const double* Qt, int ldq, int n, int K, 
                     partials};
   auto kern = gemm::gemm_tn_kernel<false, LassoEpilogue>;
   auto pkern = gemm::gemm_tn_persistent_kernel<false, LassoEpilogue>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    IPM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
-    IPM_CUDA_CHECK(cudaFuncSetAttribute(pkern, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES));
-    attr_set = true;
-  }
+  static bool attr_set[kMaxDevices], pattr_set[kMaxDevices];
+  IPM_CUDA_CHECK(ensure_dynamic_smem(kern, gemm::SMEM_BYTES, attr_set));
+  IPM_CUDA_CHECK(ensure_dynamic_smem(pkern, gemm::SMEM_BYTES, pattr_set));
   // Small batches (a per-GPU shard of K = 512 is 16 tiles on 148 SMs): spread the k-tiles of every tile over all SMs
   // with the persistent stream-K kernel; the tail-row CTAs stay co-resident behind the tile CTAs.
   const int ktiles = ceil_div(k_main, gemm::BK);
@@ -316,7 +313,7 @@ extern "C" int ipm_lasso_admm_step_f64(const double* Qt, int ldq, int n, int K, 
   // programmatic dependent launch: iteration i+1's CTAs are scheduled while iteration i drains (they wait in
   // pdl_wait() before touching z / alpha / u)
   if (few) {
-    gemm::StreamK sk{sk_partials, sk_flags, sk_epoch, grid_ctas, grid_ctas};
+    gemm::StreamK sk{sk_partials, sk_flags, sk_epoch, grid_ctas, grid_ctas, ipm_internal_fault_word()};
     IPM_CUDA_CHECK(launch_pdl(pkern, dim3(grid_ctas + tail_ctas), dim3(gemm::THREADS), gemm::SMEM_BYTES, st, tmA, tmB,
                               n_main, K, k_main, (const double*)nullptr, 0, epi, sk));
   } else {

@@ -122,11 +122,8 @@ __device__ __forceinline__ void load_diag(const double* __restrict__ Ukk, long l
   }
 }
 
-__device__ __forceinline__ void wait_block(const unsigned* flag, unsigned epoch) {
-  if (threadIdx.x == 0) {
-    while (ld_acquire_u32(flag) != epoch) {
-    }
-  }
+__device__ __forceinline__ void wait_block(const unsigned* flag, unsigned epoch, unsigned int* fault) {
+  if (threadIdx.x == 0) spin_wait([&] { return ld_acquire_u32(flag) == epoch; }, fault, IPM_FAULT_TRSV);
   __syncthreads();
 }
 
@@ -146,7 +143,8 @@ __device__ __forceinline__ void publish_block(double* __restrict__ b, int k0, in
 // ---------------------------------------------------------------------------------------------------------
 template <bool VEC>
 __global__ void __launch_bounds__(TV_THREADS, 1)
-trsv_forward_kernel(const double* __restrict__ U, long long ld, int n, double* __restrict__ b, unsigned epoch) {
+trsv_forward_kernel(const double* __restrict__ U, long long ld, int n, double* __restrict__ b, unsigned epoch,
+                    unsigned int* __restrict__ fault) {
   extern __shared__ double S[];  // NB x TS_LD
   __shared__ double xs[NB];
   __shared__ double ys[2][NB];
@@ -165,7 +163,7 @@ trsv_forward_kernel(const double* __restrict__ U, long long ld, int n, double* _
       for (int q = 0; q < 32; ++q) m[q] = load_pair<VEC>(col + (long long)(rg * 32 + q) * ld, c, nb);
     }
     for (int i = 0; i < j; ++i) {
-      wait_block(g_trsv_flag + i, epoch);
+      wait_block(g_trsv_flag + i, epoch, fault);
       double* yb = ys[i & 1];
       if (tid < NB) yb[tid] = __ldcg(b + i * NB + tid);
       __syncthreads();
@@ -198,7 +196,8 @@ trsv_forward_kernel(const double* __restrict__ U, long long ld, int n, double* _
 // ---------------------------------------------------------------------------------------------------------
 template <bool VEC>
 __global__ void __launch_bounds__(TV_THREADS, 1)
-trsv_backward_kernel(const double* __restrict__ U, long long ld, int n, double* __restrict__ b, unsigned epoch) {
+trsv_backward_kernel(const double* __restrict__ U, long long ld, int n, double* __restrict__ b, unsigned epoch,
+                     unsigned int* __restrict__ fault) {
   extern __shared__ double S[];
   __shared__ double xs[NB];
   __shared__ double xj[2][NB];
@@ -224,7 +223,7 @@ trsv_backward_kernel(const double* __restrict__ U, long long ld, int n, double* 
       }
     }
     for (int j = nblk - 1; j > kb; --j) {
-      wait_block(g_trsv_flag + j, epoch);
+      wait_block(g_trsv_flag + j, epoch, fault);
       double* xb = xj[j & 1];
       if (tid < NB) xb[tid] = (j * NB + tid < n) ? __ldcg(b + j * NB + tid) : 0.0;
       __syncthreads();
@@ -307,12 +306,13 @@ extern "C" int ipm_trsv_upper_f64(const double* U, int ld, int n, double* b, int
   unsigned epoch = ++g_epoch;
   if (epoch == 0) epoch = ++g_epoch;  // never 0 (the flags' initial value)
   const bool vec = !(ld & 1) && !(((uintptr_t)U) & 15);
+  unsigned int* fault = ipm_internal_fault_word();
   if (trans) {
-    if (vec) trsv_forward_kernel<true><<<grid, TV_THREADS, smem, st>>>(U, ld, n, b, epoch);
-    else trsv_forward_kernel<false><<<grid, TV_THREADS, smem, st>>>(U, ld, n, b, epoch);
+    if (vec) trsv_forward_kernel<true><<<grid, TV_THREADS, smem, st>>>(U, ld, n, b, epoch, fault);
+    else trsv_forward_kernel<false><<<grid, TV_THREADS, smem, st>>>(U, ld, n, b, epoch, fault);
   } else {
-    if (vec) trsv_backward_kernel<true><<<grid, TV_THREADS, smem, st>>>(U, ld, n, b, epoch);
-    else trsv_backward_kernel<false><<<grid, TV_THREADS, smem, st>>>(U, ld, n, b, epoch);
+    if (vec) trsv_backward_kernel<true><<<grid, TV_THREADS, smem, st>>>(U, ld, n, b, epoch, fault);
+    else trsv_backward_kernel<false><<<grid, TV_THREADS, smem, st>>>(U, ld, n, b, epoch, fault);
   }
   IPM_LAUNCH_CHECK();
   return IPM_OK;

@@ -512,6 +512,7 @@ class LinearNewton:
         L("ipm_axpy_dev_f64", self.nz, ws.ls_out.data_ptr(), ws.dz.data_ptr(), z.data_ptr())
         ws.host[10:11].copy_(z[self.nz - 1:self.nz], non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        _abi.check_device_fault()
         h = ws.host
         return dict(step=float(h[0]), stuck=h[1] != 0, g_dz=float(h[9]), z_last=float(h[10]),
                     info=int(ws.host_info[0]))
@@ -662,6 +663,7 @@ class LinearNewton:
         L("ipm_axpy_dev_f64", n, ws.ls_out.data_ptr(), ws.dz.data_ptr(), z.data_ptr())
         L("ipm_axpy_dev_f64", p, ws.ls_out.data_ptr(), ws.dv.data_ptr(), ws.v.data_ptr())
         torch.cuda.current_stream().synchronize()
+        _abi.check_device_fault()
         h = ws.host
         return dict(step=float(h[0]), stuck=int(h[1]), r0=float(h[3]), rnorm=float(h[4]),
                     info=int(ws.host_info[0]) or int(ws.host_info[1]))

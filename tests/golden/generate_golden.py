@@ -247,7 +247,65 @@ def option_cases():
         json.dump(out, f, indent=1)
 
 
+REF_POLYTOPES = {  # AutomatedTestsPhaseOne.py:253-318 (test_phase_one) and :364-367 (test_initialized_phase_one)
+    "ref_inside": ([[1, 3], [1, 1], [-1, 0], [0, -1]], [9, 5, 0, 0], None),
+    "ref_outside": ([[-1, -3], [-1, 1], [-1, 2], [1, 4]], [-6, 2, 2, 12], None),
+    "ref_unbounded": ([[1, -2], [-3, 1]], [-2, 0], None),
+    "ref_empty": ([[3, -1], [-1, 5], [-1, 0], [0, -1]], [-2, 1.5, 0, 0], None),
+    "ref_initialized": ([[-1, -3], [-1, 1], [-1, 2], [1, 4]], [-6, 2, 2, 12], [-2, -3]),
+}
+
+
+def phase_one_kat():
+    """The reference's OWN functional tests (AutomatedTestsPhaseOne.py:235-389) run through the real class: its four
+    polytopes, the initialised start and the 200 x 1000 random problem (:325-343), with both linear solvers."""
+    out = []
+    for solver in ("solve", "cg"):
+        for nm, (G, h, x0) in REF_POLYTOPES.items():
+            G_, h_ = np.array(G), np.array(h)
+            s = _p1.PhaseOneSolver(G_, h_, 15, x0=None if x0 is None else np.array(x0), linear_solver=solver)
+            x, sv, warn = s.solve()
+            out.append(dict(name=f"{nm}_{solver}", G=G, h=h, x0=x0, mu=15, linear_solver=solver,
+                            x=[float(v) for v in x], s=float(sv), warn=bool(warn),
+                            max_violation=float(np.max(G_ @ x - h_))))
+            print("kat", nm, solver, x, sv, warn)
+        np.random.seed(0)
+        m, n = 200, 1000
+        G = np.random.uniform(low=-10, high=10, size=(m, n))
+        x = np.random.uniform(low=-5, high=5, size=(n))
+        h = G @ x + 1
+        s = _p1.PhaseOneSolver(G, h, 15, linear_solver=solver)
+        x, sv, warn = s.solve()
+        out.append(dict(name=f"ref_random_200x1000_{solver}", seed=0, m=m, n=n, mu=15, linear_solver=solver,
+                        s=float(sv), warn=bool(warn), x=[float(v) for v in x], max_violation=float(np.max(G @ x - h))))
+        print("kat random", solver, sv, warn, np.max(G @ x - h))
+    with open(os.path.join(HERE, "phase_one_kat.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
+def large_cases():
+    """BASELINE cfg-2 family at n = 1024 and n = 2048 (cold and warm) and the cfg-3 family at n = 2048 (p = 512 equalities,
+    k = 64 inequalities: the n = 8192, p = 2048, k = 20 shape of tests/test_fullsize_gpu.py scaled down 4x), constructor
+    defaults -- the sizes at which the device engine switches to its multi-block kernels (look-ahead / tile-DAG Cholesky,
+    persistent stream-K SYRK, multi-block triangular solves).  SURVEY Appendix A lists the n = 1024 values."""
+    out = []
+    for n in (1024, 2048):
+        out.append(run_barrier(LPSolver, "lp_dense_family", dict(seed=0, n=n), None, {}, f"lp_dense_n{n}_cold"))
+        out.append(run_barrier(LPSolver, "lp_dense_family", dict(seed=0, n=n, warm=True), None, {},
+                               f"lp_dense_n{n}_warm"))
+    out.append(run_barrier(QPSolver, "qp_dense_family", dict(seed=0, n=2048, p=512, k=64), None, {}, "qp_dense_n2048"))
+    out.append(run_barrier(QPSolver, "qp_dense_family", dict(seed=1, n=1024, p=256, k=20), None, {}, "qp_dense_n1024"))
+    with open(os.path.join(HERE, "large_cases.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 def main():
+    if "--kat-only" in sys.argv:
+        phase_one_kat()
+        return
+    if "--large-only" in sys.argv:
+        large_cases()
+        return
     if "--options-only" in sys.argv:
         option_cases()
         return

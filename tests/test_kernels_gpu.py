@@ -244,6 +244,28 @@ def test_potrf_tile_dag_reports_first_bad_pivot():
     assert int(info.item()) == 601
 
 
+def test_watchdog_bounds_a_wait_that_never_ends():
+    """common.cuh: spin_wait -- a device-side wait whose condition never holds gives up after the spin limit, records its
+    code in the pinned fault word (ipm_device_fault) and the kernel returns; a later wait of the process returns at once."""
+    L = _abi.lib()
+    fn = L.ipm_internal_watchdog_selftest
+    fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    gave_up = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+    L.ipm_clear_device_fault()
+    old = L.ipm_set_spin_limit(8)  # 8 * 2^20 cycles ~ 4 ms
+    try:
+        assert fn(flag.data_ptr(), gave_up.data_ptr(), 42, None) == 0
+        torch.cuda.synchronize()
+        assert int(gave_up.item()) == 1 and L.ipm_device_fault() == 42
+        with pytest.raises(_abi.IpmError, match="watchdog"):
+            _abi.check_device_fault()
+        assert L.ipm_device_fault() == 0  # check_device_fault clears it
+    finally:
+        L.ipm_set_spin_limit(old)
+        L.ipm_clear_device_fault()
+
+
 def test_potrf_reports_first_bad_pivot():
     n = 200
     H = spd(n, 3, cond_pow=1)

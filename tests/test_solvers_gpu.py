@@ -150,16 +150,39 @@ def test_linear_solve_method_variants(case):
 
 
 DUALS = load_golden("dual_cases.json")
+SENS = load_golden("sensitivity.json")["cases"]  # tests/golden/sensitivity_options.py
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: tolerances not calibrated on a "
-                                        "device yet (the oracle side is pinned in tests/test_oracle_golden.py)")
+def assert_iters_in_envelope(got, env, tol=2):
+    """Counts within the range the REFERENCE's own arithmetic produces under a 1e-14 relative perturbation of its inputs
+    (tests/golden/sensitivity.json), widened by the usual +-2."""
+    assert len(got) == len(env["min"]), (got, env)
+    for a, lo, hi in zip(got, env["min"], env["max"]):
+        assert lo - tol <= a <= hi + tol, (got, env)
+
+
+def _host_slacks(prob, x):
+    """Slack layout of the reference: [C rows | upper bounds | lower bounds] (FunctionManager.py:118-149)."""
+    parts = []
+    if prob.get("C") is not None:
+        parts.append(prob["d"] - prob["C"] @ x)
+    if prob.get("upper_bound") is not None:
+        parts.append(prob["upper_bound"] - x)
+    if prob.get("lower_bound") is not None:
+        parts.append(x - prob["lower_bound"])
+    return np.concatenate(parts)
+
+
 @pytest.mark.parametrize("case", DUALS, ids=[c["name"] for c in DUALS])
 def test_dual_variables_and_loss_trace(case):
     """get_dual_variables=True / track_loss=True (LPSolver.py:608-609,641-646): lam_star in the reference's slack
     layout [C rows | upper bounds | lower bounds], v_star = v / t, objective_vals per accepted centering step.
-    lam = 1 / (t s) amplifies differences of the iterate on the active rows (s ~ 1e-8), so the multipliers are compared
-    through what they are used for: dual feasibility and the complementarity products, plus a norm-wise comparison."""
+
+    lam = 1 / (t s) divides by slacks that are differences of O(1) numbers; on the active rows of a solve that ends at
+    t ~ 1e13 those slacks are ~1e-13 and the REFERENCE's own lam_star moves by 39 % under a 1e-14 relative perturbation
+    of C (tests/golden/sensitivity.json: lam_rel_spread).  So: (a) lam_star must be exactly the reference's formula
+    evaluated at the returned point, (b) it must agree with the golden on every row whose slack is resolved (s > 1e-7),
+    (c) norm-wise agreement is required to max(1e-2, 10 x the reference's own spread) when that is a meaningful bar."""
     cls = _solver_class(case["solver"])
     prob = build_problem(case)
     np.random.seed(0)
@@ -170,13 +193,25 @@ def test_dual_variables_and_loss_trace(case):
     np.testing.assert_allclose(np.asarray(s.objective_vals, dtype=float), case["objective_vals"], rtol=1e-6, atol=1e-9)
     lam, lam_ref = np.asarray(s.lam_star, dtype=float).ravel(), np.array(case["lam_star"])
     assert lam.shape == lam_ref.shape and np.all(lam > 0)
-    assert np.linalg.norm(lam - lam_ref) <= 1e-2 * np.linalg.norm(lam_ref)
+    sens = SENS[case["name"]]
+    assert_iters_in_envelope(s.inner_iters, sens["inner_iters"])
+    # (a) the formula, at the device's own xstar
+    sl = _host_slacks(prob, np.asarray(s.xstar, dtype=float))
+    resolved = sl > 1e-7
+    np.testing.assert_allclose(lam[resolved], 1.0 / (s.t_final * sl[resolved]), rtol=1e-6)
+    # (b) against the golden where the reference's slack is resolved
+    sl_ref = 1.0 / (s.t_final * lam_ref)
+    ok = sl_ref > 1e-7
+    assert ok.sum() >= 0.2 * len(lam)
+    np.testing.assert_allclose(lam[ok], lam_ref[ok], rtol=1e-3)
+    # (c) norm-wise
+    if sens["lam_rel_spread"] < 1e-3:
+        assert np.linalg.norm(lam - lam_ref) <= max(1e-2, 10 * sens["lam_rel_spread"]) * np.linalg.norm(lam_ref)
     if case["v_star"] is not None:
         v, v_ref = np.asarray(s.v_star, dtype=float).ravel(), np.array(case["v_star"])
         assert np.linalg.norm(v - v_ref) <= 1e-2 * (1e-12 + np.linalg.norm(v_ref))
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent; not yet run on a device")
 def test_control_flow_behaviour():
     """Phase-I failure on an empty feasible set (LPSolver.py:553-558) and a second solve() on the same object (quirk Q7)."""
     cases = {c["name"]: c for c in load_golden("behaviour_cases.json")}
@@ -195,17 +230,50 @@ def test_control_flow_behaviour():
 OPTIONS = load_golden("option_cases.json")
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent; not yet run on a device")
 @pytest.mark.parametrize("case", OPTIONS, ids=[c["name"] for c in OPTIONS])
 def test_constructor_options_match_reference(case):
-    """try_diag=False on a bounds-only LP, update_slacks_every > 0, use_psd_condition=True: same bar as the default
-    settings (objective 1e-6, Newton counts +-2)."""
+    """try_diag=False on a bounds-only LP, update_slacks_every > 0, use_psd_condition=True: objective to 1e-6 and Newton
+    counts +-2 against the golden.  For update_slacks_every > 0 the count bar is the envelope of the reference's own
+    counts under a 1e-14 relative input perturbation (tests/golden/sensitivity_options.py: e.g. 22..50 for the first
+    centering step of the cold case), widened by the same +-2 -- the golden's single list is one sample of it."""
     cls = _solver_class(case["solver"])
     prob = build_problem(case)
     np.random.seed(0)
     s = cls(**prob, check_cvxpy=False, suppress_print=True, **case["settings"])
     val = s.solve()
+    print(case["name"], val, case["value"], s.inner_iters, case["inner_iters"])
     assert val == pytest.approx(case["value"], rel=1e-6, abs=1e-9)
+    x = np.asarray(s.xstar)
+    assert np.linalg.norm(x - np.array(case["xstar"])) <= 1e-4 * (1 + np.linalg.norm(case["xstar"]))
+    if case["name"] in SENS:
+        env = SENS[case["name"]]
+        assert_iters_in_envelope(s.inner_iters, env["inner_iters"])
+        if env["phase1_inner_iters"] is not None:
+            assert_iters_in_envelope(s.phase1_solver.inner_iters, env["phase1_inner_iters"])
+        return
     assert_iters_close(s.inner_iters, case["inner_iters"], cap=s.max_inner_iters)
     if case["phase1_inner_iters"] is not None:
         assert_iters_close(s.phase1_solver.inner_iters, case["phase1_inner_iters"])
+
+
+LARGE = load_golden("large_cases.json")
+
+
+@pytest.mark.parametrize("case", LARGE, ids=[c["name"] for c in LARGE])
+def test_large_cases_match_reference(case):
+    """cfg-2 family at n = 1024 / 2048 (cold + warm) and cfg-3 family at n = 1024 / 2048: the sizes where the multi-block
+    kernels run (look-ahead / tile-DAG Cholesky, persistent stream-K SYRK, multi-block trsv, blocked TRSM + Schur), against
+    goldens of the REAL reference (generate_golden.py --large-only): optimum 1e-6, per-centering Newton counts +-2."""
+    cls = _solver_class(case["solver"])
+    prob = build_problem(case)
+    np.random.seed(0)
+    s = cls(**prob, check_cvxpy=False, suppress_print=True, **case["settings"])
+    val = s.solve()
+    print(case["name"], val, case["value"], s.inner_iters, case["inner_iters"])
+    assert val == pytest.approx(case["value"], rel=1e-6, abs=1e-9)
+    assert_iters_close(s.inner_iters, case["inner_iters"], cap=s.max_inner_iters,
+                       noisy=noise_dominated_steps(case, prob, case["settings"]))
+    if case["phase1_inner_iters"] is not None:
+        assert_iters_close(s.phase1_solver.inner_iters, case["phase1_inner_iters"])
+    x = np.asarray(s.xstar)
+    assert np.linalg.norm(x - np.array(case["xstar"])) <= 1e-4 * (1 + np.linalg.norm(case["xstar"]))

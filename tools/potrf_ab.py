@@ -9,13 +9,14 @@ sys.path.insert(0, ".")
 from ipm_b200 import _abi  # noqa: E402
 
 _abi.require_device()
-NAMES = ["ipm_potrf_upper_f64", "ipm_potrf_upper_dag_f64"]
-if hasattr(_abi.lib(), "ipm_internal_potrf_dag2_f64"):  # pipelined variant while it is being validated
-    import ctypes as C
+import ctypes as C  # noqa: E402
 
-    fn = _abi.lib().ipm_internal_potrf_dag2_f64
-    fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
-    NAMES.append("ipm_internal_potrf_dag2_f64")
+NAMES = ["ipm_potrf_upper_f64", "ipm_potrf_upper_dag_f64"]
+for extra in ("ipm_internal_potrf_stream_f64", "ipm_internal_potrf_dag2_f64"):  # library-internal A/B entry points
+    if hasattr(_abi.lib(), extra):
+        fn = getattr(_abi.lib(), extra)
+        fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        NAMES.append(extra)
 
 
 def spd(n, seed):
@@ -27,12 +28,17 @@ def spd(n, seed):
     return H
 
 
+def call(name, *args):
+    _abi.check(getattr(_abi.lib(), name)(*args), name)
+
+
 def factor(name, H, n, ld):
     Hd = torch.full((n, ld), float("nan"), dtype=torch.float64, device="cuda")
     Hd[:, :n] = torch.triu(H)  # strict lower triangle = 0 here; it must stay untouched
     info = torch.full((1,), -7, dtype=torch.int32, device="cuda")
-    _abi.call(name, Hd.data_ptr(), ld, n, info.data_ptr(), None)
+    call(name, Hd.data_ptr(), ld, n, info.data_ptr(), None)
     torch.cuda.synchronize()
+    assert _abi.lib().ipm_device_fault() == 0, ("watchdog fired", name, n, _abi.lib().ipm_device_fault())
     return Hd, int(info.item())
 
 
@@ -72,7 +78,7 @@ for n in [int(a) for a in sys.argv[1:]] or [8192]:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             e0.record()
-            _abi.call(name, work.data_ptr(), n, n, info.data_ptr(), None)
+            call(name, work.data_ptr(), n, n, info.data_ptr(), None)
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
