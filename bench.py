@@ -69,6 +69,8 @@ def parse():
 def factorisation_section(n, reps=5):
     """ipm_potrf_upper_f64 (stream-ordered) and ipm_potrf_upper_dag_f64 (one persistent launch) on an SPD matrix with
     the Hessian's structure (C' diag(w) C + I), L2 flushed before every factorisation; n^3 / 3 flop."""
+    import torch
+
     from ipm_b200 import _abi
 
     g = torch.Generator(device="cuda").manual_seed(n)
@@ -86,11 +88,12 @@ def factorisation_section(n, reps=5):
     import ctypes as C
 
     lib = _abi.lib()
-    for nm in ("ipm_internal_potrf_stream_f64", "ipm_internal_potrf_dag2_f64"):  # library-internal A/B entry points
+    for nm in ("ipm_internal_potrf_stream_f64", "ipm_internal_potrf_dag1_f64"):  # library-internal A/B entry points
         getattr(lib, nm).restype, getattr(lib, nm).argtypes = C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                                                          C.c_void_p]
     for key, name in (("default", "ipm_potrf_upper_f64"), ("stream_ordered", "ipm_internal_potrf_stream_f64"),
-                      ("tile_dag", "ipm_potrf_upper_dag_f64"), ("tile_dag_pipelined", "ipm_internal_potrf_dag2_f64")):
+                      ("tile_dag_per_tile_deps", "ipm_internal_potrf_dag1_f64"),
+                      ("tile_dag_pipelined", "ipm_potrf_upper_dag_f64")):
         ts = []
         for _ in range(reps + 1):
             work.copy_(H)

@@ -1056,11 +1056,11 @@ unsigned long long* get_counters(int dev, cudaStream_t st, int* rc) {
   return nullptr;
 }
 
-// Which sizes ipm_potrf_upper_f64 sends through the single-launch tile-DAG kernel.  Default: n >= 6144 (measured on
-// B200: 7.64 vs 9.00 ms at n = 8192 and 44.7 vs 51.3 ms at 16384, but 3.30 vs 2.91 ms at 4096 where the dependent chain
-// per block row is longer than a block row's share of the work).  IPM_POTRF_DAG=1 forces it for every admissible size
-// (the test suite runs once that way), IPM_POTRF_DAG=0 switches it off.
-constexpr int kAutoMinN = 6144;
+// Which sizes ipm_potrf_upper_f64 sends through the single-launch tile-DAG kernel (the pipelined one).  Default:
+// n >= 2048, where it wins on B200 (profiles/potrf_ab_r02a.txt, stream-ordered / tile-DAG / pipelined tile-DAG: 1.24 /
+// 1.67 / 1.07 ms at n = 2048, 2.78 / 3.37 / 2.12 ms at 4096, 8.91 / 7.71 / 6.71 ms at 8192, 51.1 / 44.8 / 44.9 ms at
+// 16384).  IPM_POTRF_DAG=1 forces it for every admissible size (the test suite runs once that way), =0 switches it off.
+constexpr int kAutoMinN = 2048;
 bool enabled(int n) {
   static const int mode = [] {
     const char* e = getenv("IPM_POTRF_DAG");
@@ -1070,7 +1070,7 @@ bool enabled(int n) {
 }
 
 // returns 1 when the problem is not handled here (caller falls through to the stream-ordered factorisation)
-int potrf(double* H, int ld, int n, int* info_dev, cudaStream_t st, bool pipelined = false) {
+int potrf(double* H, int ld, int n, int* info_dev, cudaStream_t st, bool pipelined = true) {
   const int T = ceil_div(n, NB);
   if (T < 3 || T > MAX_T) return 1;
   int dev = 0, rc = IPM_OK;
@@ -1179,11 +1179,11 @@ extern "C" int ipm_internal_potrf_stream_f64(double* H, int ld, int n, int* info
   return potrf_stream_ordered(H, ld, n, info_dev, stream);
 }
 
-// Library-internal while it is being validated: the pipelined tile-DAG kernel (32-row dependency tracking).
-extern "C" int ipm_internal_potrf_dag2_f64(double* H, int ld, int n, int* info_dev, void* stream) {
+// Library-internal (A/B timing): the first tile-DAG kernel, which tracks dependencies per 128-row tile.
+extern "C" int ipm_internal_potrf_dag1_f64(double* H, int ld, int n, int* info_dev, void* stream) {
   if (!H || !info_dev || n < 0 || ld < n || (ld & 1)) return IPM_ERR_ARG;
   IPM_CUDA_CHECK(cudaMemsetAsync(info_dev, 0, sizeof(int), (cudaStream_t)stream));
-  const int rc = dag::potrf(H, ld, n, info_dev, (cudaStream_t)stream, true);
+  const int rc = dag::potrf(H, ld, n, info_dev, (cudaStream_t)stream, false);
   if (rc <= 0) return rc;
   return potrf_stream_ordered(H, ld, n, info_dev, stream);
 }

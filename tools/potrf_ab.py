@@ -12,7 +12,7 @@ _abi.require_device()
 import ctypes as C  # noqa: E402
 
 NAMES = ["ipm_potrf_upper_f64", "ipm_potrf_upper_dag_f64"]
-for extra in ("ipm_internal_potrf_stream_f64", "ipm_internal_potrf_dag2_f64"):  # library-internal A/B entry points
+for extra in ("ipm_internal_potrf_stream_f64", "ipm_internal_potrf_dag1_f64"):  # library-internal A/B entry points
     if hasattr(_abi.lib(), extra):
         fn = getattr(_abi.lib(), extra)
         fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
