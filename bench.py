@@ -221,15 +221,9 @@ def blas_threads():
 
 def lasso_workload(K):
     """BASELINE configs[4]: A 2048x512 (+bias), K problems, generator of testSolver.py:1096-1104 (seed 5)."""
-    n, rows = 512, 2048
-    rs = np.random.RandomState(5)
-    A = rs.rand(rows, n)
-    nnz = int(n * K / 4)
-    x_true = np.zeros((n, K))
-    x_true[np.unravel_index(rs.randint(0, n * K, nnz), (n, K))] = rs.uniform(0, 50, nnz)
-    reg = 0.05 + 0.01 * rs.randn(K)
-    b = A @ x_true + rs.randn(rows, K)
-    return A, b, reg
+    import problems
+
+    return problems.lasso_cfg5(K)
 
 
 def lasso_section(K, rank, world):

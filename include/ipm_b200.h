@@ -202,6 +202,19 @@ long long ipm_lasso_partials_doubles(int n, int K);
 int ipm_lasso_admm_step_f64(const double* Qt, int ldq, int n, int K, const double* bA, const double* eta, double rho,
                             double* alpha, double* u, const double* z_in, double* z_out, int ld, int add_bias,
                             int positive, int want_norms, double* partials, double* norms_out, void* stream);
+/* `n_iters` ADMM iterations in ONE persistent launch (csrc/lasso_multi.cu): the loop body of LassoSolver.py:240-337
+ * including the batch-coupled stop test :273-298, evaluated on the device after the last iteration when want_norms:
+ *   ||x - alpha+|| < stop_mult + eps_rel ||alpha+||  and  ||rho (alpha+ - alpha)|| < stop_mult + eps_rel rho ||u+||.
+ * z0 / z1: the two buffers of z = u - alpha (after `it` iterations in total the current one is z[it & 1]).
+ * ws: device workspace of ipm_lasso_steps_ws_bytes() bytes, zeroed by the caller at the start of a solve;
+ * ((int*)ws)[0] = 1 once the test held (later launches are then no-ops), ((int*)ws)[1] = iterations performed; the
+ * four squared norms of the last test sit at byte offset ipm_lasso_steps_norms_offset().  alpha is valid after every
+ * launch. */
+long long ipm_lasso_steps_ws_bytes(int n, int K);
+long long ipm_lasso_steps_norms_offset(int n, int K);
+int ipm_lasso_admm_steps_f64(const double* Qt, int ldq, int n, int K, const double* bA, const double* eta, double rho,
+                             double* alpha, double* u, double* z0, double* z1, int ld, int add_bias, int positive,
+                             int n_iters, int want_norms, double stop_mult, double eps_rel, void* ws, void* stream);
 /* f_c = 1/(2m)|R[:,c]|^2 + reg_c * |alpha[1:,c]|_1 with R = A alpha - b.  LassoSolver.py:314-325. */
 int ipm_lasso_objective_f64(const double* R, int ldr, int m, const double* alpha, int lda, int n, int K,
                             const double* reg, int add_bias, int positive, double* out, void* stream);

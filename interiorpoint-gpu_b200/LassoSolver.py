@@ -64,6 +64,10 @@ class LassoSolver:
         # keep the ADMM state L2-resident between iterations (ipm_l2_persist); IPM_LASSO_L2=0 switches it off
         self.l2_resident = os.environ.get("IPM_LASSO_L2", "1") != "0"
         self.l2_hit_ratio = 0.0
+        # the whole ADMM loop in persistent multi-iteration launches (csrc/lasso_multi.cu); IPM_LASSO_MULTI=0 falls back to
+        # one launch per iteration (always used with compute_loss=True, which wants the objective after every iteration)
+        self.multi_iteration = os.environ.get("IPM_LASSO_MULTI", "1") != "0"
+        self.lookahead = 4  # launches enqueued before the host looks at the device-side stop flag of an older one
         # one chunk: everything is precomputed and resident before solve() (LassoSolver.py:193-222)
         self._prep = self._prepare(np.arange(self.num_samples)) if self.num_chunks == 1 else None
 
@@ -138,7 +142,10 @@ class LassoSolver:
         if self.l2_resident:
             _abi.call("ipm_l2_persist", block.data_ptr(), block.numel() * 8, C.byref(ratio), None)
         try:
-            it = self._iterate(prep, alpha, u, zin, zout, partials, norms, host, stop_mult, cols, R, fvals)
+            if self.multi_iteration and not self.compute_loss:
+                it = self._iterate_multi(prep, alpha, u, z0, z1, stop_mult)
+            else:
+                it = self._iterate(prep, alpha, u, zin, zout, partials, norms, host, stop_mult, cols, R, fvals)
         finally:
             if self.l2_resident:
                 _abi.call("ipm_l2_persist", None, 0, None, None)
@@ -173,6 +180,40 @@ class LassoSolver:
                 if r_norm < tol_primal and d_norm < tol_dual:
                     break
         return it
+
+    def _iterate_multi(self, prep, alpha, u, z0, z1, stop_mult):
+        """The ADMM loop in launches of ``check_stop`` iterations (``ipm_lasso_admm_steps_f64``): the stop test of
+        LassoSolver.py:273-298 is evaluated on the device at the end of every launch, a launch that finds the stop flag up
+        does nothing, so the host enqueues ``lookahead`` launches ahead and only reads (flag, iterations done) of older
+        ones -- no host round trip on the critical path.  Returns the index of the last iteration performed."""
+        n, L = self.n, self.L
+        K, ld, eta, bA = (prep[k] for k in ("K", "ld", "eta", "bA"))
+        nbytes = _abi.lib().ipm_lasso_steps_ws_bytes(n, K)
+        ws = prep.get("steps_ws")
+        if ws is None or ws.numel() < nbytes:
+            ws = prep["steps_ws"] = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        ws.zero_()
+        state = ws[:8].view(torch.int32)
+        full, rem = divmod(self.max_iters, self.check_stop)
+        batches = [(self.check_stop, 1)] * full + ([(rem, 0)] if rem else [])
+        LA = self.lookahead
+        pinned = torch.zeros((LA, 2), dtype=torch.int32).pin_memory()
+        events = [None] * LA
+        for b, (n_iters, want_norms) in enumerate(batches):
+            if b >= LA:
+                events[b % LA].synchronize()
+                if int(pinned[b % LA, 0]) != 0:
+                    break
+            L("ipm_lasso_admm_steps_f64", self.Qt.data_ptr(), self.ldn, n, K, bA.data_ptr(), eta.data_ptr(), self.rho,
+              alpha.data_ptr(), u.data_ptr(), z0.data_ptr(), z1.data_ptr(), ld, int(self.add_bias), int(self.positive),
+              n_iters, want_norms, stop_mult, self.EPS_REL, ws.data_ptr())
+            pinned[b % LA].copy_(state[:2], non_blocking=True)
+            events[b % LA] = torch.cuda.Event()
+            events[b % LA].record()
+        pinned[0].copy_(state[:2], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        _abi.check_device_fault()
+        return int(pinned[0, 1]) - 1
 
     def _objective(self, alpha, b_dev, reg_dev, ld, K, R, out):
         """f = 1/(2m) ||A alpha - b||^2 + reg ||alpha[1:]||_1 per column (LassoSolver.py:314-325)."""

@@ -49,6 +49,10 @@ SIGNATURES = {
     "ipm_lasso_partials_doubles": (_ll, [_i, _i]),
     "ipm_lasso_admm_step_f64": (_i, [_dp, _i, _i, _i, _dp, _dp, _d, _dp, _dp, _dp, _dp, _i, _i, _i, _i, _dp, _dp,
                                      _dp]),
+    "ipm_lasso_steps_ws_bytes": (_ll, [_i, _i]),
+    "ipm_lasso_steps_norms_offset": (_ll, [_i, _i]),
+    "ipm_lasso_admm_steps_f64": (_i, [_dp, _i, _i, _i, _dp, _dp, _d, _dp, _dp, _dp, _dp, _i, _i, _i, _i, _i, _d, _d, _dp,
+                                      _dp]),
     "ipm_lasso_objective_f64": (_i, [_dp, _i, _i, _dp, _i, _i, _i, _dp, _i, _i, _dp, _dp]),
     "ipm_scale_shift_f64": (_i, [_dp, _i, _dp, _i, _i, _i, _d, _d, _dp]),
     "ipm_cone_eval_f64": (_i, [_i, _dp, _i, _dp, _dp, _dp, _d, _i, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]),

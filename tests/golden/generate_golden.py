@@ -283,6 +283,23 @@ def phase_one_kat():
         json.dump(out, f, indent=1)
 
 
+def lasso_full_size():
+    """BASELINE configs[4] at FULL size through the real reference: A 2048 x 512 (+ bias), K = 4096 problems, the settings of
+    the reference's GPU arm (testSolver.py:1142-1159: eps 1e-6, max_iters 5000).  Same generator as bench.py
+    (problems.lasso_cfg5).  Stores the iteration count and checksums of the solution."""
+    A, b, reg = problems.lasso_cfg5(4096)
+    kw = dict(rho=0.4, check_stop=10, add_bias=True, eps_abs=1e-6, eps_rel=1e-6, max_iters=5000)
+    s = LassoSolver(A=A.copy(), b=b, reg=reg, compute_loss=False, adaptive_rho=False, use_gpu=False, check_cvxpy=False,
+                    **kw)
+    X, sol, _, its = s.solve()
+    rec = dict(name="lasso_cfg5_full", K=4096, settings=kw, iterations=int(its), solutions_sum=float(np.sum(sol)),
+               solutions_head=[float(v) for v in sol[:16]], X_frob=float(np.linalg.norm(X)),
+               X_abs_sum=float(np.abs(X).sum()), X_nnz=int(np.count_nonzero(X)), X_col0=[float(v) for v in X[:, 0]])
+    print("lasso_cfg5_full", its, rec["solutions_sum"], rec["X_frob"], rec["X_nnz"])
+    with open(os.path.join(HERE, "lasso_full.json"), "w") as f:
+        json.dump(rec, f, indent=1)
+
+
 def large_cases():
     """BASELINE cfg-2 family at n = 1024 and n = 2048 (cold and warm) and the cfg-3 family at n = 2048 (p = 512 equalities,
     k = 64 inequalities: the n = 8192, p = 2048, k = 20 shape of tests/test_fullsize_gpu.py scaled down 4x), constructor
@@ -300,6 +317,9 @@ def large_cases():
 
 
 def main():
+    if "--lasso-full-only" in sys.argv:
+        lasso_full_size()
+        return
     if "--kat-only" in sys.argv:
         phase_one_kat()
         return

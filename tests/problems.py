@@ -57,6 +57,18 @@ def lasso_testsolver(seed=1, n=100, m=80, num_problems=30):
     return dict(A=A, b=b, reg=reg)
 
 
+def lasso_cfg5(K, n=512, rows=2048, seed=5):
+    """BASELINE configs[4]: A 2048 x 512 (+ bias added by the solver), K problems, generator of testSolver.py:1096-1104."""
+    rs = np.random.RandomState(seed)
+    A = rs.rand(rows, n)
+    nnz = int(n * K / 4)
+    x_true = np.zeros((n, K))
+    x_true[np.unravel_index(rs.randint(0, n * K, nnz), (n, K))] = rs.uniform(0, 50, nnz)
+    reg = 0.05 + 0.01 * rs.randn(K)
+    b = A @ x_true + rs.randn(rows, K)
+    return A, b, reg
+
+
 def lp_dense_family(seed, n, m=None, warm=False):
     """BASELINE cfg-2 family: inequality-only dense LP with box +-3."""
     m = 2 * n if m is None else m

@@ -387,3 +387,76 @@ def test_peer_hessian_kernels_emulated_ranks(n, m, R):
     assert np.all(got0[:, :n][il] == 7.0) and np.all(got0[:, n:] == 7.0)   # strict lower triangle / padding untouched
     for r in range(1, R):
         assert torch.equal(H[r], H[0])                                       # bit-identical on every "rank"
+
+
+def _admm_numpy(Qt, bA, eta, rho, alpha, u, add_bias, positive, iters):
+    """LassoSolver.py:245-253 / 517-543 restated for the kernel's operands (Q~ = -m rho Q, z = u - alpha)."""
+    r = d = a = un_ = None
+    for _ in range(iters):
+        x = bA + Qt @ (u - alpha)
+        v = x + u
+        an = np.maximum(v - eta, 0.0)
+        if not positive:
+            an -= np.maximum(-v - eta, 0.0)
+        if add_bias:
+            an[0] = v[0]
+        un = u + x - an
+        r, d, a, un_ = np.sum((x - an) ** 2), np.sum((rho * (an - alpha)) ** 2), np.sum(an ** 2), np.sum(un ** 2)
+        alpha, u = an, un
+    return alpha, u, np.array([r, d, a, un_])
+
+
+@pytest.mark.parametrize("n,K,add_bias,positive", [(513, 300, 1, 0), (101, 30, 1, 0), (257, 3900, 1, 1), (64, 17, 0, 0),
+                                                   (200, 1000, 0, 0)])
+def test_lasso_admm_steps_multi_iteration(n, K, add_bias, positive):
+    """ipm_lasso_admm_steps_f64 (persistent multi-iteration kernel, csrc/lasso_multi.cu) against NumPy and against the
+    one-launch-per-iteration kernel: both tile shapes (257 x 3900 takes the 128 x 64 tile, the others 64 x 32), ragged
+    rows / columns / contraction tails, tail-row units (513 = 4 * 128 + 1, 257), two launches in a row (odd iteration
+    parity), and the device-side stop test."""
+    rs = np.random.RandomState(n + K)
+    M = rs.randn(n, n)
+    Qt = -(M @ M.T) / (n * 4.0)
+    Qt = 0.5 * (Qt + Qt.T)
+    bA = rs.randn(n, K)
+    eta = np.abs(rs.randn(K)) * 0.3
+    rho = 0.4
+    ld = (K + 15) // 16 * 16
+    Qd, ldq = padded(Qt)
+    bAd, _ = padded(bA)
+    eta_d = dev(eta)
+    st = [torch.zeros((n, ld), dtype=torch.float64, device="cuda") for _ in range(4)]  # alpha, u, z0, z1
+    L = _abi.lib()
+    ws = torch.zeros(L.ipm_lasso_steps_ws_bytes(n, K), dtype=torch.uint8, device="cuda")
+    state = ws[:8].view(torch.int32)
+    off = L.ipm_lasso_steps_norms_offset(n, K)
+    total = 0
+    alpha_ref, u_ref = np.zeros((n, K)), np.zeros((n, K))
+    for n_iters in (3, 1, 4):
+        _abi.call("ipm_lasso_admm_steps_f64", Qd.data_ptr(), ldq, n, K, bAd.data_ptr(), eta_d.data_ptr(), rho,
+                  st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), st[3].data_ptr(), ld, add_bias, positive, n_iters,
+                  1, 0.0, 0.0, ws.data_ptr(), None)
+        torch.cuda.synchronize()
+        assert L.ipm_device_fault() == 0
+        total += n_iters
+        alpha_ref, u_ref, norms_ref = _admm_numpy(Qt, bA, eta[None, :], rho, alpha_ref, u_ref, add_bias, positive, n_iters)
+        assert state[:2].tolist() == [0, total]
+        scale = 1.0 + np.max(np.abs(u_ref))
+        assert np.max(np.abs(st[0][:, :K].cpu().numpy() - alpha_ref)) < 1e-11 * scale
+        assert np.max(np.abs(st[1][:, :K].cpu().numpy() - u_ref)) < 1e-11 * scale
+        z = st[2 + (total & 1)][:, :K].cpu().numpy()
+        assert np.max(np.abs(z - (u_ref - alpha_ref))) < 1e-11 * scale
+        norms = ws[off:off + 32].view(torch.float64).cpu().numpy()
+        np.testing.assert_allclose(norms, norms_ref, rtol=1e-9)
+    # a stop test that holds trivially (huge absolute tolerance) raises the flag; the next launch must be a no-op
+    _abi.call("ipm_lasso_admm_steps_f64", Qd.data_ptr(), ldq, n, K, bAd.data_ptr(), eta_d.data_ptr(), rho,
+              st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), st[3].data_ptr(), ld, add_bias, positive, 2, 1, 1e300,
+              0.0, ws.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert state[:2].tolist() == [1, total + 2]
+    snap = [t.clone() for t in st]
+    _abi.call("ipm_lasso_admm_steps_f64", Qd.data_ptr(), ldq, n, K, bAd.data_ptr(), eta_d.data_ptr(), rho,
+              st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), st[3].data_ptr(), ld, add_bias, positive, 5, 1, 1e300,
+              0.0, ws.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert state[:2].tolist() == [1, total + 2]
+    assert all(torch.equal(a, b) for a, b in zip(st, snap))
