@@ -1,27 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200 interior-point engine (contract: see DESIGN.md, "Measurement").
 
-Workload (BASELINE.json configs[1]): dense random LP, n = 8192 variables, m = 16384 inequality rows plus box
-bounds, FP64, constructor defaults of the reference's ``LPSolver``; warm start (x0 strictly feasible, so the
-timed region is the main barrier phase).  One bench "step" = one complete ``LPSolver.solve()``.
+Headline workload (BASELINE.json configs[1]): dense random LP, n = 8192 variables, m = 16384 inequality rows plus box
+bounds, FP64, constructor defaults of the reference's ``LPSolver``; warm start (x0 strictly feasible, so the timed region
+is the main barrier phase).  One bench "step" = one complete ``LPSolver.solve()``.
 
-  metric `newton_steps_per_s` = Newton iterations performed / device time, summed over all ranks.
+  metric `newton_steps_per_s` = Newton iterations performed / device time.
   value : problem data already resident in HBM (solver constructed before the timed region; what the reference
           times, testSolver.py:151-153).
   e2e   : through the public API from HOST NumPy buffers: constructor (H2D of C, d, c, bounds) + solve() + the
           device->host read of the solution, all inside the timed region.
   roofline : the Hessian kernel  H = C' diag(w) C  (ipm_gemm_tn_f64, FP64 DMMA): algorithmic m*n*(n+1) flop per
           launch / mean launch time from CUDA events recorded around every such launch inside the timed region.
-  cpu_baseline : the CPU oracle (NumPy/SciPy restatement of the reference, oracle/) on this box's host cores on
-          a bounded sample (a fixed number of full-size Newton steps).
+  cpu_baseline : the reference's own NumPy classes (oracle/_ref, copied by oracle/build_ref.py; else the oracle port) on
+          this box's host cores on a bounded sample (a fixed number of full-size Newton steps).
 
-N > 1 (torchrun): every rank solves its own copy of the same LP instance with no data-path collective ("weak"
-scaling; BASELINE north_star: batches of independent LP instances split across GPUs with no communication).  The
-copies are identical on purpose: instances drawn from different seeds need different numbers of Newton steps
-(76 .. 130 at this size), and the max-over-ranks time would then measure that imbalance instead of the hardware.
+N = 1 additionally reports, as sub-objects of the same JSON line: `cold` (cfg 2 from the default x0: phase-I + main),
+`qp` (configs[2]: n = 8192, p = 2048 equalities), `socp` (configs[3]: n = 16384, 256 cones of 64), `lasso`
+(configs[4]: 4096 problems, with its own CPU baseline) and `factorisation` (the Cholesky alone against the FP64 peak).
 
-`--impl reference` times the reference algorithm on the host CPU (oracle port; the reference itself is pure
-Python/NumPy and does not travel to the GPU box) for the same metric.
+N > 1 (torchrun): ONE cfg-2 problem, its constraint rows sharded over the ranks (BASELINE north_star: "a large single
+problem is sharded by constraint rows"): strong scaling, `value` = Newton steps/s of that one solve, with
+`hessian_formation` (partial SYRK + exchange) timed separately; sub-objects `socp` (configs[3] sharded by whole cones),
+`lasso` (batch split, no communication) and `replicas` (one independent copy of the LP per GPU, no collective -- the
+weak-scaling number).  `--shard instances` makes the replicas the headline instead.
+
+`--impl reference` times the reference implementation on the host CPU for the same metric and config (rank 0 alone).
 """
 
 import argparse
@@ -39,6 +43,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 FP64_TENSOR_PEAK_TFLOPS = 37.1  # measured DMMA.8x8x4 issue rate on this pool's B200 (profiles/fp64_peak_r01.json)
+PEAK_SOURCE = ("FP64 DMMA issue-rate microbenchmark on this pool (tools/fp64_peak.cu, profiles/fp64_peak_r01.json) = 148 SM "
+               "x 64 FMA/clk x 2 x 1.965 GHz; MEASURED_PEAKS.json has no FP64 entry")
 
 
 def parse():
@@ -49,70 +55,169 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=8192)
     ap.add_argument("--m", type=int, default=None)
-    ap.add_argument("--cpu-newton-steps", type=int, default=2, help="full-size Newton steps in the CPU sample")
+    ap.add_argument("--cpu-newton-steps", type=int, default=3, help="full-size Newton steps in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--shard", default="instances", choices=["instances", "rows"],
-                    help="N > 1: independent LP instance per GPU (weak, no collective) or ONE LP row-sharded with an "
-                         "NCCL all-reduce of the partial Hessian (strong)")
+    ap.add_argument("--shard", default="auto", choices=["auto", "instances", "rows"],
+                    help="N > 1: ONE LP row-sharded (strong scaling; the default) or an independent LP instance per GPU "
+                         "(weak, no collective)")
     ap.add_argument("--lasso-k", type=int, default=4096, help="Lasso batch size (0 disables the Lasso section)")
-    ap.add_argument("--workload", default="lp", choices=["lp", "socp"],
-                    help="lp: BASELINE configs[1] (the headline); socp: configs[3] (n=16384, 256 cones of 64 rows, "
-                         "test_SOCP settings) -- use with --shard rows for the cone-sharded Hessian scaling numbers")
+    ap.add_argument("--sections", default="all",
+                    help="comma list of the extra sections to run: cold,qp,socp,lasso,factorisation,replicas (or all / none)")
     ap.add_argument("--cones", type=int, default=256)
-    ap.add_argument("--factorisation", action="store_true",
-                    help="N = 1: also time the n x n Cholesky alone, stream-ordered and single-launch tile-DAG, and add a "
-                         "'factorisation' object (roofline against the FP64 tensor peak) to the JSON line")
+    ap.add_argument("--factorisation", action="store_true", help=argparse.SUPPRESS)  # always on now (sections)
     return ap.parse_args()
 
 
-def factorisation_section(n, reps=5):
-    """ipm_potrf_upper_f64 (stream-ordered) and ipm_potrf_upper_dag_f64 (one persistent launch) on an SPD matrix with
-    the Hessian's structure (C' diag(w) C + I), L2 flushed before every factorisation; n^3 / 3 flop."""
-    import torch
-
-    from ipm_b200 import _abi
-
-    g = torch.Generator(device="cuda").manual_seed(n)
-    C_ = torch.rand((2 * n, n), dtype=torch.float64, device="cuda", generator=g) * 4 - 2
-    w = torch.rand(2 * n, dtype=torch.float64, device="cuda", generator=g) + 0.5
-    H = torch.zeros((n, n), dtype=torch.float64, device="cuda")
-    _abi.call("ipm_gemm_tn_f64", C_.data_ptr(), n, C_.data_ptr(), n, w.data_ptr(), 1.0, 0.0, H.data_ptr(), n, n, n,
-              2 * n, 1, None)
-    H.diagonal().add_(1.0)
-    del C_
-    work = torch.empty_like(H)
-    info = torch.zeros(1, dtype=torch.int32, device="cuda")
-    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
-    out = {"n": n, "flop": n ** 3 / 3.0, "l2": "256 MB written between repetitions"}
-    import ctypes as C
-
-    lib = _abi.lib()
-    for nm in ("ipm_internal_potrf_stream_f64", "ipm_internal_potrf_dag1_f64"):  # library-internal A/B entry points
-        getattr(lib, nm).restype, getattr(lib, nm).argtypes = C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p,
-                                                                         C.c_void_p]
-    for key, name in (("default", "ipm_potrf_upper_f64"), ("stream_ordered", "ipm_internal_potrf_stream_f64"),
-                      ("tile_dag_per_tile_deps", "ipm_internal_potrf_dag1_f64"),
-                      ("tile_dag_pipelined", "ipm_potrf_upper_dag_f64")):
-        ts = []
-        for _ in range(reps + 1):
-            work.copy_(H)
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            e0.record()
-            _abi.check(getattr(lib, name)(work.data_ptr(), n, n, info.data_ptr(), None), name)
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        assert int(info.item()) == 0
-        ms = float(np.median(ts[1:]))
-        tf = out["flop"] / (ms * 1e-3) / 1e12
-        out[key] = {"ms": ms, "achieved": tf, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
-                    "frac": tf / FP64_TENSOR_PEAK_TFLOPS, "entry_point": name}
-    return out
+def wants(args, name):
+    s = args.sections
+    return s == "all" or (s != "none" and name in s.split(","))
 
 
+# --------------------------------------------------------------------------------------------------- workloads
+def workload_config(n, m):
+    """The `config` object: identical in the b200 arm and the reference arm."""
+    return {"workload": f"dense LP n={n} m={m} box+-3, warm start (BASELINE configs[1])",
+            "l2": "inputs (%.2f GB) larger than L2" % (8e-9 * m * n)}
+
+
+def lp_workload(args):
+    import problems
+
+    m = 2 * args.n if args.m is None else args.m
+    return problems.lp_dense_family(seed=8192, n=args.n, m=m, warm=True), m
+
+
+def lasso_workload(K):
+    """BASELINE configs[4]: A 2048x512 (+bias), K problems, generator of testSolver.py:1096-1104 (seed 5)."""
+    import problems
+
+    return problems.lasso_cfg5(K)
+
+
+LASSO_KW = dict(rho=0.4, check_stop=10, add_bias=True, check_cvxpy=False, eps_abs=1e-6, eps_rel=1e-6, max_iters=5000)
+
+
+# --------------------------------------------------------------------------------------------------- host CPU arm
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank, which would time the CPU arm on ONE core.  The CPU arm runs on
+    rank 0 alone (the other ranks exit), so it may -- and per the contract must -- use every core of the host."""
+    try:
+        import scipy.linalg  # noqa: F401  (SciPy ships its own OpenBLAS; it must be loaded before the limit is raised)
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=len(os.sched_getaffinity(0)), user_api="blas")
+    except Exception:
+        pass
+
+
+def blas_info():
+    """BLAS vendor / thread count behind NumPy on this host (SURVEY 8(d): report them with the CPU baseline)."""
+    try:
+        from threadpoolctl import threadpool_info
+
+        libs = [f"{i.get('internal_api', '?')} {i.get('version', '')} x{i.get('num_threads', '?')}"
+                for i in threadpool_info() if i.get("user_api") == "blas"]
+        return "; ".join(libs) or "unknown BLAS"
+    except Exception:
+        return "unknown BLAS"
+
+
+def blas_threads():
+    """Threads the NumPy BLAS actually uses (the `cores` of the CPU baseline); os.cpu_count() if unknown."""
+    try:
+        from threadpoolctl import threadpool_info
+
+        n = [i.get("num_threads") for i in threadpool_info() if i.get("user_api") == "blas"]
+        return int(max(n)) if n else os.cpu_count()
+    except Exception:
+        return os.cpu_count()
+
+
+_REF = None
+
+
+def reference_classes():
+    """(classes, kind): the reference's own modules from oracle/_ref when the recipe has been run, else the oracle port."""
+    global _REF
+    if _REF is None:
+        from oracle import build_ref
+
+        cls = build_ref.import_reference()
+        if cls is not None:
+            _REF = (cls, "reference")
+        else:
+            from oracle import OracleLasso, OracleLP
+
+            _REF = ({"LPSolver": OracleLP, "LassoSolver": OracleLasso}, "port")
+    return _REF
+
+
+def cpu_sample(prob, newton_steps):
+    """Bounded CPU sample: `newton_steps` full-size Newton iterations (first centering step) of the reference's
+    LPSolver.  Returns (Newton steps, seconds, kind)."""
+    cls, kind = reference_classes()
+    p = dict(prob)
+    p["x0"] = prob["x0"].copy()
+    extra = dict(check_cvxpy=False, suppress_print=True) if kind == "reference" else {}
+    o = cls["LPSolver"](**p, max_outer_iters=1, max_inner_iters=newton_steps, **extra)
+    t0 = time.perf_counter()
+    o.solve()
+    dt = time.perf_counter() - t0
+    return sum(o.inner_iters), dt, kind
+
+
+def cpu_lasso_sample(K_sample=128):
+    """The reference's LassoSolver on a K_sample-column subset of the cfg-5 batch, solved to its stop test."""
+    cls, kind = reference_classes()
+    A, b, reg = lasso_workload(4096)
+    step = 4096 // K_sample
+    kw = {k: v for k, v in LASSO_KW.items() if k != "check_cvxpy"}
+    bs, rs_ = np.ascontiguousarray(b[:, ::step]), np.ascontiguousarray(reg[::step])
+    if kind == "reference":
+        s = cls["LassoSolver"](A=A.copy(), b=bs, reg=rs_, compute_loss=False, adaptive_rho=False, use_gpu=False,
+                               check_cvxpy=False, **kw)
+    else:
+        s = cls["LassoSolver"](A.copy(), bs, rs_, **kw)
+    t0 = time.perf_counter()
+    out = s.solve()
+    dt = time.perf_counter() - t0
+    its = out[-1]
+    return K_sample / dt, dt, int(its if not isinstance(its, list) else its[0]), kind
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    use_all_host_threads()
+    prob, m = lp_workload(args)
+    times, steps, kind = [], 0, "port"
+    for i in range(args.warmup + args.steps):
+        k, dt, kind = cpu_sample(prob, 1)
+        if i >= args.warmup:
+            times.append(dt)
+            steps += k
+    total = sum(times)
+    val = steps / total
+    cores = blas_threads()
+    what = ("the reference's own LPSolver / NewtonSolverCholesky / FunctionManagerLP (oracle/_ref, unmodified)"
+            if kind == "reference" else "the oracle port (oracle/_ref absent)")
+    cfg = workload_config(args.n, m)
+    cfg["per_rank"] = "host CPU, rank 0 alone"
+    line = {
+        "impl": "reference", "metric": "newton_steps_per_s", "value": val, "unit": "Newton steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "step": "a bounded sample: one full-size Newton iteration of the first centering step per bench step",
+        "cpu_baseline": {"value": val, "unit": "Newton steps/s", "cores": cores, "kind": kind,
+                         "sample": f"{steps} full-size Newton iterations of {what} (NumPy/SciPy; BLAS: {blas_info()})"},
+        "e2e": {"value": val, "unit": "Newton steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------- device helpers
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -171,181 +276,72 @@ def hessian_dram_traffic(n, m):
         return None
 
 
-def workload(args, rank):
-    import problems
+class Dist:
+    """Rank bookkeeping + the contract's timing bracket (barrier + synchronize on both sides, MAX over ranks)."""
 
-    if args.workload == "socp":
-        n = 16384 if args.n == 8192 else args.n  # --n default is the LP's
-        args.n = n
-        return problems.socp_family(seed=4, n=n, M=args.cones, k=64), args.cones * 66
-    m = 2 * args.n if args.m is None else args.m
-    prob = problems.lp_dense_family(seed=8192, n=args.n, m=m, warm=True)
-    return prob, m
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
 
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
 
-def cpu_sample(prob, newton_steps):
-    """Bounded CPU sample: `newton_steps` full-size Newton iterations of the oracle (first centering step)."""
-    from oracle import OracleLP
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    p = dict(prob)
-    p["x0"] = prob["x0"].copy()
-    o = OracleLP(**p, max_outer_iters=1, max_inner_iters=newton_steps)
-    t0 = time.perf_counter()
-    o.solve()
-    dt = time.perf_counter() - t0
-    return sum(o.inner_iters), dt
+    def timed(self, fn, steps):
+        """fn() `steps` times between two barriers; returns (ms max over ranks, list of fn results)."""
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = [fn() for _ in range(steps)]
+        e1.record()
+        self.barrier()
+        return self.max(e0.elapsed_time(e1)), out
 
+    def max(self, v):
+        if self.world == 1:
+            return float(v)
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t[0])
 
-def blas_info():
-    """BLAS vendor / thread count behind NumPy on this host (SURVEY 8(d): report them with the CPU baseline)."""
-    try:
-        from threadpoolctl import threadpool_info
+    def sum(self, v):
+        if self.world == 1:
+            return float(v)
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t[0])
 
-        libs = [f"{i.get('internal_api', '?')} {i.get('version', '')} x{i.get('num_threads', '?')}"
-                for i in threadpool_info() if i.get("user_api") == "blas"]
-        return "; ".join(libs) or "unknown BLAS"
-    except Exception:
-        return "unknown BLAS"
-
-
-def blas_threads():
-    """Threads the NumPy BLAS actually uses (the `cores` of the CPU baseline); os.cpu_count() if unknown."""
-    try:
-        from threadpoolctl import threadpool_info
-
-        n = [i.get("num_threads") for i in threadpool_info() if i.get("user_api") == "blas"]
-        return int(max(n)) if n else os.cpu_count()
-    except Exception:
-        return os.cpu_count()
-
-
-def lasso_workload(K):
-    """BASELINE configs[4]: A 2048x512 (+bias), K problems, generator of testSolver.py:1096-1104 (seed 5)."""
-    import problems
-
-    return problems.lasso_cfg5(K)
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
 
 
-def lasso_section(K, rank, world):
-    """Second headline metric (Lasso solves/s): the batch is split by strided columns across ranks (the
-    reference's num_chunks semantics), no communication.  Settings of the reference's GPU arm
-    (testSolver.py:1142-1159: eps 1e-6, max_iters 5000)."""
+def pin(prob):
     import torch
 
-    from ipm_b200 import dist as D
-    from ipm_b200.LassoSolver import LassoSolver
-
-    A, b, reg = lasso_workload(K)
-    cols = D.strided_columns(K, rank, world)
-    kw = dict(rho=0.4, check_stop=10, add_bias=True, check_cvxpy=False, eps_abs=1e-6, eps_rel=1e-6, max_iters=5000)
-    s = LassoSolver(A, b[:, cols], reg[cols], **kw)
-    s.solve()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = s.L.kernel_launches()
-    e0.record()
-    _, sol, _, its = s.solve()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    launches = s.L.kernel_launches() - l0
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    s2 = LassoSolver(A, b[:, cols], reg[cols], **kw)
-    X2, _, _, _ = s2.solve()
-    f1.record()
-    torch.cuda.synchronize()
-    ms_e2e = f0.elapsed_time(f1)
-    n1 = A.shape[1] + 1
-    return dict(ms=ms, ms_e2e=ms_e2e, iters=int(its), k_local=len(cols), launches=launches,
-                flop=2.0 * n1 * n1 * len(cols) * its, h2d=s2.h2d_bytes, d2h=int(X2.nbytes))
+    return {k: (torch.as_tensor(v).pin_memory().numpy() if isinstance(v, np.ndarray) else v) for k, v in prob.items()}
 
 
-def use_all_host_threads():
-    """torchrun exports OMP_NUM_THREADS=1 to every rank, which would time the CPU arm on ONE core.  The CPU arm runs on
-    rank 0 alone (the other ranks exit), so it may -- and per the contract must -- use every core of the host."""
-    try:
-        import scipy.linalg  # noqa: F401  (SciPy ships its own OpenBLAS; it must be loaded before the limit is raised)
-        from threadpoolctl import threadpool_limits
+# --------------------------------------------------------------------------------------------------- sections
+def lp_section(D, args, prob, m, rows_mode, steps, warmup, e2e=True, profile=True):
+    """cfg 2 (warm): resident-data arm + end-to-end arm.  Returns a dict of raw numbers (rank-reduced)."""
+    torch = D.torch
+    from ipm_b200.LPSolver import LPSolver
 
-        threadpool_limits(limits=len(os.sched_getaffinity(0)), user_api="blas")
-    except Exception:
-        pass
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    use_all_host_threads()
-    prob, m = workload(args, 0)
-    times, steps = [], 0
-    for i in range(args.warmup + args.steps):
-        k, dt = cpu_sample(prob, 1)
-        if i >= args.warmup:
-            times.append(dt)
-            steps += k
-    total = sum(times)
-    val = steps / total
-    cores = blas_threads()
-    line = {
-        "impl": "reference", "metric": "newton_steps_per_s", "value": val, "unit": "Newton steps/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"dense LP n={args.n} m={m} box+-3, warm start (BASELINE configs[1])",
-                   "sample": "one full-size Newton iteration per step"},
-        "cpu_baseline": {"value": val, "unit": "Newton steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{steps} full-size Newton iterations of the oracle (NumPy/SciPy; BLAS: "
-                                   f"{blas_info()})"},
-        "e2e": {"value": val, "unit": "Newton steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    print(json.dumps(line))
-
-
-def main():
-    args = parse()
-    if args.impl == "reference":
-        run_reference(args)
-        return
-    import torch
-    import torch.distributed as dist
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    from ipm_b200.LPSolver import LPSolver as _LP
-    from ipm_b200.SOCPSolver import SOCPSolver as _SOCP
-    import problems
-
-    rows_mode = world > 1 and args.shard == "rows"
-    prob, m = workload(args, 0 if rows_mode else rank)
-    n = args.n
-    socp = args.workload == "socp"
-    if socp:
-        args.lasso_k = 0
-        args.no_cpu_baseline = True
-
-        def LPSolver(**kw):  # same call shape as the LP arm
-            return _SOCP(**kw, **problems.SOCP_TEST_SETTINGS)
-        host = prob
-    else:
-        LPSolver = _LP
-        host = {k: (torch.as_tensor(v).pin_memory().numpy() if isinstance(v, np.ndarray) else v)
-                for k, v in prob.items()}
+    host = pin(prob)
     x0 = prob["x0"].copy()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ------------------------------------------------------------------ resident-data arm
-    solver = LPSolver(**{k: v for k, v in host.items() if k != "x0"}, x0=x0.copy(), check_cvxpy=False,
-                      suppress_print=True, shard_rows=rows_mode)
+    kw = dict(check_cvxpy=False, suppress_print=True, shard_rows=rows_mode)
+    solver = LPSolver(**{k: v for k, v in host.items() if k != "x0"}, x0=x0.copy(), **kw)
     x0_dev = solver.x_dev.clone()
 
     def one_solve():
@@ -353,147 +349,369 @@ def main():
         solver.solve()
         return sum(solver.inner_iters)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         one_solve()
     L = solver.launcher
-    L.timed_ops = {"ipm_gemm_tn_f64": [], "ipm_syrk_scatter_f64": [], "range:hessian_formation": []}
+    if profile:
+        L.timed_ops = {"ipm_gemm_tn_f64": [], "ipm_syrk_scatter_f64": [], "range:hessian_formation": [],
+                       "ipm_potrf_upper_f64": []}
     launches0 = L.kernel_launches()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    newton = 0
-    with ClockSampler(local_rank) as clk:
-        e0.record()
-        for _ in range(args.steps):
-            newton += one_solve()
-        e1.record()
-        barrier()
-    ms = e0.elapsed_time(e1)
-    launches = L.kernel_launches() - launches0
-    hess = [a.elapsed_time(b) for key in ("ipm_gemm_tn_f64", "ipm_syrk_scatter_f64")
-            for a, b, tag in L.timed_ops[key] if tag == "hessian"]
-    hform = [a.elapsed_time(b) for a, b, _ in L.timed_ops["range:hessian_formation"]]
-    comm_bytes = getattr(solver.ns, "comm_bytes", 0)
-    solver_ns = solver.ns
-    L.timed_ops = None
-    value_ref = solver.value
-    m_local = solver.data.rows_w if socp else solver.data.m
-
-    # ------------------------------------------------------------------ end-to-end arm (host buffers)
-    e2e_ms, e2e_newton, h2d, d2h = None, 0, 0, 0
-    if not args.no_e2e:
-        del solver
-        torch.cuda.empty_cache()
+    with ClockSampler(D.local_rank) as clk:
+        ms, counts = D.timed(one_solve, steps)
+    out = dict(ms=ms, newton=float(sum(counts)), launches=D.sum(L.kernel_launches() - launches0), clocks=clk.summary(),
+               value_obj=solver.value, m_local=solver.data.m, comm_bytes=getattr(solver.ns, "comm_bytes", 0),
+               peer=getattr(solver.ns, "peer", None) is not None, inner_iters=list(solver.inner_iters))
+    if profile:
+        out["hess"] = [a.elapsed_time(b) for key in ("ipm_gemm_tn_f64", "ipm_syrk_scatter_f64")
+                       for a, b, tag in L.timed_ops[key] if tag == "hessian"]
+        out["hform"] = [a.elapsed_time(b) for a, b, _ in L.timed_ops["range:hessian_formation"]]
+        out["potrf"] = [a.elapsed_time(b) for a, b, _ in L.timed_ops["ipm_potrf_upper_f64"]]
+        L.timed_ops = None
+    del solver
+    torch.cuda.empty_cache()
+    if e2e:
+        n = args.n
 
         def e2e_step():
-            s = LPSolver(**{k: v for k, v in host.items() if k != "x0"}, x0=x0.copy(), check_cvxpy=False,
-                         suppress_print=True, shard_rows=rows_mode)
+            s = LPSolver(**{k: v for k, v in host.items() if k != "x0"}, x0=x0.copy(), **kw)
             s.solve()
             xs = s.xstar  # device -> host read of the result
             return sum(s.inner_iters), s.data.h2d_bytes + 8 * n, xs.nbytes + 8
 
         e2e_step()  # warm-up (allocator)
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(args.steps):
-            k, h2d, d2h = e2e_step()
-            e2e_newton += k
-        f1.record()
-        barrier()
-        e2e_ms = f0.elapsed_time(f1)
-
-    # ------------------------------------------------------------------ Lasso batch (second headline metric)
-    lasso = None
-    if args.lasso_k > 0:
+        e2e_ms, res = D.timed(e2e_step, steps)
+        out.update(e2e_ms=e2e_ms, e2e_newton=float(sum(r[0] for r in res)), h2d=res[-1][1], d2h=res[-1][2])
         torch.cuda.empty_cache()
-        barrier()
-        lasso = lasso_section(args.lasso_k, rank, world)
-        lt = torch.tensor([lasso["ms"], lasso["ms_e2e"]], dtype=torch.float64, device="cuda")
-        ls = torch.tensor([lasso["flop"], float(lasso["launches"])], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(lt, op=dist.ReduceOp.MAX)
-            dist.all_reduce(ls, op=dist.ReduceOp.SUM)
-        lasso.update(ms=float(lt[0]), ms_e2e=float(lt[1]), flop=float(ls[0]), launches=int(ls[1]))
+    return out
 
-    # ------------------------------------------------------------------ reduce over ranks (max time, sum work)
-    stats = torch.tensor([ms, float(newton), e2e_ms or 0.0, float(e2e_newton), float(launches)], dtype=torch.float64,
-                         device="cuda")
-    if world > 1:
-        tmax = stats.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = stats.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms, e2e_ms = float(tmax[0]), float(tmax[2])
-        launches = float(tsum[4])
-        if not rows_mode:  # independent instances: work adds up; one sharded problem: every rank counted the same steps
-            newton, e2e_newton = float(tsum[1]), float(tsum[3])
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
 
-    value = newton / (ms * 1e-3)
+def cold_section(D, args, prob):
+    """cfg 2 from the reference's default x0 (box midpoint, infeasible for C x <= d): phase-I + main phase -- what a user
+    who passes no x0 gets."""
+    from ipm_b200.LPSolver import LPSolver
+
+    s = LPSolver(**{k: v for k, v in prob.items() if k != "x0"}, check_cvxpy=False, suppress_print=True)
+    ms, counts = D.timed(lambda: (s.solve(), sum(s.inner_iters) + sum(s.phase1_solver.inner_iters))[1], 1)
+    out = {"workload": "cfg 2 from the default x0 (phase-I + main phase), one LPSolver.solve()", "time_to_solve_s": ms * 1e-3,
+           "newton_steps": int(counts[0]), "phase1_newton_steps": int(sum(s.phase1_solver.inner_iters)),
+           "main_newton_steps": int(sum(s.inner_iters)), "value": counts[0] / (ms * 1e-3), "unit": "Newton steps/s",
+           "objective": s.value}
+    del s
+    D.torch.cuda.empty_cache()
+    return out
+
+
+def qp_section(D, args):
+    """configs[2]: random QP n = 8192, p = 2048 equalities (infeasible start, block elimination / Schur complement), 20
+    inequalities (phase-I), box; test_QP settings."""
+    torch = D.torch
+    import problems
+    from ipm_b200.QPSolver import QPSolver
+
+    def gram(Pp):
+        t = torch.as_tensor(Pp).to("cuda")
+        return (t.T @ t).cpu().numpy()
+
+    n, p, k = args.n, args.n // 4, 20
+    prob = problems.qp_dense_family(seed=3, n=n, p=p, k=k, gram=gram)
+    s = QPSolver(**prob, check_cvxpy=False, suppress_print=True, **problems.QP_TEST_SETTINGS)
+    del prob
+    L = s.launcher
+    L.timed_ops = {"ipm_gemm_tn_f64": [], "ipm_potrf_upper_f64": [], "ipm_trsm_upper_t_f64": []}
+    marks = {}
+
+    orig = s.phase1_solver.solve
+
+    def phase1_then_mark(*a, **k_):
+        out = orig(*a, **k_)
+        torch.cuda.synchronize()
+        marks["t1"] = time.perf_counter()
+        for v in L.timed_ops.values():
+            v.clear()
+        return out
+
+    s.phase1_solver.solve = phase1_then_mark
+    D.barrier()
+    t0 = time.perf_counter()
+    s.solve()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    tm = {k_: float(np.sum([a.elapsed_time(b) for a, b, _ in v])) for k_, v in L.timed_ops.items()}
+    L.timed_ops = None
+    t1 = marks.get("t1", t0)
+    steps = int(sum(s.inner_iters))
+    ms = (t2 - t1) * 1e3
+    # per main-phase Newton step: SYRK k n^2 (tiny) + potrf n^3/3 + TRSM n^2 p + Schur n p^2 + potrf p^3/3
+    flop = k * n * (n + 1) + n ** 3 / 3 + float(n) * n * p + float(n) * p * (p + 1) + p ** 3 / 3
+    ms_step = ms / steps
+    out = {"workload": f"QP n={n}, p={p} equalities, k={k} inequalities, box, test_QP settings (BASELINE configs[2]); one "
+           "QPSolver.solve() = phase-I + main phase", "time_to_solve_s": t2 - t0, "main_time_s": ms * 1e-3,
+           "phase1_time_s": t1 - t0, "phase1_newton_steps": int(sum(s.phase1_solver.inner_iters)),
+           "main_newton_steps": steps, "ms_per_newton_step": ms_step, "value": steps / (ms * 1e-3),
+           "unit": "Newton steps/s (main phase)", "objective": s.value, "timing": "host clock around synchronised phases",
+           "roofline": {"bound": "tensor", "achieved": flop / (ms_step * 1e-3) / 1e12, "peak": FP64_TENSOR_PEAK_TFLOPS,
+                        "unit": "TFLOP/s", "frac": flop / (ms_step * 1e-3) / 1e12 / FP64_TENSOR_PEAK_TFLOPS,
+                        "flop_per_newton_step": flop,
+                        "what": "whole main-phase Newton step (potrf H, TRSM of A', Schur Y'Y, potrf S) against the FP64 "
+                                "tensor peak"},
+           "ms_per_newton_step_by_call": {k_: v / steps for k_, v in tm.items()}}
+    del s
+    torch.cuda.empty_cache()
+    return out
+
+
+def socp_section(D, args, rows_mode):
+    """configs[3]: SOCP n = 16384, 256 cones of 64 rows, P = I, warm start, test_SOCP settings; N > 1: whole cones sharded
+    over the ranks (partial W' diag(w) W per GPU + peer-memory exchange)."""
+    torch = D.torch
+    import problems
+    from ipm_b200.SOCPSolver import SOCPSolver
+
+    n = 2 * args.n
+    prob = problems.socp_family(seed=4, n=n, M=args.cones, k=64)
+    x0 = prob["x0"].copy()
+    s = SOCPSolver(**{k: v for k, v in prob.items() if k != "x0"}, x0=x0, check_cvxpy=False, suppress_print=True,
+                   shard_rows=rows_mode, **problems.SOCP_TEST_SETTINGS)
+    del prob
+    L = s.launcher
+    L.timed_ops = {"ipm_gemm_tn_f64": [], "ipm_syrk_scatter_f64": [], "range:hessian_formation": [],
+                   "ipm_potrf_upper_f64": []}
+    ms, counts = D.timed(lambda: (s.solve(), sum(s.inner_iters))[1], 1)
+    hess = [a.elapsed_time(b) for key in ("ipm_gemm_tn_f64", "ipm_syrk_scatter_f64")
+            for a, b, tag in L.timed_ops[key] if tag == "hessian"]
+    hform = [a.elapsed_time(b) for a, b, _ in L.timed_ops["range:hessian_formation"]]
+    potrf = [a.elapsed_time(b) for a, b, _ in L.timed_ops["ipm_potrf_upper_f64"]]
+    L.timed_ops = None
+    steps = counts[0]
+    rows_local = s.data.rows_w
+    flops = float(rows_local) * n * (n + 1)
     hess_ms = float(np.mean(hess)) if hess else None
-    flops = float(m_local) * n * (n + 1)  # rows resident on this rank (all m rows unless row-sharded)
+    out = {"workload": f"SOCP n={n}, {args.cones} cones of 64 rows, P=I, warm start, test_SOCP settings (BASELINE "
+           "configs[3]); one SOCPSolver.solve()" + (", whole cones sharded over the GPUs" if rows_mode else ""),
+           "time_to_solve_s": ms * 1e-3, "newton_steps": int(steps), "ms_per_newton_step": ms / steps,
+           "value": steps / (ms * 1e-3), "unit": "Newton steps/s", "objective": s.value,
+           "roofline": {"bound": "tensor", "kernel": "gemm_tn_persistent_kernel (W' diag(w) W, rows of this rank)",
+                        "achieved": flops / (hess_ms * 1e-3) / 1e12 if hess_ms else None, "peak": FP64_TENSOR_PEAK_TFLOPS,
+                        "unit": "TFLOP/s per GPU",
+                        "frac": flops / (hess_ms * 1e-3) / 1e12 / FP64_TENSOR_PEAK_TFLOPS if hess_ms else None,
+                        "ms_per_launch": hess_ms, "launches_timed": len(hess)},
+           "potrf_ms": float(np.mean(potrf)) if potrf else None}
+    if potrf:
+        tf = n ** 3 / 3.0 / (out["potrf_ms"] * 1e-3) / 1e12
+        out["potrf_frac_fp64_peak"] = tf / FP64_TENSOR_PEAK_TFLOPS
+    if rows_mode and hform:
+        out["hessian_formation_ms"] = D.max(float(np.mean(hform)))
+    del s
+    torch.cuda.empty_cache()
+    return out
+
+
+def lasso_section(D, args):
+    """Second headline metric (Lasso solves/s): the batch is split by strided columns across ranks (the reference's
+    num_chunks semantics), no communication.  Settings of the reference's GPU arm (testSolver.py:1142-1159)."""
+    torch = D.torch
+    from ipm_b200 import dist as dmod
+    from ipm_b200.LassoSolver import LassoSolver
+
+    K = args.lasso_k
+    A, b, reg = lasso_workload(K)
+    cols = dmod.strided_columns(K, D.rank, D.world)
+    bl, rl = np.ascontiguousarray(b[:, cols]), np.ascontiguousarray(reg[cols])
+    s = LassoSolver(A, bl, rl, **LASSO_KW)
+    s.solve()
+    launches0 = s.L.kernel_launches()
+    ms, res = D.timed(lambda: s.solve()[3], 2)
+    ms /= 2
+    its = res[-1]
+    launches = (s.L.kernel_launches() - launches0) / 2
+    multi = s.multi_iteration
+    del s
+    torch.cuda.empty_cache()
+    hA, hb, hr = (torch.as_tensor(a).pin_memory().numpy() for a in (A, bl, rl))
+    LassoSolver(hA, hb, hr, **LASSO_KW).solve()  # warm-up of the end-to-end arm (allocator)
+
+    def e2e():
+        s2 = LassoSolver(hA, hb, hr, **LASSO_KW)
+        X2, _, _, _ = s2.solve()
+        return s2.h2d_bytes, int(X2.nbytes)
+
+    ms_e2e, r2 = D.timed(e2e, 1)
+    n1 = A.shape[1] + 1
+    flop = D.sum(2.0 * n1 * n1 * len(cols) * its)
+    tf = flop / (ms * 1e-3) / 1e12 / D.world
+    out = {"metric": "lasso_solves_per_s", "workload": f"LassoSolver ADMM, A 2048x512 + bias, K={K} problems, eps 1e-6 "
+           "(BASELINE configs[4]); strided column split across ranks, no collective",
+           "value": K / (ms * 1e-3), "e2e_value": K / (ms_e2e * 1e-3), "unit": "solves/s", "admm_iterations": int(its),
+           "ms_per_iteration": ms / its, "gpu_launches": int(D.sum(launches)), "h2d_bytes": r2[-1][0],
+           "d2h_bytes": r2[-1][1],
+           "kernel": "lasso_admm_multi_kernel (persistent, check_stop iterations per launch)" if multi else
+           "gemm_tn_kernel<LassoEpilogue> (one launch per iteration)",
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s per GPU",
+                        "frac": tf / FP64_TENSOR_PEAK_TFLOPS,
+                        "note": "2 n^2 K flop per ADMM iteration over the whole solve() incl. stop checks"}}
+    torch.cuda.empty_cache()
+    return out
+
+
+def factorisation_section(n, reps=5):
+    """The n x n Cholesky alone on an SPD matrix with the Hessian's structure (C' diag(w) C + I), L2 flushed before every
+    factorisation; n^3 / 3 flop against the FP64 tensor peak.  `default` is what ipm_potrf_upper_f64 does at this size."""
+    import ctypes as C
+
+    import torch
+
+    from ipm_b200 import _abi
+
+    g = torch.Generator(device="cuda").manual_seed(n)
+    C_ = torch.rand((2 * n, n), dtype=torch.float64, device="cuda", generator=g) * 4 - 2
+    w = torch.rand(2 * n, dtype=torch.float64, device="cuda", generator=g) + 0.5
+    H = torch.zeros((n, n), dtype=torch.float64, device="cuda")
+    _abi.call("ipm_gemm_tn_f64", C_.data_ptr(), n, C_.data_ptr(), n, w.data_ptr(), 1.0, 0.0, H.data_ptr(), n, n, n,
+              2 * n, 1, None)
+    H.diagonal().add_(1.0)
+    del C_
+    work = torch.empty_like(H)
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
+    out = {"n": n, "flop": n ** 3 / 3.0, "l2": "256 MB written between repetitions"}
+    lib = _abi.lib()
+    for nm in ("ipm_internal_potrf_stream_f64", "ipm_internal_potrf_dag1_f64"):  # library-internal A/B entry points
+        getattr(lib, nm).restype, getattr(lib, nm).argtypes = C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                                                         C.c_void_p]
+    for key, name in (("default", "ipm_potrf_upper_f64"), ("stream_ordered", "ipm_internal_potrf_stream_f64"),
+                      ("tile_dag_per_tile_deps", "ipm_internal_potrf_dag1_f64"),
+                      ("tile_dag_pipelined", "ipm_potrf_upper_dag_f64")):
+        ts = []
+        for _ in range(reps + 1):
+            work.copy_(H)
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            _abi.check(getattr(lib, name)(work.data_ptr(), n, n, info.data_ptr(), None), name)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        assert int(info.item()) == 0
+        ms = float(np.median(ts[1:]))
+        tf = out["flop"] / (ms * 1e-3) / 1e12
+        out[key] = {"ms": ms, "achieved": tf, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
+                    "frac": tf / FP64_TENSOR_PEAK_TFLOPS, "entry_point": name}
+    del H, work, flush
+    torch.cuda.empty_cache()
+    return out
+
+
+# --------------------------------------------------------------------------------------------------- main
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    D = Dist()
+    rows_mode = D.world > 1 and args.shard in ("auto", "rows")
+    prob, m = lp_workload(args)
+    n = args.n
+
+    r = lp_section(D, args, prob, m, rows_mode, args.steps, args.warmup, e2e=not args.no_e2e)
+    ms, newton = r["ms"], r["newton"]
+    if D.world > 1 and not rows_mode:
+        newton = D.sum(newton)  # independent instances: the work adds up
+    e2e_newton = r.get("e2e_newton", 0.0)
+    if D.world > 1 and not rows_mode and e2e_newton:
+        e2e_newton = D.sum(e2e_newton)
+    hess_ms = float(np.mean(r["hess"])) if r["hess"] else None
+    flops = float(r["m_local"]) * n * (n + 1)  # rows resident on this rank (all m rows unless row-sharded)
     achieved = flops / (hess_ms * 1e-3) / 1e12 if hess_ms else None
+    potrf_ms = float(np.mean(r["potrf"])) if r["potrf"] else None
+    hform_ms = D.max(float(np.mean(r["hform"]))) if (rows_mode and r["hform"]) else None
+    cfg = workload_config(n, m)
+    cfg["per_rank"] = ("single GPU" if D.world == 1 else
+                       "ONE problem, constraint rows sharded over the GPUs; partial Hessian exchanged tile by tile over "
+                       "peer memory (NCCL all-reduce fallback), replicated factorisation" if rows_mode else
+                       "one copy of the instance per GPU (independent solves), no collective")
     line = {
-        "metric": "newton_steps_per_s", "value": value, "unit": "Newton steps/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "strong" if rows_mode else "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": (f"SOCP n={n}, {args.cones} cones of 64 rows, P=I, warm start, test_SOCP settings "
-                                "(BASELINE configs[3]); one step = one SOCPSolver.solve()" if socp else
-                                f"dense LP n={n} m={m} box+-3, warm start (BASELINE configs[1]); one step = one "
-                                "LPSolver.solve()"), "l2": "inputs (%.2f GB) larger than L2" % (8e-9 * m * n),
-                   "per_rank": ("ONE problem, constraint rows / whole cones sharded over the GPUs, NCCL all-reduce of "
-                                "the partial Hessian" if rows_mode else "one copy of the instance per GPU (independent solves), no collective")
-                   if world > 1 else "single GPU"},
+        "metric": "newton_steps_per_s", "value": newton / (ms * 1e-3), "unit": "Newton steps/s", "n_gpus": D.world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if rows_mode else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg, "step": "one complete LPSolver.solve() (all centering steps of the barrier method)",
         "time_to_solve_s": ms * 1e-3 / args.steps,
-        "newton_steps_per_solve": newton / args.steps / (1 if rows_mode else world),
-        "objective": value_ref, "gpu_launches": int(launches), "clocks": clk.summary(),
+        "newton_steps_per_solve": newton / args.steps / (1 if (rows_mode or D.world == 1) else D.world),
+        "objective": r["value_obj"], "gpu_launches": int(r["launches"]), "clocks": r["clocks"],
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
                      "frac": achieved / FP64_TENSOR_PEAK_TFLOPS if achieved else None,
-                     "traffic": hessian_dram_traffic(n, m), "algorithmic_bytes": 8.0 * (m * n + n * (n + 1) / 2),
-                     "kernel": "gemm_tn_persistent_kernel<true> (Hessian C'diag(w)C / W'diag(w)W, upper tiles, "
-                               "stream-K remainder)",
-                     "flop_per_launch": flops, "ms_per_launch": hess_ms, "launches_timed": len(hess),
-                     "peak_source": "FP64 DMMA issue-rate microbenchmark on this pool (tools/fp64_peak.cu, "
-                                    "profiles/fp64_peak_r01.json); MEASURED_PEAKS.json has no FP64 entry"},
+                     "traffic": hessian_dram_traffic(n, m),
+                     "traffic_source": "profiles/syrk_hessian_ncu_r01d.csv: dram__bytes_read.sum + dram__bytes_write.sum "
+                                       "of one `ncu --set full` capture of this kernel at this shape (not re-measured in "
+                                       "this run; ncu cannot run inside a timed bench)",
+                     "algorithmic_bytes": 8.0 * (m * n + n * (n + 1) / 2),
+                     "kernel": "gemm_tn_persistent_kernel<true> (Hessian C'diag(w)C, upper tiles, stream-K remainder)",
+                     "flop_per_launch": flops, "ms_per_launch": hess_ms, "launches_timed": len(r["hess"]),
+                     "peak_source": PEAK_SOURCE},
     }
-    if rows_mode and hform:
-        peer = getattr(solver_ns, "peer", None) is not None
-        line["hessian_formation"] = {"ms": float(np.mean(hform)), "exchange": "peer-memory scatter / reduce / "
-                                     "broadcast kernels (no NCCL)" if peer else "NCCL all-reduce of the n x ld buffer",
-                                     "what": "local partial C_r' diag(w) C_r + exchange + diagonal terms, per Newton "
-                                     "step (rank 0)",
-                                     "allreduce_bytes_per_newton_step": comm_bytes / max(newton + args.warmup *
-                                                                                        newton / args.steps, 1)}
-    if e2e_ms:
-        line["e2e"] = {"value": e2e_newton / (e2e_ms * 1e-3), "unit": "Newton steps/s", "h2d_bytes_per_step": int(h2d),
-                       "d2h_bytes_per_step": int(d2h), "time_to_solve_s": e2e_ms * 1e-3 / args.steps}
-    if lasso is not None:
-        K = args.lasso_k
-        line["lasso"] = {
-            "metric": "lasso_solves_per_s", "workload": f"LassoSolver ADMM, A 2048x512 + bias, K={K} problems, eps 1e-6 "
-            "(BASELINE configs[4]); strided column split across ranks, no collective",
-            "value": K / (lasso["ms"] * 1e-3), "e2e_value": K / (lasso["ms_e2e"] * 1e-3), "unit": "solves/s",
-            "admm_iterations": lasso["iters"], "ms_per_iteration": lasso["ms"] / lasso["iters"],
-            "gpu_launches": lasso["launches"], "h2d_bytes": lasso["h2d"], "d2h_bytes": lasso["d2h"],
-            "roofline": {"bound": "tensor", "achieved": lasso["flop"] / (lasso["ms"] * 1e-3) / 1e12 / world,
-                         "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s per GPU",
-                         "frac": lasso["flop"] / (lasso["ms"] * 1e-3) / 1e12 / world / FP64_TENSOR_PEAK_TFLOPS,
-                         "note": "2 n^2 K flop per ADMM iteration over the whole solve() incl. stop checks"}}
-    if args.factorisation and world == 1:
-        line["factorisation"] = factorisation_section(n)
-    if not args.no_cpu_baseline and world == 1:
+    if potrf_ms:
+        tf = n ** 3 / 3.0 / (potrf_ms * 1e-3) / 1e12
+        line["potrf_in_solve"] = {"ms": potrf_ms, "achieved": tf, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
+                                  "frac": tf / FP64_TENSOR_PEAK_TFLOPS, "launches_timed": len(r["potrf"]),
+                                  "what": "ipm_potrf_upper_f64 (pipelined tile-DAG kernel at this size), CUDA events around "
+                                          "every call inside the timed solves; n^3/3 flop"}
+    if hform_ms:
+        line["hessian_formation"] = {
+            "ms": hform_ms, "exchange": "peer-memory scatter / reduce / broadcast kernels (no NCCL)" if r["peer"] else
+            "NCCL all-reduce of the n x ld buffer", "what": "local partial C_r' diag(w) C_r + exchange + diagonal terms, per "
+            "Newton step (max over ranks)", "partial_syrk_ms": hess_ms,
+            "allreduce_bytes_per_newton_step": r["comm_bytes"] / max(newton * (args.steps + args.warmup) / args.steps, 1)}
+    if "e2e_ms" in r:
+        line["e2e"] = {"value": e2e_newton / (r["e2e_ms"] * 1e-3), "unit": "Newton steps/s",
+                       "h2d_bytes_per_step": int(r["h2d"]), "d2h_bytes_per_step": int(r["d2h"]),
+                       "time_to_solve_s": r["e2e_ms"] * 1e-3 / args.steps}
+
+    def section(name, fn):
+        if not wants(args, name):
+            return
+        try:
+            out = fn()
+        except Exception as e:  # a failing extra section must not take the headline line down with it
+            import traceback
+
+            traceback.print_exc(file=sys.stderr)
+            out = {"error": f"{type(e).__name__}: {e}"}
+        if out is not None:
+            line[name] = out
+
+    if D.world == 1:
+        section("cold", lambda: cold_section(D, args, prob))
+        section("qp", lambda: qp_section(D, args))
+    section("socp", lambda: socp_section(D, args, rows_mode))
+    if args.lasso_k > 0:
+        section("lasso", lambda: lasso_section(D, args))
+    if D.world > 1 and rows_mode:
+        def replicas():
+            rr = lp_section(D, args, prob, m, False, 1, 1, e2e=False, profile=False)
+            tot = D.sum(rr["newton"])
+            return {"what": "one independent copy of the LP per GPU, no collective (weak scaling)",
+                    "value": tot / (rr["ms"] * 1e-3), "unit": "Newton steps/s", "time_to_solve_s": rr["ms"] * 1e-3}
+        section("replicas", replicas)
+    if D.world == 1:
+        section("factorisation", lambda: factorisation_section(n))
+    if D.rank == 0 and not args.no_cpu_baseline and D.world == 1:
         use_all_host_threads()
-        k, dt = cpu_sample(prob, args.cpu_newton_steps)
-        line["cpu_baseline"] = {"value": k / dt, "unit": "Newton steps/s", "cores": blas_threads(), "kind": "port",
-                                "sample": f"{k} full-size Newton iterations (first centering step) of the oracle, "
+        k, dt, kind = cpu_sample(prob, args.cpu_newton_steps)
+        line["cpu_baseline"] = {"value": k / dt, "unit": "Newton steps/s", "cores": blas_threads(), "kind": kind,
+                                "sample": f"{k} full-size Newton iterations (first centering step) of "
+                                          f"{'the reference LPSolver (oracle/_ref)' if kind == 'reference' else 'the oracle port'}, "
                                           f"{dt:.1f} s; NumPy BLAS: {blas_info()}"}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        if "lasso" in line and "error" not in line["lasso"]:
+            try:
+                v, dt, its, kind = cpu_lasso_sample()
+                line["lasso"]["cpu_baseline"] = {"value": v, "unit": "solves/s", "cores": blas_threads(), "kind": kind,
+                                                 "sample": f"128 of the 4096 problems (every 32nd column) solved to the stop "
+                                                           f"test by the reference LassoSolver: {its} ADMM iterations, {dt:.1f} s"}
+            except Exception as e:
+                line["lasso"]["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
+    if D.rank == 0:
+        print(json.dumps(line))
+    D.close()
 
 
 if __name__ == "__main__":

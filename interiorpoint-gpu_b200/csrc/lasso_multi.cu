@@ -18,11 +18,14 @@
 //   * no kernel boundary and no launch gap between iterations, no global barrier: a CTA that finishes early moves on
 //     to the next iteration of a column group that is complete;
 //   * units flow continuously over all 148 SMs instead of 128 tiles per launch on 148 SMs (0.86 fill);
-//   * two CTAs per SM (128 x 64 tile, 32 accumulators per thread, 2 x 48 KB ring): while one CTA sits in its L2-bound
-//     epilogue the other one's warps keep the DMMA pipe busy;
+//   * (measured and dropped: a 128 x 64 tile with two CTAs per SM so that one CTA's L2-bound epilogue overlaps the other's
+//     DMMAs -- only two 48 KB ring stages fit twice, the TMA latency was exposed at every k-tile and the kernel ran at
+//     107 us per iteration against 91 us for one launch per iteration; profiles/lasso_multi_r02a.jsonl);
 //   * alpha is neither read nor written except in the last two iterations of a launch (the stop test needs alpha and
 //     alpha+; in between alpha = u - z is implicit): 4 instead of 6 state arrays per iteration through L2.
-// Small batches (a per-GPU shard of K = 512) use a 64 x 32 tile so that there are still ~128 units per iteration.
+// Small batches (the per-GPU shards of a 2/4/8-way split, K <= 2048) use a 64 x 32 tile so that there are still >= 128
+// units per iteration; with fewer units than SMs the grid is one CTA per SM, so two units never share an SM while
+// others idle.
 //
 // Stop test on the device: the last iteration of a launch leaves four partial sums of squares per warp in a slot that
 // depends only on (g, r, warp); lasso_batch_end_kernel adds them in slot order (deterministic whatever CTA ran the
@@ -39,11 +42,12 @@ using namespace gemm;  // mbarrier / TMA / DMMA primitives, BK, CHUNK_BYTES
 constexpr int LM_THREADS = 256;
 constexpr int LM_TAIL_MAX = 8;  // rows beyond the last full row tile handled as dot products (n = 513: the one extra row)
 
-struct ShapeBig {  // 128 x 64 tile, warps 2 x 4, warp tile 64 x 16
-  static constexpr int WM = 2, MI = 8, NI = 2, NSTAGES = 2;
+// MINB = CTAs per SM the kernel is compiled for (register budget) and launched with at most.
+struct ShapeBig {  // 128 x 128 tile, warps 2 x 4, warp tile 64 x 32 (the shape of gemm_tn_core.cuh), 3 x 64 KB ring
+  static constexpr int WM = 2, MI = 8, NI = 4, NSTAGES = 3, MINB = 1;
 };
-struct ShapeSmall {  // 64 x 32 tile, warps 4 x 2, warp tile 16 x 16
-  static constexpr int WM = 4, MI = 2, NI = 2, NSTAGES = 4;
+struct ShapeSmall {  // 64 x 32 tile, warps 4 x 2, warp tile 16 x 16, 4 x 24 KB ring
+  static constexpr int WM = 4, MI = 2, NI = 2, NSTAGES = 4, MINB = 2;
 };
 template <class S>
 struct Geo {
@@ -152,7 +156,7 @@ __device__ __forceinline__ void frags(double (&a)[S::MI], double (&b)[S::NI], ui
 }
 
 template <class S>
-__global__ void __launch_bounds__(LM_THREADS, 2)
+__global__ void __launch_bounds__(LM_THREADS, S::MINB)
 lasso_admm_multi_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmZ0,
                         const __grid_constant__ CUtensorMap tmZ1, const Params p) {
   using G = Geo<S>;
@@ -186,12 +190,14 @@ lasso_admm_multi_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint32_t it = 0;   // k-tiles consumed through the ring (all warps)
   uint32_t pit = 0;  // k-tiles issued into the ring (all warps keep the same count)
 
-  while (true) {
-    __syncthreads();  // everybody is done with s_unit / s_tail of the previous unit
+  if (tid == 0) s_unit = (int)atomicAdd(sched, 1u);
+  __syncthreads();
+  int unit = s_unit;
+  while (unit < total) {
+    __syncthreads();  // everybody has read s_unit and is done with the ring / tail scratch of the previous unit
+    // claim the NEXT unit now: the atomic's round trip hides under this unit.  (Still deadlock-free: a unit held in
+    // reserve belongs to a CTA whose current unit is smaller, so the smallest unfinished unit is always running.)
     if (tid == 0) s_unit = (int)atomicAdd(sched, 1u);
-    __syncthreads();
-    const int unit = s_unit;
-    if (unit >= total) break;
     const int li = unit / per_iter;            // iteration inside this launch
     const int rem = unit - li * per_iter;
     const int g = rem / p.U, r = rem - g * p.U;
@@ -410,6 +416,7 @@ lasso_admm_multi_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     asm volatile("fence.proxy.async;" ::: "memory");
     __syncthreads();
     if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.done + g) : "memory");
+    unit = s_unit;  // written before the barriers above
   }
 }
 
@@ -456,11 +463,11 @@ struct Layout {
 
 static Layout layout_for(int n, int K, int sms) {
   Layout L;
-  // big tiles while they still fill most of the machine; otherwise the 64 x 32 tile (4x as many units)
-  const int rt_big = ceil_div(n_main_of(n, 128), 128), cg_big = ceil_div(K, 64);
-  L.small = (long long)rt_big * cg_big * 5 < (long long)sms * 4;
+  // 128 x 128 tiles while they still fill most of the machine; otherwise the 64 x 32 tile (16x as many units)
+  const int rt_big = ceil_div(n_main_of(n, 128), 128), cg_big = ceil_div(K, 128);
+  L.small = (long long)rt_big * cg_big * 20 < (long long)sms * 17;
   L.TM = L.small ? 64 : 128;
-  L.TN = L.small ? 32 : 64;
+  L.TN = L.small ? 32 : 128;
   L.n_main = n_main_of(n, L.TM);
   L.RT = ceil_div(L.n_main, L.TM);
   L.CG = ceil_div(K, L.TN);
@@ -485,6 +492,28 @@ static int lm_num_sms(int* out) {
   if (dev < 0 || dev >= kMaxDevices) return IPM_ERR_ARG;
   if (!g_lm_sms[dev]) IPM_CUDA_CHECK(cudaDeviceGetAttribute(&g_lm_sms[dev], cudaDevAttrMultiProcessorCount, dev));
   *out = g_lm_sms[dev];
+  return IPM_OK;
+}
+
+template <class S>
+static int launch_multi(const CUtensorMap& tmQ, const CUtensorMap& tmZ0, const CUtensorMap& tmZ1, const lasso::Params& p,
+                        int sms, long long per_iter, long long units, cudaStream_t st) {
+  auto kern = lasso::lasso_admm_multi_kernel<S>;
+  static bool attr_set[kMaxDevices];
+  static int per_sm[kMaxDevices];
+  IPM_CUDA_CHECK(ensure_dynamic_smem(kern, lasso::Geo<S>::SMEM, attr_set));
+  int dev = 0;
+  IPM_CUDA_CHECK(cudaGetDevice(&dev));
+  if (!per_sm[dev])
+    IPM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[dev], kern, lasso::LM_THREADS,
+                                                                 lasso::Geo<S>::SMEM));
+  if (per_sm[dev] < 1) return IPM_ERR_ARG;
+  int ctas_per_sm = per_sm[dev] < S::MINB ? per_sm[dev] : S::MINB;
+  if (per_iter <= sms) ctas_per_sm = 1;
+  long long grid = (long long)sms * ctas_per_sm;
+  if (grid > units) grid = units;
+  IPM_CUDA_CHECK(launch_cooperative(kern, dim3((unsigned)grid), dim3(lasso::LM_THREADS), lasso::Geo<S>::SMEM, st, tmQ,
+                                    tmZ0, tmZ1, p));
   return IPM_OK;
 }
 
@@ -539,39 +568,15 @@ extern "C" int ipm_lasso_admm_steps_f64(const double* Qt, int ldq, int n, int K,
   p.partials = (double*)(wsb + L.off_partials);
   p.fault = ipm_internal_fault_word();
   const long long units = (long long)n_iters * L.CG * L.U;
+  // grid: every CTA resident (cooperative launch).  One CTA per SM unless an iteration has more units than SMs and the
+  // shape allows two: with fewer units than SMs a second CTA per SM would let two units share an SM while others idle.
+  const long long per_iter = (long long)L.CG * L.U;
   if (L.small) {
-    using S = lasso::ShapeSmall;
-    auto kern = lasso::lasso_admm_multi_kernel<S>;
-    static bool attr_set[kMaxDevices];
-    static int per_sm[kMaxDevices];
-    IPM_CUDA_CHECK(ensure_dynamic_smem(kern, lasso::Geo<S>::SMEM, attr_set));
-    int dev = 0;
-    IPM_CUDA_CHECK(cudaGetDevice(&dev));
-    if (!per_sm[dev])
-      IPM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[dev], kern, lasso::LM_THREADS,
-                                                                   lasso::Geo<S>::SMEM));
-    if (per_sm[dev] < 1) return IPM_ERR_ARG;
-    long long grid = (long long)sms * per_sm[dev];
-    if (grid > units) grid = units;
-    IPM_CUDA_CHECK(launch_cooperative(kern, dim3((unsigned)grid), dim3(lasso::LM_THREADS), lasso::Geo<S>::SMEM, st, tmQ,
-                                      tmZ0, tmZ1, p));
+    rc = launch_multi<lasso::ShapeSmall>(tmQ, tmZ0, tmZ1, p, sms, per_iter, units, st);
   } else {
-    using S = lasso::ShapeBig;
-    auto kern = lasso::lasso_admm_multi_kernel<S>;
-    static bool attr_set[kMaxDevices];
-    static int per_sm[kMaxDevices];
-    IPM_CUDA_CHECK(ensure_dynamic_smem(kern, lasso::Geo<S>::SMEM, attr_set));
-    int dev = 0;
-    IPM_CUDA_CHECK(cudaGetDevice(&dev));
-    if (!per_sm[dev])
-      IPM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[dev], kern, lasso::LM_THREADS,
-                                                                   lasso::Geo<S>::SMEM));
-    if (per_sm[dev] < 1) return IPM_ERR_ARG;
-    long long grid = (long long)sms * per_sm[dev];
-    if (grid > units) grid = units;
-    IPM_CUDA_CHECK(launch_cooperative(kern, dim3((unsigned)grid), dim3(lasso::LM_THREADS), lasso::Geo<S>::SMEM, st, tmQ,
-                                      tmZ0, tmZ1, p));
+    rc = launch_multi<lasso::ShapeBig>(tmQ, tmZ0, tmZ1, p, sms, per_iter, units, st);
   }
+  if (rc) return rc;
   IPM_LAUNCH_CHECK();
   lasso::lasso_batch_end_kernel<<<1, 256, 0, st>>>(p.state, p.partials, L.CG * L.U * 8, n_iters, want_norms, stop_mult,
                                                    eps_rel, rho, (double*)(wsb + L.off_norms));

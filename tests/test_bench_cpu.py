@@ -18,7 +18,11 @@ def test_reference_arm_line_and_threads():
     assert line["steps"] == 1 and line["warmup"] == 1 and line["value"] > 0 and line["dtype"] == "f64"
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["value"] == line["value"]
+    # the reference's own modules when oracle/build_ref.py has been run (this container, and the GPU box via the
+    # snapshot), else the oracle port
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "LPSolver.py"))
+    assert cb["kind"] == ("reference" if have_ref else "port") and cb["value"] == line["value"]
+    assert line["config"]["workload"].startswith("dense LP n=96")
     assert cb["cores"] == len(os.sched_getaffinity(0))
 
 

@@ -407,10 +407,11 @@ def _admm_numpy(Qt, bA, eta, rho, alpha, u, add_bias, positive, iters):
 
 
 @pytest.mark.parametrize("n,K,add_bias,positive", [(513, 300, 1, 0), (101, 30, 1, 0), (257, 3900, 1, 1), (64, 17, 0, 0),
-                                                   (200, 1000, 0, 0)])
+                                                   (200, 1000, 0, 0), (1025, 2100, 1, 0)])
 def test_lasso_admm_steps_multi_iteration(n, K, add_bias, positive):
     """ipm_lasso_admm_steps_f64 (persistent multi-iteration kernel, csrc/lasso_multi.cu) against NumPy and against the
-    one-launch-per-iteration kernel: both tile shapes (257 x 3900 takes the 128 x 64 tile, the others 64 x 32), ragged
+    one-launch-per-iteration kernel: both tile shapes (1025 x 2100 takes the 128 x 128 tile, the others 64 x 32 -- 257 x 3900
+    with two CTAs per SM, the small ones with one), ragged
     rows / columns / contraction tails, tail-row units (513 = 4 * 128 + 1, 257), two launches in a row (odd iteration
     parity), and the device-side stop test."""
     rs = np.random.RandomState(n + K)
