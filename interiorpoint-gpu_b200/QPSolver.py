@@ -57,8 +57,8 @@ class QPSolver(BarrierSolverBase):
         self.sharded = bool(shard_rows) and tdist.is_available() and tdist.is_initialized() and \
             tdist.get_world_size() > 1
         if self.sharded:
-            if C is None or A is not None:
-                raise NotImplementedError("shard_rows needs inequality rows and no equality constraints")
+            if C is None:
+                raise NotImplementedError("shard_rows needs inequality rows to shard")
             lo, hi = row_range(C.shape[0], tdist.get_rank(), tdist.get_world_size())
             C_loc, d_loc = C[lo:hi], d[lo:hi]
             if tdist.get_rank() != 0:

@@ -121,8 +121,6 @@ class SOCPSolver(BarrierSolverBase):
         self.sharded = bool(shard_rows) and tdist.is_available() and tdist.is_initialized() and \
             tdist.get_world_size() > 1
         if self.sharded:
-            if F is not None:
-                raise NotImplementedError("shard_rows is implemented for SOCPs without equality constraints")
             x_all = torch.as_tensor(self.x).to(device=self.device, dtype=F64).clone()
             tdist.broadcast(x_all, src=0)  # default_x0 may be random (SOCPSolver.py:166): one x0 for all ranks
             self.x = x_all.cpu().numpy()

@@ -35,8 +35,9 @@ class _RowSharded:
     collectives that make their outputs global."""
 
     def _init_sharding(self, group):
-        if self.equality:
-            raise NotImplementedError("row sharding is implemented for the feasible-start method (no A x = b)")
+        # Equality constraints (infeasible-start method, NewtonSolverInfeasibleStart.py:386-511): the equality rows A, the
+        # dual iterate and the block elimination (TRSM of A', Schur complement, its factorisation) are replicated; only the
+        # barrier pieces -- slacks, gradient, Hessian, feasibility back-off -- are sharded, through the same overrides.
         if self.update_slacks_every > 0 or self.diagonal:
             raise NotImplementedError("row sharding supports the default dense Cholesky path only")
         self.group = group
@@ -130,7 +131,24 @@ class _RowSharded:
         dist.all_reduce(self.ws.kmax, op=dist.ReduceOp.MAX, group=self.group)
 
     def slacks_at(self, x):
-        raise NotImplementedError("dual variables are not gathered in row-sharded mode")
+        """All slacks in the reference's layout [inequality rows / cones of rank 0, 1, ... | bound rows] gathered on every
+        rank (``get_dual_variables``: lam = 1 / (t slacks), LPSolver.py:641-646)."""
+        d, ws = self.d, self.ws
+        super()._eval(x, ws.cur)  # the engine's own evaluation: this rank's rows only, no reduction
+        n_rows = getattr(d, "M", None) if d.m == 0 and hasattr(d, "M") else d.m
+        sizes = torch.tensor([n_rows, d.n_slacks - n_rows], dtype=torch.int64, device=d.device)
+        allsz = [torch.zeros_like(sizes) for _ in range(self.world)]
+        dist.all_gather(allsz, sizes, group=self.group)
+        allsz = [t.tolist() for t in allsz]
+        width = max(max(a) for a in allsz)
+        pad = torch.zeros(2, max(width, 1), dtype=F64, device=d.device)
+        pad[0, :n_rows] = ws.slacks[:n_rows]
+        pad[1, :d.n_slacks - n_rows] = ws.slacks[n_rows:d.n_slacks]
+        parts = [torch.zeros_like(pad) for _ in range(self.world)]
+        dist.all_gather(parts, pad, group=self.group)
+        rows = [parts[r][0, :allsz[r][0]] for r in range(self.world)]
+        bounds = [parts[r][1, :allsz[r][1]] for r in range(self.world)]
+        return torch.cat(rows + bounds)
 
 
 class ShardedLinearNewton(_RowSharded, LinearNewton):
