@@ -123,6 +123,20 @@ int ipm_potrf_upper_f64(double* H, int ld, int n, int* info_dev, void* stream);
  * Used by ipm_potrf_upper_f64 itself for n >= 6144 (IPM_POTRF_DAG=1: every admissible size, =0: never); sizes it does not cover
  * (n <= 256, n > 32768) go through the stream-ordered code.  One factorisation at a time per stream. */
 int ipm_potrf_upper_dag_f64(double* H, int ld, int n, int* info_dev, void* stream);
+/* The same factorisation distributed over the R <= 8 GPUs of a node (north_star: "replicated or 2D-block-cyclic
+ * factorisation"): block column j belongs to rank j % R; the owner pushes every finished 32-row step into ALL R copies
+ * of the matrix over NVLink and release-stores the progress counter of every rank, so loads and waits stay local and
+ * every rank ends with the whole factor.  Called by every rank at the same point of its stream.  peer_H / peer_info /
+ * peer_prog: R device pointers each (host arrays) to every rank's matrix copy, info word and progress counters
+ * (ipm_potrf_peer_prog_words() 64-bit words, zeroed once); epoch != 0, new for every call, identical on all ranks;
+ * max_ctas = 0 (one CTA per SM).  n <= 256: IPM_ERR_ARG (factor replicated).  NewtonSolver.py:286,303. */
+int ipm_potrf_peer_prog_words(void);
+int ipm_potrf_upper_peer_f64(void* const* peer_H, int ld, int n, void* const* peer_info, void* const* peer_prog, int me,
+                             int R, unsigned int epoch, int max_ctas, void* stream);
+/* H = U^T U in place AND B <- U^{-T} B (B: n x p) in ONE persistent launch: the right-hand sides are extra block columns
+ * of the tile DAG.  cho_factor(H) + the forward half of cho_solve(L1, A.T) NewtonSolverInfeasibleStart.py:398-426
+ * (the Schur complement is then Y'Y).  Sizes the tile-DAG kernel does not take: potrf followed by trsm. */
+int ipm_potrf_trsm_upper_f64(double* H, int ld, int n, double* B, int ldb, int p, int* info_dev, void* stream);
 /* b <- U^{-T} b (trans = 1) or U^{-1} b (trans = 0), in place; ws is unused (kept for ABI stability, may be NULL).
  * One persistent launch; not re-entrant per device (two concurrent solves on different streams of one device would
  * share the block flags).  cho_solve / solve_triangular NewtonSolver.py:287-313. */

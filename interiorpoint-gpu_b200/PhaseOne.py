@@ -98,7 +98,7 @@ class PhaseOneSolver:
             ns._eval(z, ws.cur)
             ns._gradient(t, None, ws.cur, ws.g, want_border=True)
             ns._hessian(t)
-            L("ipm_potrf_upper_f64", ws.H.data_ptr(), ws.ldh, ns.nz, ws.info.data_ptr())
+            ns._factor()
             L("ipm_lincomb3_f64", ns.nz, -1.0, ws.g.data_ptr(), 0.0, None, 0.0, None, ws.dz.data_ptr())
             ns._chol_solve_vec(ws.dz)
             pairs = ns._objective_pairs(z, None) + [(ws.g, z, ns.nz), (ws.g, ws.dz, ns.nz)]

@@ -41,6 +41,9 @@ SIGNATURES = {
     "ipm_axpy_dev_f64": (_i, [_i, _dp, _dp, _dp, _dp]),
     "ipm_potrf_upper_f64": (_i, [_dp, _i, _i, _dp, _dp]),
     "ipm_potrf_upper_dag_f64": (_i, [_dp, _i, _i, _dp, _dp]),
+    "ipm_potrf_peer_prog_words": (_i, []),
+    "ipm_potrf_upper_peer_f64": (_i, [C.POINTER(_dp), _i, _i, C.POINTER(_dp), C.POINTER(_dp), _i, _i, C.c_uint, _i, _dp]),
+    "ipm_potrf_trsm_upper_f64": (_i, [_dp, _i, _i, _dp, _i, _i, _dp, _dp]),
     "ipm_trsm_upper_t_f64": (_i, [_dp, _i, _i, _dp, _i, _i, _dp]),
     "ipm_trsv_upper_f64": (_i, [_dp, _i, _i, _dp, _i, _dp, _dp]),
     "ipm_lin_barrier_ws_doubles": (_ll, []),

@@ -697,26 +697,63 @@ namespace dag {
 // overlap: the solve consumes U(i, i) one 32-row step behind the factorisation, and the contraction consumes
 // U(i, i+1) one k-tile (32 rows) behind the solve.  Chain per block row: potf2 + one solve step + one k-tile + three
 // flag hops, instead of potf2 + whole solve + four k-tiles.
-//   prog[c]          (c < MAX_T)  : 32-row groups of the OFF-diagonal tiles of block column c that are final
-//                                   (4 per tile, published top-down: tile (k, c) step g -> 4 k + g + 1)
-//   prog[MAX_T + c]               : 32-row steps of the diagonal tile (c, c) that are final (0 .. 4)
+//   prog[c]          (c < MAX_COLS) : 32-row groups of the OFF-diagonal tiles of block column c that are final
+//                                     (4 per tile, published top-down: tile (k, c) step g -> 4 k + g + 1)
+//   prog[MAX_COLS + c]  (c < MAX_T) : 32-row steps of the diagonal tile (c, c) that are final (0 .. 4)
+//
+// Fused triangular solve (ipm_potrf_trsm_upper_f64): the right-hand sides B (n x p) of  Y = U^{-T} B  are simply TB =
+// ceil(p / 128) more block columns of the same DAG -- U(i, j) = U(i, i)^{-T} (A(i, j) - sum_{k<i} U(k, i)^T U(k, j)) is
+// the forward substitution when column j belongs to B -- so block row i has the tasks (i, i) .. (i, T - 1) of H followed by
+// (i, T) .. (i, T + TB - 1) of B, and ONE launch factors H and solves for all right-hand sides (the stream-ordered TRSM
+// took ~150 launches per solve).  The extra columns also keep every SM busy through the last block rows of H.
 // The tile solve handles all 128 columns at once (B tile in shared memory, U(i, i) streamed through a 32-row slab),
 // and B = A - acc goes from the accumulators straight to shared memory.
 // ------------------------------------------------------------------------------------------------
+constexpr int MAX_COLS = 2 * MAX_T;  // block columns of H plus block columns of the right-hand sides
 constexpr int TILE_LD = NB + 4;  // 132: the potf2 / solve tile in shared memory
 constexpr int SLAB_ROWS = 32;
 constexpr int SCRATCH2_BYTES = STAGES * STAGE_BYTES;  // ring (192 KiB) >= tile (132 KiB) + slab (33 KiB)
 static_assert(SCRATCH2_BYTES >= (NB + SLAB_ROWS) * TILE_LD * 8, "tile + slab alias the TMA ring");
 constexpr int SMEM2 = 1024 + SCRATCH2_BYTES + 2 * STAGES * 8;
 
+// Distributed factorisation (ipm_potrf_upper_peer_f64): R GPUs, block column j of H belongs to rank j % R, which runs the
+// tasks (i, j) of its columns on its own CTAs.  Every rank keeps the WHOLE matrix (it needs all of U for the triangular
+// solves that follow) in peer-mapped memory.  PUSH model: the owner of a finished 32-row step stores it into all R copies
+// and then release-stores the column's progress counter of every rank (system scope), so every TMA load and every
+// dependency wait stays local and the consumer side of the kernel is the single-GPU one.  R == 1: plain pointers.
+constexpr int kMaxRanks = 8;
+struct Peers {
+  double* H[kMaxRanks];                 // the matrix on every rank (H[me] = local)
+  unsigned long long* prog[kMaxRanks];  // the progress counters on every rank
+  int* info[kMaxRanks];
+  int R, me;
+};
+
+__device__ __forceinline__ int column_progress_sys(const unsigned long long* p, unsigned epoch) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return (unsigned)(v >> 32) == epoch ? (int)(unsigned)v : 0;
+}
+__device__ __forceinline__ void set_info(const Peers& pr, int* info, int value) {
+  if (pr.R == 1) {
+    atomicCAS(info, 0, value);
+  } else {
+    for (int r = 0; r < pr.R; ++r) atomicCAS_system(pr.info[r], 0, value);
+  }
+}
+
 // Spins until prog[idx] >= need (bounded by the watchdog, common.cuh: spin_wait; on a fault info becomes -1 and the wait
 // reports success so that the kernel drains on garbage instead of hanging).
 __device__ __forceinline__ int wait_progress(unsigned long long* prog, int idx, unsigned epoch, int need, int* info,
-                                             unsigned int* fault) {
+                                             unsigned int* fault, bool sys = false) {
   int r = 0;
-  if (!spin_wait([&] { return (r = column_progress(prog + idx, epoch)) >= need; }, fault, IPM_FAULT_POTRF_DAG)) {
+  const bool ok = sys ? spin_wait([&] { return (r = column_progress_sys(prog + idx, epoch)) >= need; }, fault,
+                                  IPM_FAULT_POTRF_PEER)
+                      : spin_wait([&] { return (r = column_progress(prog + idx, epoch)) >= need; }, fault,
+                                  IPM_FAULT_POTRF_DAG);
+  if (!ok) {
     atomicCAS(info, 0, -1);
-    r = 4 * MAX_T;
+    r = 4 * MAX_COLS;
   }
   return r;
 }
@@ -724,14 +761,27 @@ __device__ __forceinline__ void publish(unsigned long long* p, unsigned epoch, i
   const unsigned long long v = ((unsigned long long)epoch << 32) | (unsigned)count;
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// counter `idx` of every rank (the caller has fenced at system scope when R > 1)
+__device__ __forceinline__ void publish_all(const Peers& pr, unsigned long long* prog, int idx, unsigned epoch, int count) {
+  if (pr.R == 1) {
+    publish(prog + idx, epoch, count);
+    return;
+  }
+  const unsigned long long v = ((unsigned long long)epoch << 32) | (unsigned)count;
+  for (int r = 0; r < pr.R; ++r)
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pr.prog[r] + idx), "l"(v) : "memory");
+}
 
 struct Producer2 {
   const CUtensorMap* tm;
+  const CUtensorMap* tmB;  // right-hand sides (block columns >= T), or null
+  int T;
   Ring ring;
   unsigned long long* prog;
   int* info;
   unsigned int* fault;
   unsigned epoch;
+  bool sys;  // counters are written by other GPUs: system-scope acquire
   int ti, tj, kt, k1, ready_i, ready_j;  // ready_*: 32-row groups of columns ti / tj known to be final
   uint32_t it;
   __device__ __forceinline__ void begin(int i, int j) {
@@ -742,9 +792,9 @@ struct Producer2 {
     if (lane == 0) {
       const int need = kt + 1;  // BK == 32 rows == one group
       if (ready_i < need || ready_j < need) {
-        if (ready_i < need) ready_i = wait_progress(prog, ti, epoch, need, info, fault);
+        if (ready_i < need) ready_i = wait_progress(prog, ti, epoch, need, info, fault, sys);
         if (tj == ti) ready_j = ready_i;
-        if (ready_j < need) ready_j = wait_progress(prog, tj, epoch, need, info, fault);
+        if (ready_j < need) ready_j = wait_progress(prog, tj, epoch, need, info, fault, sys);
         asm volatile("fence.proxy.async;" ::: "memory");  // the rows were written through the generic proxy
       }
       const uint32_t s = it % STAGES;
@@ -753,7 +803,11 @@ struct Producer2 {
       mbar_expect_tx(full, 2 * CHUNK_BYTES);
       const uint32_t dstA = ring.tiles0 + s * STAGE_BYTES + wp * CHUNK_BYTES;
       tma_load_2d(dstA, tm, ti * BM + wp * 16, kt * BK, full);
-      tma_load_2d(dstA + OPERAND_BYTES, tm, tj * BN + wp * 16, kt * BK, full);
+      if (tj < T) {
+        tma_load_2d(dstA + OPERAND_BYTES, tm, tj * BN + wp * 16, kt * BK, full);
+      } else {
+        tma_load_2d(dstA + OPERAND_BYTES, tmB, (tj - T) * BN + wp * 16, kt * BK, full);
+      }
     }
     __syncwarp();
     ++it;
@@ -765,10 +819,10 @@ static_assert(BK == SLAB_ROWS, "one k-tile == one 32-row group");
 // Tile (row0.., col0..) of B = A - acc from the accumulators into shared memory S (ld TILE_LD): entries outside the
 // matrix are 0 (1 on the diagonal of a diagonal tile: identity padding), the strict lower triangle of a diagonal tile 0.
 __device__ __forceinline__ void stage_tile(double* __restrict__ S, const double* __restrict__ H, long long ld, int n,
-                                           int row0, int col0, bool diag, const double (&acc)[8][4][2],
+                                           int ncols, int row0, int col0, bool diag, const double (&acc)[8][4][2],
                                            const LaneMap& lm) {
   const int lr0 = lm.wm * 64, lc0 = lm.wn * 32;
-  const bool interior = !(ld & 1) && !(((uintptr_t)H) & 15) && (row0 + lr0 + 64 <= n) && (col0 + lc0 + 32 <= n) &&
+  const bool interior = !(ld & 1) && !(((uintptr_t)H) & 15) && (row0 + lr0 + 64 <= n) && (col0 + lc0 + 32 <= ncols) &&
                         (!diag || lc0 >= lr0 + 63);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -781,8 +835,8 @@ __device__ __forceinline__ void stage_tile(double* __restrict__ S, const double*
         const double2 a = __ldcg(reinterpret_cast<const double2*>(H + (long long)row * ld + col));
         v = make_double2(a.x - acc[i][jn][0], a.y - acc[i][jn][1]);
       } else {
-        const bool in0 = row < n && col < n && !(diag && col < row);
-        const bool in1 = row < n && col + 1 < n && !(diag && col + 1 < row);
+        const bool in0 = row < n && col < ncols && !(diag && col < row);
+        const bool in1 = row < n && col + 1 < ncols && !(diag && col + 1 < row);
         v.x = in0 ? __ldcg(H + (long long)row * ld + col) - acc[i][jn][0] : ((diag && lr == lc && row >= n) ? 1.0 : 0.0);
         v.y = in1 ? __ldcg(H + (long long)row * ld + col + 1) - acc[i][jn][1]
                   : ((diag && lr == lc + 1 && row >= n) ? 1.0 : 0.0);
@@ -811,11 +865,24 @@ __device__ __forceinline__ void store_rows(const double* __restrict__ S, double*
   }
 }
 
+// The same rows into every rank's copy of the matrix (R == 1: the local one).
+template <bool UPPER>
+__device__ __forceinline__ void store_rows_all(const Peers& pr, const double* __restrict__ S, double* __restrict__ G,
+                                               long long ld, int r_begin, int nrows, int ncols) {
+  if (pr.R == 1) {
+    store_rows<UPPER>(S, G, ld, r_begin, nrows, ncols);
+    return;
+  }
+  const long long off = G - pr.H[pr.me];
+  for (int r = 0; r < pr.R; ++r) store_rows<UPPER>(S, pr.H[(r + pr.me) % pr.R] + off, ld, r_begin, nrows, ncols);
+}
+
 // Diagonal task: potf2 of the tile in S, publishing every 32-row step (rows final after the pivot block and its row
 // panel) before the trailing update of the step.
-__device__ __forceinline__ void potf2_pipelined(double* __restrict__ S, double* __restrict__ rs, double* __restrict__ G,
-                                                long long ld, int nb, int k0, int* __restrict__ info,
-                                                unsigned long long* diag_prog, unsigned epoch) {
+__device__ __forceinline__ void potf2_pipelined(const Peers& pr, double* __restrict__ S, double* __restrict__ rs,
+                                                double* __restrict__ G, long long ld, int nb, int k0,
+                                                int* __restrict__ info, unsigned long long* prog, int diag_idx,
+                                                unsigned epoch) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll 1
   for (int base = 0; base < nb; base += 32) {
@@ -838,7 +905,7 @@ __device__ __forceinline__ void potf2_pipelined(double* __restrict__ S, double* 
           d[i] = fma(-ui, u, d[i]);
         }
       }
-      if (bad && lane == 0) atomicCAS(info, 0, k0 + base + bad);
+      if (bad && lane == 0) set_info(pr, info, k0 + base + bad);
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (lane >= i) S[(base + i) * TILE_LD + base + lane] = d[i];
@@ -861,10 +928,10 @@ __device__ __forceinline__ void potf2_pipelined(double* __restrict__ S, double* 
       for (int l = 0; l < 32; ++l) S[(base + l) * TILE_LD + c] = v[l];
     }
     __syncthreads();
-    store_rows<true>(S, G, ld, base, nb, nb);
-    __threadfence();
+    store_rows_all<true>(pr, S, G, ld, base, nb, nb);
+    if (pr.R == 1) __threadfence(); else __threadfence_system();
     __syncthreads();
-    if (tid == 0) publish(diag_prog, epoch, (base >> 5) + 1);
+    if (tid == 0) publish_all(pr, prog, diag_idx, epoch, (base >> 5) + 1);
     if (W > 0) {
       potf2_trailing_update(S, base, W, warp, lane);
       __syncthreads();
@@ -874,10 +941,10 @@ __device__ __forceinline__ void potf2_pipelined(double* __restrict__ S, double* 
 
 // Off-diagonal task (ti, tj): X = U(ti, ti)^{-T} B for the B tile in Ps (all 128 columns), one 32-row step behind the
 // factorisation of U(ti, ti); every finished step is stored and published.
-__device__ __forceinline__ void solve_pipelined(double* __restrict__ Ps, double* __restrict__ Us,
+__device__ __forceinline__ void solve_pipelined(const Peers& pr, double* __restrict__ Ps, double* __restrict__ Us,
                                                 double* __restrict__ rinv, const double* __restrict__ Uii,
-                                                double* __restrict__ G, long long ld, int ncols,
-                                                unsigned long long* prog, int ti, int tj, unsigned epoch,
+                                                long long ld, double* __restrict__ G, long long ldg, int nrows,
+                                                int ncols, unsigned long long* prog, int ti, int tj, unsigned epoch,
                                                 int* __restrict__ info, unsigned int* fault) {
   const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5, l4 = lane & 3, g8 = lane >> 2;
   const bool vecU = !(ld & 1) && !(((uintptr_t)Uii) & 15);
@@ -885,13 +952,16 @@ __device__ __forceinline__ void solve_pipelined(double* __restrict__ Ps, double*
 #pragma unroll 1
   for (int b0 = 0; b0 < NB; b0 += 32) {
     const int g = b0 >> 5;
-    if (tid == 0 && dready < g + 1) dready = wait_progress(prog, MAX_T + ti, epoch, g + 1, info, fault);  // cached by thread 0
+    if (tid == 0 && dready < g + 1)  // cached by thread 0
+      dready = wait_progress(prog, MAX_COLS + ti, epoch, g + 1, info, fault, pr.R > 1);
     __syncthreads();  // U rows published (thread 0 acquired); previous step's readers of the slab are done
     // slab: rows b0 .. b0+31 of U(ti, ti), columns >= row
     for (int idx = tid; idx < SLAB_ROWS * (NB / 2); idx += THREADS) {
       const int r = idx >> 6, cc = (idx & 63) * 2, row = b0 + r;
       double2 v = make_double2(0.0, 0.0);
-      if (cc + 1 >= row) {
+      if (row >= nrows) {  // ragged last row block (right-hand-side columns only): identity padding, nothing to read
+        v = make_double2(cc == row ? 1.0 : 0.0, cc + 1 == row ? 1.0 : 0.0);
+      } else if (cc + 1 >= row) {
         if (vecU) {
           v = __ldcg(reinterpret_cast<const double2*>(Uii + (long long)row * ld + cc));
         } else {
@@ -922,7 +992,7 @@ __device__ __forceinline__ void solve_pipelined(double* __restrict__ Ps, double*
       for (int l = 0; l < 32; ++l) Ps[(b0 + l) * TILE_LD + c] = v[l];
     }
     __syncthreads();
-    store_rows<false>(Ps, G, ld, b0, NB, ncols);  // rows b0 .. b0+31 of X are final
+    store_rows_all<false>(pr, Ps, G, ldg, b0, nrows, ncols);  // rows b0 .. b0+31 of X are final
     // rows below:  Ps[r0.., :] -= U[b0..b0+32, r0..]^T X[b0..b0+32, :]; warp wp owns columns 16 wp .. 16 wp + 15
     {
       double bf[2][8];
@@ -958,17 +1028,18 @@ __device__ __forceinline__ void solve_pipelined(double* __restrict__ Ps, double*
             *reinterpret_cast<double2*>(Ps + (r0 + 8 * i + g8) * TILE_LD + 16 * wp + 8 * cb + 2 * l4) = cacc[cb][i];
       }
     }
-    __threadfence();
+    if (pr.R == 1) __threadfence(); else __threadfence_system();
     asm volatile("fence.proxy.async;" ::: "memory");  // the rows will be read by TMA
     __syncthreads();
-    if (tid == 0) publish(prog + tj, epoch, 4 * ti + g + 1);
+    if (tid == 0) publish_all(pr, prog, tj, epoch, 4 * ti + g + 1);
   }
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-potrf_dag2_kernel(const __grid_constant__ CUtensorMap tm, double* __restrict__ H, long long ld, int n, int T,
-                  int* __restrict__ info, unsigned long long* __restrict__ prog, unsigned epoch,
-                  unsigned int* __restrict__ fault) {
+potrf_dag2_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmB,
+                  double* __restrict__ H, long long ld, int n, int T, double* __restrict__ Bm, long long ldb, int p,
+                  int TB, int* __restrict__ info, unsigned long long* __restrict__ prog, unsigned epoch,
+                  unsigned int* __restrict__ fault, const Peers pr) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ double rinv[SLAB_ROWS];
   __shared__ double rs[32];
@@ -990,12 +1061,31 @@ potrf_dag2_kernel(const __grid_constant__ CUtensorMap tm, double* __restrict__ H
   __syncthreads();
   pdl_wait();
   const LaneMap lm = make_lane_map<S>(warp, lane);
-  Producer2 prod{&tm, ring, prog, info, fault, epoch, 0, 0, 0, 0, 0, 0, 0u};
+  Producer2 prod{&tm, &tmB, T, ring, prog, info, fault, epoch, pr.R > 1, 0, 0, 0, 0, 0, 0, 0u};
   uint32_t it = 0;
-  const int ntasks = T * (T + 1) / 2;
-  for (int lin = blockIdx.x; lin < ntasks; lin += gridDim.x) {
+  // Task list of this rank, row-major: R == 1: all (ti, tj), tj in [ti, T + TB); R > 1: the columns tj = me (mod R).
+  // The CTA runs tasks blockIdx.x, blockIdx.x + gridDim.x, ... of that list; `row` / `row_base` walk the rows.
+  const int R = pr.R, me = pr.me;
+  const int ntasks = T * (T + 1) / 2 + T * TB;  // R == 1
+  int row = 0, row_base = 0;
+  for (int lin = blockIdx.x;; lin += gridDim.x) {
     int ti, tj;
-    decode_tile(lin, T, T, true, ti, tj);
+    if (R == 1) {
+      if (lin >= ntasks) break;
+      decode_tile(lin, T, T + TB, true, ti, tj);  // row ti: columns ti .. T + TB - 1 (block columns >= T: right-hand sides)
+    } else {
+      int first = 0, cnt = 0;
+      while (row < T) {
+        first = row + ((me - row) % R + R) % R;  // first column >= row owned by this rank
+        cnt = first < T ? (T - 1 - first) / R + 1 : 0;
+        if (lin < row_base + cnt) break;
+        row_base += cnt;
+        ++row;
+      }
+      if (row >= T) break;
+      ti = row;
+      tj = first + (lin - row_base) * R;
+    }
     const bool diag = ti == tj;
     double acc[S::MI][S::NI][2];
     zero_acc(acc);
@@ -1006,26 +1096,38 @@ potrf_dag2_kernel(const __grid_constant__ CUtensorMap tm, double* __restrict__ H
                                                   prod);
       __syncthreads();  // every warp is done with the ring before it becomes the tile
     }
-    stage_tile(tile, H, ld, n, ti * NB, tj * NB, diag, acc, lm);
-    __syncthreads();
     const int k0 = ti * NB;
+    const bool rhs = tj >= T;
+    double* M = rhs ? Bm : H;                       // matrix the tile lives in
+    const long long ldm = rhs ? ldb : ld;
+    const int c0 = rhs ? (tj - T) * NB : tj * NB, mcols = rhs ? p : n;
+    stage_tile(tile, M, ldm, n, mcols, k0, c0, diag, acc, lm);
+    __syncthreads();
     if (diag) {
-      potf2_pipelined(tile, rs, H + (long long)k0 * ld + k0, ld, min(NB, n - k0), k0, info, prog + MAX_T + ti, epoch);
-      if (tid == 0) publish(prog + MAX_T + ti, epoch, 4);  // a ragged last tile has fewer than four steps
+      potf2_pipelined(pr, tile, rs, H + (long long)k0 * ld + k0, ld, min(NB, n - k0), k0, info, prog, MAX_COLS + ti,
+                      epoch);
+      if (tid == 0) publish_all(pr, prog, MAX_COLS + ti, epoch, 4);  // a ragged last tile has fewer than four steps
     } else {
-      const int c0 = tj * NB;
-      solve_pipelined(tile, slab, rinv, H + (long long)k0 * ld + k0, H + (long long)k0 * ld + c0, ld, min(NB, n - c0),
-                      prog, ti, tj, epoch, info, fault);
+      solve_pipelined(pr, tile, slab, rinv, H + (long long)k0 * ld + k0, ld, M + (long long)k0 * ldm + c0, ldm,
+                      min(NB, n - k0), min(NB, mcols - c0), prog, ti, tj, epoch, info, fault);
     }
     // this task's generic accesses to the tile / slab precede the next task's TMA writes into the same bytes
     asm volatile("fence.proxy.async;" ::: "memory");
     __syncthreads();
   }
+  // Distributed: the kernel -- and with it everything the stream runs next on this rank's copy of U -- ends only when
+  // the other ranks' columns have arrived in full (off-diagonal tiles of column c: 4 c groups, diagonal tile: 4 steps).
+  if (R > 1 && blockIdx.x == 0) {
+    for (int c = tid; c < T; c += THREADS) {
+      wait_progress(prog, c, epoch, 4 * c, info, fault, true);
+      wait_progress(prog, MAX_COLS + c, epoch, 4, info, fault, true);
+    }
+  }
 }
 
 struct Slot {
   cudaStream_t stream;
-  unsigned long long* done;  // progress counters: MAX_T per block column + MAX_T per diagonal tile (pipelined kernel)
+  unsigned long long* done;  // progress counters: MAX_COLS per block column + MAX_T per diagonal tile (pipelined kernel)
   bool used;
 };
 constexpr int kMaxDev = kMaxDevices, kSlotsPerDev = 4;
@@ -1044,8 +1146,8 @@ unsigned long long* get_counters(int dev, cudaStream_t st, int* rc) {
   for (int i = 0; i < kSlotsPerDev; ++i) {
     Slot* s = &g_slots[dev][i];
     if (s->used) continue;
-    if (cudaMalloc(&s->done, (2 * MAX_T + 1) * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(s->done, 0, (2 * MAX_T + 1) * sizeof(unsigned long long)) != cudaSuccess) {
+    if (cudaMalloc(&s->done, (MAX_COLS + MAX_T) * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(s->done, 0, (MAX_COLS + MAX_T) * sizeof(unsigned long long)) != cudaSuccess) {
       *rc = ipm_set_cuda_error(cudaGetLastError());
       return nullptr;
     }
@@ -1070,9 +1172,13 @@ bool enabled(int n) {
 }
 
 // returns 1 when the problem is not handled here (caller falls through to the stream-ordered factorisation)
-int potrf(double* H, int ld, int n, int* info_dev, cudaStream_t st, bool pipelined = true) {
-  const int T = ceil_div(n, NB);
-  if (T < 3 || T > MAX_T) return 1;
+// Bm / ldb / p: optional right-hand sides solved in the same launch (pipelined kernel only), Bm <- U^{-T} Bm.
+// peers / peer_epoch / max_ctas: distributed factorisation (see struct Peers): counters, info and the matrix live in
+// peer-mapped memory owned by the caller, the epoch is the caller's (identical on every rank).
+int potrf(double* H, int ld, int n, int* info_dev, cudaStream_t st, bool pipelined = true, double* Bm = nullptr,
+          int ldb = 0, int p = 0, const Peers* peers = nullptr, unsigned peer_epoch = 0, int max_ctas = 0) {
+  const int T = ceil_div(n, NB), TB = Bm ? ceil_div(p, NB) : 0;
+  if (T < 3 || T > MAX_T || T + TB > MAX_COLS || (Bm && !pipelined) || (peers && (Bm || !pipelined))) return 1;
   int dev = 0, rc = IPM_OK;
   IPM_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= kMaxDev) return 1;
@@ -1085,23 +1191,43 @@ int potrf(double* H, int ld, int n, int* info_dev, cudaStream_t st, bool pipelin
     if (per_sm < 1) return 1;
     g_sms[dev] = sms * per_sm;
   }
-  unsigned long long* done = get_counters(dev, st, &rc);
+  unsigned long long* done = peers ? peers->prog[peers->me] : get_counters(dev, st, &rc);
   if (rc) return rc;
   if (!done) return 1;
-  CUtensorMap tm;
+  CUtensorMap tm, tmB;
   if (make_operand_map(&tm, H, ld, n, n)) return 1;  // unaligned base: the stream-ordered path reports it
-  unsigned epoch = ++g_epoch;
-  if (epoch == 0) epoch = ++g_epoch;  // never 0 (the counters' initial value)
-  const int ntasks = T * (T + 1) / 2;
-  const int grid = ntasks < g_sms[dev] ? ntasks : g_sms[dev];
+  tmB = tm;
+  if (Bm && make_operand_map(&tmB, Bm, ldb, n, p)) return 1;
+  unsigned epoch = peer_epoch;
+  if (!peers) {
+    epoch = ++g_epoch;
+    if (epoch == 0) epoch = ++g_epoch;  // never 0 (the counters' initial value)
+  }
+  Peers pr;
+  if (peers) {
+    pr = *peers;
+  } else {
+    pr.R = 1, pr.me = 0;
+    for (int r = 0; r < kMaxRanks; ++r) pr.H[r] = nullptr, pr.prog[r] = nullptr, pr.info[r] = nullptr;
+    pr.H[0] = H, pr.prog[0] = done, pr.info[0] = info_dev;
+  }
+  int ntasks = T * (T + 1) / 2 + T * TB;
+  if (peers) {  // tasks of this rank's columns
+    ntasks = 0;
+    for (int j = pr.me; j < T; j += pr.R) ntasks += j + 1;
+    if (ntasks == 0) ntasks = 1;  // a rank without columns still runs the final wait
+  }
+  int grid = ntasks < g_sms[dev] ? ntasks : g_sms[dev];
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   // cooperative: the CTAs wait for each other's tiles, so all of them must be resident (a second persistent kernel on
   // another stream, MPS SM limits or green contexts would otherwise leave round >= 1 tasks waiting for CTAs that are
   // never scheduled); every wait is additionally bounded by the watchdog
   if (pipelined) {
     static bool attr2_set[kMaxDevices];
     IPM_CUDA_CHECK(ensure_dynamic_smem(potrf_dag2_kernel, SMEM2, attr2_set));
-    IPM_CUDA_CHECK(launch_cooperative(potrf_dag2_kernel, dim3(grid), dim3(THREADS), SMEM2, st, tm, H, (long long)ld, n,
-                                      T, info_dev, done, epoch, ipm_internal_fault_word()));
+    IPM_CUDA_CHECK(launch_cooperative(potrf_dag2_kernel, dim3(grid), dim3(THREADS), SMEM2, st, tm, tmB, H, (long long)ld,
+                                      n, T, Bm, (long long)ldb, p, TB, info_dev, done, epoch,
+                                      ipm_internal_fault_word(), pr));
   } else {
     IPM_CUDA_CHECK(launch_cooperative(potrf_dag_kernel, dim3(grid), dim3(THREADS), SMEM, st, tm, H, (long long)ld, n, T,
                                       info_dev, done, epoch, ipm_internal_fault_word()));
@@ -1170,6 +1296,62 @@ extern "C" int ipm_potrf_upper_dag_f64(double* H, int ld, int n, int* info_dev, 
   const int rc = dag::potrf(H, ld, n, info_dev, (cudaStream_t)stream);
   if (rc <= 0) return rc;
   return potrf_stream_ordered(H, ld, n, info_dev, stream);
+}
+
+extern "C" int ipm_trsm_upper_t_f64(const double* U, int ldu, int n, double* B, int ldb, int p, void* stream);
+
+// H = U^T U in place AND B <- U^{-T} B (B: n x p row-major) -- the first two steps of the block elimination
+// (NewtonSolverInfeasibleStart.py:398-426: cho_factor(H), cho_solve halves on A^T) -- in ONE persistent launch when the
+// tile-DAG kernel covers the size; otherwise ipm_potrf_upper_f64 followed by ipm_trsm_upper_t_f64.
+extern "C" int ipm_potrf_trsm_upper_f64(double* H, int ld, int n, double* B, int ldb, int p, int* info_dev,
+                                        void* stream) {
+  if (!H || !B || !info_dev || n < 0 || p < 0 || ld < n || ldb < p || (ld & 1) || (ldb & 1)) return IPM_ERR_ARG;
+  IPM_CUDA_CHECK(cudaMemsetAsync(info_dev, 0, sizeof(int), (cudaStream_t)stream));
+  if (p > 0 && dag::enabled(n)) {
+    const int rc = dag::potrf(H, ld, n, info_dev, (cudaStream_t)stream, true, B, ldb, p);
+    if (rc <= 0) return rc;
+  }
+  int rc = ipm_potrf_upper_f64(H, ld, n, info_dev, stream);
+  if (rc) return rc;
+  return ipm_trsm_upper_t_f64(H, ld, n, B, ldb, p, stream);
+}
+
+// Distributed factorisation over R <= 8 GPUs of one node (north_star: "replicated or 2D-block-cyclic factorisation" --
+// here block columns dealt cyclically, push model over peer memory; see struct dag::Peers).  Every rank calls it at the
+// same point of its stream with its own `me`:
+//   peer_H[r]    : rank r's copy of the n x n matrix (leading dimension ld on every rank), upper triangle holds H
+//   peer_info[r] : rank r's info word (all of them receive the index of a non-positive pivot, or -1 from the watchdog)
+//   peer_prog[r] : rank r's progress counters, ipm_potrf_peer_prog_words() 64-bit words, zeroed once at allocation
+//   epoch        : != 0, different from the previous call's, identical on all ranks
+//   max_ctas     : 0 = one CTA per SM; smaller values let several "ranks" share one device (single-GPU tests)
+// On return (stream order) the rank's copy holds the complete factor U.  Replaces the same call sites as
+// ipm_potrf_upper_f64 in the row-sharded engine (NewtonSolver.py:286,303).
+extern "C" int ipm_potrf_peer_prog_words(void) { return dag::MAX_COLS + dag::MAX_T; }
+extern "C" int ipm_potrf_upper_peer_f64(void* const* peer_H, int ld, int n, void* const* peer_info,
+                                        void* const* peer_prog, int me, int R, unsigned int epoch, int max_ctas,
+                                        void* stream) {
+  if (!peer_H || !peer_info || !peer_prog || n < 0 || ld < n || (ld & 1) || R < 1 || R > dag::kMaxRanks || me < 0 ||
+      me >= R || epoch == 0)
+    return IPM_ERR_ARG;
+  dag::Peers pr;
+  pr.R = R, pr.me = me;
+  for (int r = 0; r < dag::kMaxRanks; ++r) {
+    pr.H[r] = r < R ? (double*)peer_H[r] : nullptr;
+    pr.prog[r] = r < R ? (unsigned long long*)peer_prog[r] : nullptr;
+    pr.info[r] = r < R ? (int*)peer_info[r] : nullptr;
+    if (r < R && (!pr.H[r] || !pr.prog[r] || !pr.info[r])) return IPM_ERR_ARG;
+  }
+  const int rc = dag::potrf(pr.H[me], ld, n, pr.info[me], (cudaStream_t)stream, true, nullptr, 0, 0, &pr, epoch, max_ctas);
+  return rc == 1 ? IPM_ERR_ARG : rc;  // sizes the tile-DAG kernel does not take (n <= 256): the caller factors replicated
+}
+
+// Library-internal (kernel tests): the fused launch for every admissible size, whatever the size policy says.
+extern "C" int ipm_internal_potrf_trsm_dag_f64(double* H, int ld, int n, double* B, int ldb, int p, int* info_dev,
+                                               void* stream) {
+  if (!H || !B || !info_dev || n < 0 || p <= 0 || ld < n || ldb < p || (ld & 1) || (ldb & 1)) return IPM_ERR_ARG;
+  IPM_CUDA_CHECK(cudaMemsetAsync(info_dev, 0, sizeof(int), (cudaStream_t)stream));
+  const int rc = dag::potrf(H, ld, n, info_dev, (cudaStream_t)stream, true, B, ldb, p);
+  return rc == 1 ? IPM_ERR_ARG : rc;
 }
 
 // Library-internal (A/B timing in tools/ and bench.py --factorisation): always the stream-ordered code.

@@ -155,6 +155,43 @@ __device__ __forceinline__ void frags(double (&a)[S::MI], double (&b)[S::NI], ui
   }
 }
 
+// Variant builds (-DIPM_LASSO_TIMING, tools/lasso_timing.py): per-CTA cycle counters of the phases of a unit --
+// [0] whole kernel, [1] claim, [2] dependency wait, [3] TMA + DMMA loop, [4] rank-1 terms, [5] epilogue / tail-row unit,
+// [6] publish, [7] tile units, [8] tail units.  Thread 0's view (it passes every CTA barrier).
+#ifdef IPM_LASSO_TIMING
+__device__ long long g_lm_t[1024 * 16];
+#define LM_T0() long long lm_t = clock64(); const long long lm_t_kernel = lm_t
+#define LM_MARK(slot)                                                        \
+  do {                                                                       \
+    if (threadIdx.x == 0) {                                                  \
+      const long long now = clock64();                                       \
+      g_lm_t[(blockIdx.x & 1023) * 16 + (slot)] += now - lm_t;               \
+      lm_t = now;                                                            \
+    }                                                                        \
+  } while (0)
+#define LM_COUNT(slot)                                                       \
+  do {                                                                       \
+    if (threadIdx.x == 0) g_lm_t[(blockIdx.x & 1023) * 16 + (slot)] += 1;    \
+  } while (0)
+#define LM_TOTAL()                                                                              \
+  do {                                                                                          \
+    if (threadIdx.x == 0) g_lm_t[(blockIdx.x & 1023) * 16] += clock64() - lm_t_kernel;          \
+  } while (0)
+#else
+#define LM_T0() \
+  do {          \
+  } while (0)
+#define LM_MARK(slot) \
+  do {                \
+  } while (0)
+#define LM_COUNT(slot) \
+  do {                 \
+  } while (0)
+#define LM_TOTAL() \
+  do {             \
+  } while (0)
+#endif
+
 template <class S>
 __global__ void __launch_bounds__(LM_THREADS, S::MINB)
 lasso_admm_multi_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmZ0,
@@ -190,14 +227,17 @@ lasso_admm_multi_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint32_t it = 0;   // k-tiles consumed through the ring (all warps)
   uint32_t pit = 0;  // k-tiles issued into the ring (all warps keep the same count)
 
-  if (tid == 0) s_unit = (int)atomicAdd(sched, 1u);
-  __syncthreads();
-  int unit = s_unit;
-  while (unit < total) {
-    __syncthreads();  // everybody has read s_unit and is done with the ring / tail scratch of the previous unit
-    // claim the NEXT unit now: the atomic's round trip hides under this unit.  (Still deadlock-free: a unit held in
-    // reserve belongs to a CTA whose current unit is smaller, so the smallest unfinished unit is always running.)
+  // (Claiming the next unit early, to hide the atomic's round trip, was measured and dropped: a reserved unit cannot be
+  // taken by an idle CTA, and with the lock-step dependencies of a column group one late unit delays the whole group --
+  // K = 1024: 27.9 -> 33.9 us per iteration.)
+  LM_T0();
+  while (true) {
+    __syncthreads();  // everybody is done with s_unit and the ring / tail scratch of the previous unit
     if (tid == 0) s_unit = (int)atomicAdd(sched, 1u);
+    __syncthreads();
+    const int unit = s_unit;
+    if (unit >= total) break;
+    LM_MARK(1);
     const int li = unit / per_iter;            // iteration inside this launch
     const int rem = unit - li * per_iter;
     const int g = rem / p.U, r = rem - g * p.U;
@@ -223,6 +263,7 @@ lasso_admm_multi_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
       __syncthreads();
     }
+    LM_MARK(2);
     Sums sums{0.0, 0.0, 0.0, 0.0};
     if (r < p.RT) {
       // ================================ DMMA tile =========================================
@@ -283,6 +324,7 @@ lasso_admm_multi_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         }
       }
       const int m_base = m0 + lm.wm * (S::MI * 8), n_base = n0 + lm.wn * (S::NI * 8);
+      LM_MARK(3);
       // contraction rows beyond the last full k-tile (n = 513: one row) as rank-1 terms
       for (int k = p.k_main; k < p.n; ++k) {
         double qk[S::MI], zk[S::NI][2];
@@ -306,6 +348,7 @@ lasso_admm_multi_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             acc[i][jn][1] = fma(qk[i], zk[jn][1], acc[i][jn][1]);
           }
       }
+      LM_MARK(4);
       // ---- epilogue on the accumulators
       const bool interior = (m_base + S::MI * 8 <= p.n_main) && (n_base + S::NI * 8 <= p.K);
       if (interior) {
@@ -411,13 +454,16 @@ lasso_admm_multi_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
     }
     if (norms) flush_sums(p, rem, sums);
+    LM_MARK(5);
     // ---- publish: this unit's z+ / u+ -> device scope (and the async proxy of the CTAs that will TMA-load z+)
     __threadfence();
     asm volatile("fence.proxy.async;" ::: "memory");
     __syncthreads();
     if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.done + g) : "memory");
-    unit = s_unit;  // written before the barriers above
+    LM_MARK(6);
+    LM_COUNT(r < p.RT ? 7 : 8);
   }
+  LM_TOTAL();
 }
 
 // End of a launch: add the partial sums in slot order, evaluate the stop test (LassoSolver.py:284-298), advance the
@@ -583,6 +629,18 @@ extern "C" int ipm_lasso_admm_steps_f64(const double* Qt, int ldq, int n, int K,
   IPM_LAUNCH_CHECK();
   return IPM_OK;
 }
+
+#ifdef IPM_LASSO_TIMING
+// variant builds only: copies the per-CTA cycle counters to the host and clears them
+extern "C" int ipm_internal_lasso_timing(long long* out, int count) {
+  static long long zero[1024 * 16];
+  if (count > 1024 * 16) count = 1024 * 16;
+  IPM_CUDA_CHECK(cudaDeviceSynchronize());
+  IPM_CUDA_CHECK(cudaMemcpyFromSymbol(out, lasso::g_lm_t, count * sizeof(long long)));
+  IPM_CUDA_CHECK(cudaMemcpyToSymbol(lasso::g_lm_t, zero, sizeof(zero)));
+  return IPM_OK;
+}
+#endif
 
 // Byte offset inside `ws` of the four squared norms {|x - alpha+|^2, |rho (alpha+ - alpha)|^2, |alpha+|^2, |u+|^2} of the
 // last stop test (for the device the caller is on).

@@ -399,6 +399,11 @@ class LinearNewton:
         """Quadratic line-search coefficients (second-order cones only)."""
         return None
 
+    def _factor(self):
+        """ws.H (upper) <- U with H = U'U; ws.info[0] = LAPACK-style info (NewtonSolver.py:286,303)."""
+        ws = self.ws
+        self.L("ipm_potrf_upper_f64", ws.H.data_ptr(), ws.ldh, self.nz, ws.info.data_ptr())
+
     def _chol_solve_vec(self, vec):
         """vec <- H^{-1} vec using the factor in ws.H."""
         ws, L = self.ws, self.L
@@ -488,7 +493,7 @@ class LinearNewton:
             L("ipm_vec_op_f64", 1, d.n, ws.g.data_ptr(), ws.hdiag.data_ptr(), ws.dz.data_ptr(), -1.0)
         else:
             self._hessian(t)
-            L("ipm_potrf_upper_f64", ws.H.data_ptr(), ws.ldh, self.nz, ws.info.data_ptr())
+            self._factor()
             L("ipm_lincomb3_f64", self.nz, -1.0, ws.g.data_ptr(), 0.0, None, 0.0, None, ws.dz.data_ptr())
             self._chol_solve_vec(ws.dz)
         self._feasibility(z)
@@ -574,7 +579,9 @@ class LinearNewton:
     # ---------------------------------------------------------------- infeasible-start (equality constrained)
     def _direction_infeasible(self, z, lin):
         """Block elimination (NewtonSolverInfeasibleStart.py:386-490):
-        H = U'U;  Y = U^{-T} A';  S = Y'Y;  y = H^{-1} g;  w = S^{-1}(Ax - b - A y);  dx = -H^{-1}(g + A'w)."""
+        H = U'U;  [Y | f] = U^{-T} [A' | g];  S = Y'Y;  w = S^{-1}(Ax - b - Y'f);  dx = -U^{-1}(f + Y w)
+        (= the reference's  y = H^{-1} g;  w = S^{-1}(Ax - b - A y);  dx = -H^{-1}(g + A'w)  with the forward solves folded
+        into the factorisation launch)."""
         d, ws, L = self.d, self.ws, self.L
         n, p, t = d.n, d.p, self.t
         # b2 = A x - b
@@ -588,30 +595,38 @@ class LinearNewton:
             L("ipm_vec_op_f64", 0, n, ws.hinv.data_ptr(), ws.g.data_ptr(), ws.yv.data_ptr(), 1.0)
         else:
             self._hessian(t)
-            L("ipm_potrf_upper_f64", ws.H.data_ptr(), ws.ldh, n, ws.info.data_ptr())
+            # ONE launch: H = U'U and [Y | f] = U^{-T} [A' | g] (the right-hand sides are extra block columns of the tile
+            # DAG).  With Y and f the block elimination needs no further forward solve:
+            #   A H^{-1} A' = Y'Y,   A H^{-1} g = Y'f,   H^{-1}(g + A'w) = U^{-1}(f + Y w)
             ws.Y[:, :p].copy_(d.At[:, :p])
-            L("ipm_trsm_upper_t_f64", ws.H.data_ptr(), ws.ldh, n, ws.Y.data_ptr(), ws.ldy, p)
+            ws.Y[:, p].copy_(ws.g)
+            L("ipm_potrf_trsm_upper_f64", ws.H.data_ptr(), ws.ldh, n, ws.Y.data_ptr(), ws.ldy, p + 1, ws.info.data_ptr())
+            ws.yv.copy_(ws.Y[:, p])  # f = U^{-T} g
             L("ipm_gemm_tn_f64", ws.Y.data_ptr(), ws.ldy, ws.Y.data_ptr(), ws.ldy, None, 1.0, 0.0, ws.S.data_ptr(),
               ws.lds, p, p, n, 1)
-            ws.yv.copy_(ws.g)
-            self._chol_solve_vec(ws.yv)
         if self.shift:
             L("ipm_hess_finish_f64", ws.S.data_ptr(), ws.lds, p, None, None, None, self.shift)
         L("ipm_potrf_upper_f64", ws.S.data_ptr(), ws.lds, p, ws.info.data_ptr() + 4)
-        # rhs = b2 - A y ; w = S^{-1} rhs
+        # rhs = b2 - A H^{-1} g ; w = S^{-1} rhs
         ws.rhs_p.copy_(ws.Axb)
-        L("ipm_gemv_n_f64", d.A.data_ptr(), d.lda, p, n, ws.yv.data_ptr(), ws.rhs_p.data_ptr(), -1.0, 1.0)
+        if self.diagonal:
+            L("ipm_gemv_n_f64", d.A.data_ptr(), d.lda, p, n, ws.yv.data_ptr(), ws.rhs_p.data_ptr(), -1.0, 1.0)
+        else:
+            L("ipm_gemv_t_f64", ws.Y.data_ptr(), ws.ldy, n, p, ws.yv.data_ptr(), 1, n, ws.rhs_p.data_ptr(), p, -1.0, 1.0,
+              ws.gt_ws.data_ptr(), ws.gt_ws_n)
         ws.wv.copy_(ws.rhs_p)
         L("ipm_trsv_upper_f64", ws.S.data_ptr(), ws.lds, p, ws.wv.data_ptr(), 1, ws.tr_ws.data_ptr())
         L("ipm_trsv_upper_f64", ws.S.data_ptr(), ws.lds, p, ws.wv.data_ptr(), 0, ws.tr_ws.data_ptr())
         # dx = -H^{-1}(g + A'w)
-        ws.dz.copy_(ws.g)
-        L("ipm_gemv_t_f64", d.A.data_ptr(), d.lda, p, n, ws.wv.data_ptr(), 1, p, ws.dz.data_ptr(), n, 1.0, 1.0,
-          ws.gt_ws.data_ptr(), ws.gt_ws_n)
         if self.diagonal:
+            ws.dz.copy_(ws.g)
+            L("ipm_gemv_t_f64", d.A.data_ptr(), d.lda, p, n, ws.wv.data_ptr(), 1, p, ws.dz.data_ptr(), n, 1.0, 1.0,
+              ws.gt_ws.data_ptr(), ws.gt_ws_n)
             L("ipm_vec_op_f64", 0, n, ws.hinv.data_ptr(), ws.dz.data_ptr(), ws.dz.data_ptr(), -1.0)
         else:
-            self._chol_solve_vec(ws.dz)
+            ws.dz.copy_(ws.yv)
+            L("ipm_gemv_n_f64", ws.Y.data_ptr(), ws.ldy, n, p, ws.wv.data_ptr(), ws.dz.data_ptr(), 1.0, 1.0)
+            L("ipm_trsv_upper_f64", ws.H.data_ptr(), ws.ldh, n, ws.dz.data_ptr(), 0, ws.tr_ws.data_ptr())
             L("ipm_lincomb3_f64", n, -1.0, ws.dz.data_ptr(), 0.0, None, 0.0, None, ws.dz.data_ptr())
         # dv = w - v
         L("ipm_lincomb3_f64", p, 1.0, ws.wv.data_ptr(), -1.0, ws.v.data_ptr(), 0.0, None, ws.dv.data_ptr())

@@ -68,16 +68,24 @@ class _RowSharded:
             Hs = symm.empty((ws.H.shape[0], ws.H.shape[1]), dtype=F64, device=self.d.device)
             inbox = symm.empty((self.world * slots * 128 * 128,), dtype=F64, device=self.d.device)
             sig = symm.empty((slots * self.world + 64,), dtype=torch.int32, device=self.d.device)
+            # distributed factorisation (ipm_potrf_upper_peer_f64): progress counters and the info word of every rank
+            words = _abi.lib().ipm_potrf_peer_prog_words()
+            prog = symm.empty((words,), dtype=torch.int64, device=self.d.device)
+            info = symm.empty((4,), dtype=torch.int32, device=self.d.device)
             Hs.zero_()
             sig.zero_()
-            hH, hI, hS = (symm.rendezvous(t, grp.group_name) for t in (Hs, inbox, sig))
-            st = dict(slots=slots, tiles=T * (T + 1) // 2, H=Hs, inbox=inbox, sig=sig, handles=(hH, hI, hS),
-                      done_off=slots * self.world, epoch=0, target=0)
+            prog.zero_()
+            info.zero_()
+            hH, hI, hS, hP, hN = (symm.rendezvous(t, grp.group_name) for t in (Hs, inbox, sig, prog, info))
+            st = dict(slots=slots, tiles=T * (T + 1) // 2, H=Hs, inbox=inbox, sig=sig, prog=prog, info=info,
+                      handles=(hH, hI, hS, hP, hN), done_off=slots * self.world, epoch=0, target=0, potrf_epoch=0)
             R = self.world
             st["p_inbox"] = (C.c_void_p * R)(*[int(p) for p in hI.buffer_ptrs])
             st["p_flags"] = (C.c_void_p * R)(*[int(p) for p in hS.buffer_ptrs])
             st["p_H"] = (C.c_void_p * R)(*[int(p) for p in hH.buffer_ptrs])
             st["p_done"] = (C.c_void_p * R)(*[int(p) + 4 * st["done_off"] for p in hS.buffer_ptrs])
+            st["p_prog"] = (C.c_void_p * R)(*[int(p) for p in hP.buffer_ptrs])
+            st["p_info"] = (C.c_void_p * R)(*[int(p) for p in hN.buffer_ptrs])
         except Exception as e:  # noqa: BLE001 -- any failure means "no peer path on this box"
             ok.zero_()
             self.peer_error = repr(e)
@@ -85,6 +93,10 @@ class _RowSharded:
         if int(ok.item()) == 1:
             self.peer = st
             self.ws.H = st["H"]  # the factorisation runs in the peer-mapped buffer the owners write into
+            self.ws.info = st["info"]
+            # block columns of the factorisation dealt over the ranks (csrc/chol.cu, struct dag::Peers);
+            # IPM_PEER_POTRF=0 keeps the factorisation replicated
+            self.peer_potrf = os.environ.get("IPM_PEER_POTRF", "1") != "0" and self.nz > 384
             torch.cuda.synchronize()
             dist.barrier(group=self.group)
 
@@ -101,6 +113,17 @@ class _RowSharded:
         L("ipm_hess_reduce_bcast_f64", pr["inbox"].data_ptr(), pr["sig"].data_ptr(), pr["p_H"], pr["p_done"], ws.ldh,
           d.n, self.rank, self.world, pr["slots"], pr["epoch"], pr["target"], _abi.ptr(P), ldp, tP)
         self.comm_bytes += 2 * pr["tiles"] * 128 * 128 * 8 * (self.world - 1) // self.world
+
+    def _factor(self):
+        """Distributed tile-DAG Cholesky over the ranks: block column j on rank j % R, finished rows pushed into every
+        rank's copy of H over NVLink, so every rank ends with the whole factor (the triangular solves stay replicated)."""
+        pr = self.peer
+        if pr is None or not getattr(self, "peer_potrf", False):
+            return super()._factor()
+        pr["potrf_epoch"] = pr["potrf_epoch"] % 0x7FFFFFFF + 1
+        with self.L.timed_range("factorisation"):
+            self.L("ipm_potrf_upper_peer_f64", pr["p_H"], self.ws.ldh, self.nz, pr["p_info"], pr["p_prog"], self.rank,
+                   self.world, pr["potrf_epoch"], 0)
 
     def _sum(self, t):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)

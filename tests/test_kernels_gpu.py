@@ -389,6 +389,78 @@ def test_peer_hessian_kernels_emulated_ranks(n, m, R):
         assert torch.equal(H[r], H[0])                                       # bit-identical on every "rank"
 
 
+@pytest.mark.parametrize("n,p", [(385, 64), (513, 200), (1000, 129), (2500, 300)])
+def test_potrf_trsm_fused_tile_dag(n, p):
+    """ipm_potrf_trsm_upper_f64 / the forced tile-DAG entry: H = U'U and Y = U^{-T} B in one launch, ragged last row block
+    and ragged last right-hand-side panel, twice in a row (epoch-stamped counters)."""
+    import scipy.linalg
+
+    fn = _abi.lib().ipm_internal_potrf_trsm_dag_f64
+    fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    H = spd(n, n + 11, cond_pow=2)
+    rs = np.random.RandomState(p)
+    B = rs.randn(n, p)
+    U = scipy.linalg.cholesky(H, lower=False)
+    Y = scipy.linalg.solve_triangular(U, B, trans="T", lower=False)
+    info = torch.full((1,), -7, dtype=torch.int32, device="cuda")
+    for entry in ("forced", "public", "forced"):
+        Hd, ld = padded(H)
+        Bd, ldb = padded(B)
+        guard = Bd.clone()
+        if entry == "forced":
+            _abi.check(fn(Hd.data_ptr(), ld, n, Bd.data_ptr(), ldb, p, info.data_ptr(), None), "potrf_trsm_dag")
+        else:
+            _abi.call("ipm_potrf_trsm_upper_f64", Hd.data_ptr(), ld, n, Bd.data_ptr(), ldb, p, info.data_ptr(), None)
+        torch.cuda.synchronize()
+        assert _abi.lib().ipm_device_fault() == 0 and int(info.item()) == 0
+        Ud = torch.triu(Hd[:, :n]).cpu().numpy()
+        assert np.max(np.abs(Ud.T @ Ud - H)) / np.max(np.abs(H)) < 1e-13
+        Yd = Bd[:, :p].cpu().numpy()
+        assert np.max(np.abs(Yd - Y)) <= 1e-10 * np.max(np.abs(Y))
+        assert torch.equal(Bd[:, p:], guard[:, p:])  # padding columns untouched
+
+
+@pytest.mark.parametrize("n,R", [(1000, 2), (1537, 3)])
+def test_potrf_peer_emulated_ranks(n, R):
+    """ipm_potrf_upper_peer_f64 with R emulated ranks on ONE device: R copies of the matrix, R streams, each launch limited
+    to #SMs / R CTAs so that the R cooperative grids are resident together; every copy must end with the whole factor.
+    (The real multi-GPU run is tests/test_sharded_gpu.py.)"""
+    L = _abi.lib()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    H = spd(n, n + 3, cond_pow=2)
+    words = L.ipm_potrf_peer_prog_words()
+    copies = [padded(H) for _ in range(R)]
+    ld = copies[0][1]
+    progs = [torch.zeros(words, dtype=torch.int64, device="cuda") for _ in range(R)]
+    infos = [torch.full((4,), 0, dtype=torch.int32, device="cuda") for _ in range(R)]
+    pH = (C.c_void_p * R)(*[c[0].data_ptr() for c in copies])
+    pP = (C.c_void_p * R)(*[t.data_ptr() for t in progs])
+    pI = (C.c_void_p * R)(*[t.data_ptr() for t in infos])
+    streams = [torch.cuda.Stream() for _ in range(R)]
+    L.ipm_clear_device_fault()
+    old = L.ipm_set_spin_limit(600)  # ~0.3 s: fail fast if the grids cannot be co-resident
+    try:
+        for epoch in (1, 2):
+            for c in copies:
+                c[0][:, :n] = torch.as_tensor(H, device="cuda")
+            torch.cuda.synchronize()
+            for r in range(R):
+                _abi.call("ipm_potrf_upper_peer_f64", pH, ld, n, pI, pP, r, R, epoch, sms // R, streams[r].cuda_stream)
+            torch.cuda.synchronize()
+            fault = L.ipm_device_fault()
+            if fault == 7:
+                L.ipm_clear_device_fault()
+                pytest.skip("the R cooperative grids were not co-resident on this device (peer wait timed out)")
+            assert fault == 0
+            for r in range(R):
+                assert int(infos[r][0]) == 0
+                U = torch.triu(copies[r][0][:, :n]).cpu().numpy()
+                assert np.max(np.abs(U.T @ U - H)) / np.max(np.abs(H)) < 1e-13, r
+    finally:
+        L.ipm_set_spin_limit(old)
+        L.ipm_clear_device_fault()
+
+
 def _admm_numpy(Qt, bA, eta, rho, alpha, u, add_bias, positive, iters):
     """LassoSolver.py:245-253 / 517-543 restated for the kernel's operands (Q~ = -m rho Q, z = u - alpha)."""
     r = d = a = un_ = None

@@ -15,7 +15,7 @@ from test_solvers_gpu import assert_iters_close, noise_dominated_steps
 
 pytestmark = pytest.mark.gpu
 
-CASES = {c["name"]: c for f in ("barrier_cases.json", "dual_cases.json") for c in load_golden(f)}
+CASES = {c["name"]: c for f in ("barrier_cases.json", "dual_cases.json", "large_cases.json") for c in load_golden(f)}
 
 
 def _worker(rank, world, port, name, q):
@@ -64,13 +64,14 @@ def _run(name):
 
 @pytest.mark.parametrize("name", ["lp_dense_n256_cold", "lp_dense_n97_ragged", "socp_n48_warm", "socp_n48_cold",
                                   "socp_n96_warm", "lp_seed1_n100_0", "qp_seed1_n100_0", "qp_dense_n512",
-                                  "socp_n48_eq_warm"])
+                                  "socp_n48_eq_warm", "lp_dense_n1024_warm", "lp_dense_n1024_cold"])
 def test_row_sharded_matches_reference(name):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     case = CASES[name]
     val, iters, p1, x, peer, peer_error, _, _ = _run(name)
-    # the Hessian exchange ran over peer memory (fused SYRK + reduce-scatter + all-gather), not the NCCL fallback
+    # the Hessian exchange ran over peer memory (fused SYRK + reduce-scatter + all-gather), not the NCCL fallback; the
+    # n = 1024 cases also run the factorisation distributed over the two GPUs (ipm_potrf_upper_peer_f64)
     assert peer, peer_error
     assert val == pytest.approx(case["value"], rel=1e-6, abs=1e-9)
     prob = getattr(problems, case["generator"])(**case["generator_kwargs"])
