@@ -417,7 +417,8 @@ def qp_section(D, args):
     s = QPSolver(**prob, check_cvxpy=False, suppress_print=True, **problems.QP_TEST_SETTINGS)
     del prob
     L = s.launcher
-    L.timed_ops = {"ipm_gemm_tn_f64": [], "ipm_potrf_upper_f64": [], "ipm_trsm_upper_t_f64": []}
+    L.timed_ops = {"ipm_gemm_tn_f64": [], "ipm_potrf_upper_f64": [], "ipm_potrf_trsm_upper_f64": [], "ipm_trsv_upper_f64": [],
+                   "ipm_gemv_n_f64": [], "ipm_gemv_t_f64": []}
     marks = {}
 
     orig = s.phase1_solver.solve
