@@ -243,8 +243,8 @@ class NewtonWorkspace:
                   _abi.lib().ipm_gemv_t_ws_doubles(n, max(p, 1), 2))
         self.gt_ws, self.gt_ws_n = z(nws), nws
         if p:
-            self.ldy = _round_up(p, 16)
-            self.Y = z(n, self.ldy)      # U^{-T} A^T
+            self.ldy = _round_up(p + 1, 16)
+            self.Y = z(n, self.ldy)      # U^{-T} [A^T | g]
             self.lds = _round_up(p, 16)
             self.S = z(p, self.lds)      # Schur complement
             self.v, self.dv, self.wv = z(p), z(p), z(p)
