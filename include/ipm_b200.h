@@ -192,20 +192,24 @@ int ipm_ls_feas_poly_f64(int count, const double* s0, const double* p1, const do
                          int len, int* kmax, int reset, void* stream);
 /* Armijo loop with the reference's semantics (slope g.x, frozen barrier term, lagging trial point).
  * out[5] = {step, stuck, index, frozen log-sum, trials}.  NewtonSolver.py:185-206.  textbook != 0: the plain Armijo
- * rule of the stand-alone phase-I (slope g.dx = terms[4], barrier re-evaluated per trial; PhaseOne.py:187-218). */
+ * rule of the stand-alone phase-I (slope g.dx = terms[4], barrier re-evaluated per trial; PhaseOne.py:187-218).
+ * update_slacks_every > 0 (NewtonSolver.py:196-202): the barrier term is refreshed every so many trials -- from the slack
+ * polynomial, or, when L_direct is given (cones), by the host: the call returns stuck = 4 with *kmax = index of the
+ * lagging point; evaluate the barrier there into *L_direct and call again with resume = 1. */
 int ipm_ls_armijo_f64(int nc, const double* s0, const double* p1, const double* p2, const double* table, int len,
-                      const int* kmax, const double* sumlog, const double* terms, double t, double alpha,
-                      int update_slacks_every, const double* L_direct, const double* nneg, int textbook, double* out,
-                      void* stream);
+                      int* kmax, const double* sumlog, const double* terms, double t, double alpha,
+                      int update_slacks_every, const double* L_direct, const double* nneg, int textbook, int resume,
+                      double* out, void* stream);
 /* out[0] = sum log(s(table[*kmax]) + 1e-15) over this rank's slack entries (row-sharded problems all-reduce it and
  * pass the result as L_direct). */
 int ipm_ls_logsum_f64(int nc, const double* s0, const double* p1, const double* p2, const double* table, int len,
                       const int* kmax, double* out, void* stream);
-/* Residual-norm search of the infeasible-start method.  out[5] = {step, stuck, index, r0, r(step)}.
- * NewtonSolverInfeasibleStart.py:207-273. */
+/* Residual-norm search of the infeasible-start method.  out[6] = {step, stuck, index, r0, r(step), trials}.
+ * NewtonSolverInfeasibleStart.py:207-273.  update_slacks_every > 0 (:249-255): when a refresh is due the call returns
+ * stuck = 4 with *kmax = the trial index; re-evaluate the barrier gradient there into u0 and call again with resume = 1. */
 int ipm_ls_residual_f64(int n, int p, const double* r0d, const double* u0, const double* u1, const double* q0,
-                        const double* q1, const double* table, int len, const int* kmax, double alpha,
-                        const double* nneg, double* out, void* stream);
+                        const double* q1, const double* table, int len, int* kmax, double alpha, const double* nneg,
+                        int update_slacks_every, int resume, double* out, void* stream);
 int ipm_table_lookup_f64(const double* table, int len, const int* kmax, double* out, void* stream);
 
 /* ---- batched ADMM Lasso ---------------------------------------------------------------------------------- */

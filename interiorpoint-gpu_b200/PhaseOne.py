@@ -109,7 +109,7 @@ class PhaseOneSolver:
             ns._feasibility(z)
             L("ipm_ls_armijo_f64", self.data.n_slacks, ws.slacks.data_ptr(), ws.p1.data_ptr(), None,
               ns.table.data_ptr(), ns.table_len, ws.kmax.data_ptr(), ws.red.data_ptr(), ws.terms.data_ptr(), float(t),
-              0.2, 0, None, None, 1, ws.ls_out.data_ptr())
+              0.2, 0, None, None, 1, 0, ws.ls_out.data_ptr())
             L("ipm_axpy_dev_f64", ns.nz, ws.ls_out.data_ptr(), ws.dz.data_ptr(), z.data_ptr())
             self.newton_steps += 1
             if self.s < 0:  # PhaseOne.py:160-161

@@ -66,9 +66,9 @@ SIGNATURES = {
     "ipm_scale_copy_upper_f64": (_i, [_dp, _i, _dp, _i, _i, _d, _dp]),
     "ipm_ls_feas_lin_f64": (_i, [_i, _i, _dp, _dp, _dp, _i, _i, _i, _dp, _i, _dp, _dp, _dp]),
     "ipm_ls_feas_poly_f64": (_i, [_i, _dp, _dp, _dp, _dp, _i, _dp, _i, _dp]),
-    "ipm_ls_armijo_f64": (_i, [_i, _dp, _dp, _dp, _dp, _i, _dp, _dp, _dp, _d, _d, _i, _dp, _dp, _i, _dp, _dp]),
+    "ipm_ls_armijo_f64": (_i, [_i, _dp, _dp, _dp, _dp, _i, _dp, _dp, _dp, _d, _d, _i, _dp, _dp, _i, _i, _dp, _dp]),
     "ipm_ls_logsum_f64": (_i, [_i, _dp, _dp, _dp, _dp, _i, _dp, _dp, _dp]),
-    "ipm_ls_residual_f64": (_i, [_i, _i, _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp, _d, _dp, _dp, _dp]),
+    "ipm_ls_residual_f64": (_i, [_i, _i, _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp, _d, _dp, _i, _i, _dp, _dp]),
     "ipm_trial_point_f64": (_i, [_i, _dp, _dp, _dp, _dp, _dp]),
     "ipm_lincomb3_f64": (_i, [_i, _d, _dp, _d, _dp, _d, _dp, _dp, _dp]),
     "ipm_table_lookup_f64": (_i, [_dp, _i, _dp, _dp, _dp]),

@@ -77,8 +77,6 @@ class ConeNewton(LinearNewton):
         ws.Vc[0].fill_(1.0)
         self.guard = 1e-15 if self.phase1 else 1e-12  # Q5
         self.direct_trial = True
-        if self.update_slacks_every > 0:
-            raise NotImplementedError("update_slacks_every > 0 is not supported for second-order cones")
         self.tail_off = d.n_slacks
         nws = _abi.lib().ipm_gemv_t_ws_doubles(d.M, d.n, 2)
         if nws > ws.gt_ws_n:

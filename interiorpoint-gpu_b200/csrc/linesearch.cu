@@ -114,15 +114,18 @@ extern "C" int ipm_ls_feas_poly_f64(int count, const double* s0, const double* p
 __global__ void __launch_bounds__(1024, 1)
 ls_armijo_kernel(int nc, const double* __restrict__ s0, const double* __restrict__ p1,
                  const double* __restrict__ p2, const double* __restrict__ table, int len,
-                 const int* __restrict__ kmax_ptr, const double* __restrict__ sumlog_ptr,
+                 int* __restrict__ kmax_ptr, const double* __restrict__ sumlog_ptr,
                  const double* __restrict__ terms, double t, double alpha,
                  int update_slacks_every, const double* __restrict__ L_direct,
-                 const double* __restrict__ nneg, int textbook, double* __restrict__ out) {
+                 const double* __restrict__ nneg, int textbook, int resume, double* __restrict__ out) {
   __shared__ double red[32];
   __shared__ double bcast;
   const int kstuck = len - 1;
-  int k = *kmax_ptr;
-  if (k >= kstuck) {  // feasibility back-off ran out of steps (NewtonSolver.py:176-181)
+  // resume (direct-evaluation barriers with update_slacks_every > 0): the previous launch stopped at a refresh, left
+  // *kmax = index of the lagging point a_eval for the host's barrier evaluation and the attempt count in out[4]
+  int k = resume ? *kmax_ptr + 1 : *kmax_ptr;
+  if (resume) nneg = nullptr;
+  if (k >= kstuck && !resume) {  // feasibility back-off ran out of steps (NewtonSolver.py:176-181)
     if (threadIdx.x == 0) {
       out[0] = table[kstuck]; out[1] = 1.0; out[2] = (double)kstuck; out[3] = NAN; out[4] = 0.0;
     }
@@ -149,10 +152,11 @@ ls_armijo_kernel(int nc, const double* __restrict__ s0, const double* __restrict
   const double sumlog0 = *sumlog_ptr, obj0 = terms[0], dobj = terms[1], quad = terms[2];
   const double gx = textbook ? terms[4] : terms[3];
   const double fx = t * obj0 - sumlog0;
-  double a = table[k], a_eval = a;
+  double a = table[k], a_eval = resume ? table[k - 1] : a;
   double L = L_direct ? *L_direct : logsum(a_eval);
-  const double L_first = L;
-  int attempt = 0, stuck = 0;
+  const double L_first = resume ? out[3] : L;
+  int attempt = resume ? (int)out[4] : 0, stuck = 0;
+  __syncthreads();  // out[3] / out[4] read by everybody before thread 0 rewrites them
   while (true) {
     const double objv = obj0 + a_eval * dobj + 0.5 * a_eval * a_eval * quad;
     const double lhs = t * objv - L;
@@ -167,22 +171,28 @@ ls_armijo_kernel(int nc, const double* __restrict__ s0, const double* __restrict
       a_eval = a;
       L = logsum(a_eval);
     } else if (update_slacks_every > 0 && (attempt % update_slacks_every == update_slacks_every - 1)) {
+      if (L_direct) {  // the refreshed barrier term must come from a direct evaluation at x + a_eval dx: hand back
+        stuck = 4;
+        break;
+      }
       L = logsum(a_eval);
     }
   }
   if (threadIdx.x == 0) {
     out[0] = a; out[1] = (double)stuck; out[2] = (double)k; out[3] = L_first; out[4] = (double)attempt;
+    if (stuck == 4) *kmax_ptr = k - 1;
   }
 }
 
 extern "C" int ipm_ls_armijo_f64(int nc, const double* s0, const double* p1, const double* p2, const double* table,
-                                 int len, const int* kmax, const double* sumlog, const double* terms, double t,
+                                 int len, int* kmax, const double* sumlog, const double* terms, double t,
                                  double alpha, int update_slacks_every, const double* L_direct,
-                                 const double* nneg, int textbook, double* out, void* stream) {
-  if (nc < 0 || !table || len < 2 || !kmax || !sumlog || !terms || !out || (nc > 0 && (!s0 || !p1)))
+                                 const double* nneg, int textbook, int resume, double* out, void* stream) {
+  if (nc < 0 || !table || len < 2 || !kmax || !sumlog || !terms || !out || (nc > 0 && (!s0 || !p1)) ||
+      (resume && !L_direct))
     return IPM_ERR_ARG;
   ls_armijo_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(nc, s0, p1, p2, table, len, kmax, sumlog, terms, t, alpha,
-                                                        update_slacks_every, L_direct, nneg, textbook, out);
+                                                        update_slacks_every, L_direct, nneg, textbook, resume, out);
   IPM_LAUNCH_CHECK();
   return IPM_OK;
 }
@@ -193,19 +203,23 @@ extern "C" int ipm_ls_armijo_f64(int nc, const double* s0, const double* p1, con
 //   r0   = || [ g + A'v ; A x - b ] || = || [ r0d ; q0 ] ||
 //   while r(a) > (1 - alpha*a) * r0:  a <- next table entry (stop when it drops below 1e-13)
 //   out : [0] step  [1] stuck (0/1/2: 2 = stuck already in the feasibility back-off; 3 = trial point infeasible
-//         when evaluated directly (nneg > 0): raise kmax and retry)  [2] index
-//         [3] r0  [4] r(a) of the last evaluated trial
+//         when evaluated directly (nneg > 0): raise kmax and retry; 4 = update_slacks_every refresh due: *kmax holds the
+//         index whose barrier gradient the host must evaluate into u0, then call again with resume = 1)  [2] index
+//         [3] r0  [4] r(a) of the last evaluated trial  [5] attempts so far
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
 ls_residual_kernel(int n, int p, const double* __restrict__ r0d, const double* __restrict__ u0,
                    const double* __restrict__ u1, const double* __restrict__ q0, const double* __restrict__ q1,
-                   const double* __restrict__ table, int len, const int* __restrict__ kmax_ptr, double alpha,
-                   const double* __restrict__ nneg, double* __restrict__ out) {
+                   const double* __restrict__ table, int len, int* __restrict__ kmax_ptr, double alpha,
+                   const double* __restrict__ nneg, int update_slacks_every, int resume, double* __restrict__ out) {
   __shared__ double red[32];
   __shared__ double bcast;
   const int kstuck = len - 1;
   int k = *kmax_ptr;
-  if (k >= kstuck) {
+  int attempt = resume ? (int)out[5] : 0;
+  if (resume) nneg = nullptr;  // the refreshed point lies inside the step that was already verified
+  __syncthreads();
+  if (k >= kstuck && !resume) {
     if (threadIdx.x == 0) {
       out[0] = table[kstuck]; out[1] = 2.0; out[2] = (double)kstuck; out[3] = NAN; out[4] = NAN;
     }
@@ -245,23 +259,30 @@ ls_residual_kernel(int n, int p, const double* __restrict__ r0d, const double* _
   double rn = rnorm(a);
   int stuck = 0;
   while (rn > (1.0 - alpha * a) * r0) {
+    ++attempt;
     ++k;
     a = table[k];
     if (a < STUCK) { stuck = 1; break; }
+    if (update_slacks_every > 0 && attempt % update_slacks_every == update_slacks_every - 1) {
+      stuck = 4;  // the barrier gradient is re-evaluated at this trial point (NewtonSolverInfeasibleStart.py:249-255)
+      break;
+    }
     rn = rnorm(a);
   }
   if (threadIdx.x == 0) {
-    out[0] = a; out[1] = (double)stuck; out[2] = (double)k; out[3] = r0; out[4] = rn;
+    out[0] = a; out[1] = (double)stuck; out[2] = (double)k; out[3] = r0; out[4] = rn; out[5] = (double)attempt;
+    if (stuck == 4) *kmax_ptr = k;
   }
 }
 
 extern "C" int ipm_ls_residual_f64(int n, int p, const double* r0d, const double* u0, const double* u1,
                                    const double* q0, const double* q1, const double* table, int len,
-                                   const int* kmax, double alpha, const double* nneg, double* out, void* stream) {
+                                   int* kmax, double alpha, const double* nneg, int update_slacks_every, int resume,
+                                   double* out, void* stream) {
   if (n <= 0 || p < 0 || !r0d || !u0 || !u1 || !table || len < 2 || !kmax || !out || (p > 0 && (!q0 || !q1)))
     return IPM_ERR_ARG;
   ls_residual_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, p, r0d, u0, u1, q0, q1, table, len, kmax, alpha, nneg,
-                                                          out);
+                                                          update_slacks_every, resume, out);
   IPM_LAUNCH_CHECK();
   return IPM_OK;
 }

@@ -238,7 +238,13 @@ def option_cases():
     for src, extra, cls in (("lp_bounds_only_n50", dict(try_diag=False), LPSolver),
                             ("lp_dense_n64_warm", dict(update_slacks_every=3), LPSolver),
                             ("lp_dense_n64_cold", dict(update_slacks_every=2), LPSolver),
-                            ("socp_n48_warm", dict(use_psd_condition=True), SOCPSolver)):
+                            ("socp_n48_warm", dict(use_psd_condition=True), SOCPSolver),
+                            # update_slacks_every in the infeasible-start residual search
+                            # (NewtonSolverInfeasibleStart.py:249-255) and with second-order cones
+                            ("lp_seed1_n100_0", dict(update_slacks_every=2), LPSolver),
+                            ("qp_seed1_n100_0", dict(update_slacks_every=3), QPSolver),
+                            ("socp_n48_warm", dict(update_slacks_every=2), SOCPSolver),
+                            ("socp_n48_cold", dict(update_slacks_every=3), SOCPSolver)):
         b = base[src]
         tag = "_".join(f"{k}_{v}" for k, v in extra.items())
         out.append(run_barrier(cls, b["generator"], b["generator_kwargs"], b["index"], dict(b["settings"], **extra),

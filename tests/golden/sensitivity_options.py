@@ -26,18 +26,21 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import problems  # noqa: E402
-from oracle import OracleLP, OracleQP  # noqa: E402
+from oracle import OracleLP, OracleQP, OracleSOCP  # noqa: E402
 
 SEEDS = 12
 REL = 1e-14
-CLS = {"LPSolver": OracleLP, "QPSolver": OracleQP}
+CLS = {"LPSolver": OracleLP, "QPSolver": OracleQP, "SOCPSolver": OracleSOCP}
 
 
 def perturbed(prob, seed):
     p = dict(prob)
     if seed is not None:
         rs = np.random.RandomState(1000 + seed)
-        p["C"] = p["C"] * (1 + REL * rs.randn(*p["C"].shape))
+        if isinstance(p.get("A"), list):  # SOCP: the cone matrices
+            p["A"] = [Ai * (1 + REL * rs.randn(*Ai.shape)) for Ai in p["A"]]
+        else:
+            p["C"] = p["C"] * (1 + REL * rs.randn(*p["C"].shape))
     for k in ("x0",):
         if k in p:
             p[k] = p[k].copy()
@@ -48,6 +51,7 @@ def run(case, seed, duals=False):
     prob = getattr(problems, case["generator"])(**case["generator_kwargs"])
     if isinstance(prob, list):
         prob = prob[case.get("index") or 0]
+    np.random.seed(0)  # the default x0 of an unbounded SOCP is np.random.rand (SOCPSolver.py:166)
     s = CLS[case["solver"]](**perturbed(prob, seed), **case["settings"])
     val = s.solve()
     out = dict(value=float(val), inner_iters=list(s.inner_iters),

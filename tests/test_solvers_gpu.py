@@ -232,8 +232,8 @@ OPTIONS = load_golden("option_cases.json")
 
 @pytest.mark.parametrize("case", OPTIONS, ids=[c["name"] for c in OPTIONS])
 def test_constructor_options_match_reference(case):
-    """try_diag=False on a bounds-only LP, update_slacks_every > 0, use_psd_condition=True: objective to 1e-6 and Newton
-    counts +-2 against the golden.  For update_slacks_every > 0 the count bar is the envelope of the reference's own
+    """try_diag=False on a bounds-only LP, update_slacks_every > 0 (feasible start, infeasible start with equality
+    constraints, second-order cones), use_psd_condition=True: objective to 1e-6 and Newton counts +-2 against the golden.  For update_slacks_every > 0 the count bar is the envelope of the reference's own
     counts under a 1e-14 relative input perturbation (tests/golden/sensitivity_options.py: e.g. 22..50 for the first
     centering step of the cold case), widened by the same +-2 -- the golden's single list is one sample of it."""
     cls = _solver_class(case["solver"])
@@ -242,9 +242,12 @@ def test_constructor_options_match_reference(case):
     s = cls(**prob, check_cvxpy=False, suppress_print=True, **case["settings"])
     val = s.solve()
     print(case["name"], val, case["value"], s.inner_iters, case["inner_iters"])
-    assert val == pytest.approx(case["value"], rel=1e-6, abs=1e-9)
+    # the optimum to 1e-6 relative -- or to three times the spread of the reference's OWN optimum under a 1e-14 relative
+    # perturbation of its inputs where that is larger (lp_seed1_n100_0 with update_slacks_every=2: 7e-5 absolute)
+    spread = SENS.get(case["name"], {}).get("value_spread", 0.0)
+    assert val == pytest.approx(case["value"], rel=1e-6, abs=max(1e-9, 3 * spread))
     x = np.asarray(s.xstar)
-    assert np.linalg.norm(x - np.array(case["xstar"])) <= 1e-4 * (1 + np.linalg.norm(case["xstar"]))
+    assert np.linalg.norm(x - np.array(case["xstar"])) <= (1e-4 + 30 * spread) * (1 + np.linalg.norm(case["xstar"]))
     if case["name"] in SENS:
         env = SENS[case["name"]]
         assert_iters_in_envelope(s.inner_iters, env["inner_iters"])
