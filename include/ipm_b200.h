@@ -114,6 +114,19 @@ int ipm_vec_op_f64(int op, int n, const double* a, const double* b, double* out,
 int ipm_scale_shift_f64(const double* in, int ldi, double* out, int ldo, int rows, int cols, double s, double dshift,
                         void* stream);
 
+/* ---- conjugate-gradient Newton solves (linear_solve_method="cg") ----------------------------------------- */
+/* scipy.sparse.linalg.cg semantics (rtol on ||b||, at most maxiter steps, last iterate returned) for (sign*H) x = b with
+ * H dense symmetric; no host synchronisation (the scalars and the convergence flag stay on the device).
+ * NewtonSolverCG NewtonSolver.py:365-400: cg(-H, gradf, x0, maxiter); PhaseOne.py:137-150: cg(hess, -grad, x0=[x, s]). */
+int ipm_symmetrize_upper_f64(double* H, int ld, int n, void* stream);   /* H[j][i] = H[i][j], j > i */
+long long ipm_cg_ws_doubles(int n);
+/* x0 = (x.g < 0) ? -(x.g) x / (x.Hx) : 0 and Hx0 = H x0 (NewtonSolver.py:379-383); Hx = H x from ipm_gemv_n_f64. */
+int ipm_cg_descent_x0_f64(int n, const double* x, const double* g, const double* Hx, double* x0, double* Hx0,
+                          void* stream);
+/* x: x0 in / solution out; Hx0: H x0 or NULL for x0 = 0; ws[3n+2] != 0 when converged, ws[3n+3] = iterations. */
+int ipm_cg_solve_f64(const double* H, int ld, int n, const double* b, double* x, const double* Hx0, double sign,
+                     int maxiter, double rtol, double* ws, void* stream);
+
 /* ---- factorisation and triangular solves ---------------------------------------------------------------- */
 /* In-place H = U^T U on the upper triangle; *info_dev (device int) = 0 or the 1-based index of the first
  * non-positive pivot.  Uses a library-owned high-priority side stream for the panel chain (joined before return).  scipy.linalg.cho_factor / cp.linalg.cholesky NewtonSolver.py:286,303;

@@ -89,7 +89,8 @@ class LPSolver(BarrierSolverBase):
             raise ValueError("LP without inequality constraints or bounds has no barrier Hessian")
         self.ns = newton_cls(self.data, phase1=False, max_iters=max_inner_iters, epsilon=inner_epsilon, alpha=alpha,
                                beta=beta, update_slacks_every=update_slacks_every, diagonal=diagonal,
-                               launcher=self.launcher)
+                               launcher=self.launcher, max_cg_iters=max_cg_iters,
+                               linear_solver="cg" if linear_solve_method == "cg" else "cholesky")
 
     def _cvxpy_precheck(self):
         """Optional CVXPY/Clarabel feasibility pre-check (LPSolver.py:471-505); skipped when cvxpy is absent."""

@@ -2,8 +2,8 @@
 B200 engine: find a strictly interior point of ``G x <= h`` by minimising s subject to ``G x - h <= s``.
 
 Differences in mechanism, not in contract: the Newton system ``(H + 0.01 I) d = -g`` (PhaseOne.py:120-134) is
-solved with the engine's Cholesky (the matrix is SPD) instead of ``numpy.linalg.solve``; ``linear_solver="cg"`` is
-accepted and mapped to the same direct solve.  The line search is the reference's plain Armijo rule
+solved with the engine's Cholesky (the matrix is SPD) instead of ``numpy.linalg.solve``; ``linear_solver="cg"`` runs
+conjugate gradients on the device with the reference's start vector ``[x, s]`` and iteration cap (PhaseOne.py:137-150).  The line search is the reference's plain Armijo rule
 (PhaseOne.py:187-218: slope ``g.d``, alpha 0.2, beta 0.7, barrier re-evaluated at every trial)."""
 
 import numpy as np
@@ -35,7 +35,8 @@ class PhaseOneSolver:
         self.m, self.n = m, n
         device = torch.device("cuda", torch.cuda.current_device())
         self.data = LinearProblemData(n, device, C=G, d=np.asarray(h, dtype=np.float64).ravel())
-        self.ns = LinearNewton(self.data, phase1=True, max_iters=max_iter_newton, epsilon=eps, alpha=0.2, beta=0.7)
+        self.ns = LinearNewton(self.data, phase1=True, max_iters=max_iter_newton, epsilon=eps, alpha=0.2, beta=0.7,
+                               linear_solver="cg" if linear_solver == "cg" else "cholesky", max_cg_iters=max_cg_iters)
         self.ns.shift = 0.01  # "some conditioning", PhaseOne.py:123-127
         self.z = torch.zeros(n + 1, dtype=F64, device=device)
         self.z[:n].copy_(torch.as_tensor(np.ones(n) if x0 is None else np.asarray(x0, dtype=np.float64)))
@@ -98,9 +99,18 @@ class PhaseOneSolver:
             ns._eval(z, ws.cur)
             ns._gradient(t, None, ws.cur, ws.g, want_border=True)
             ns._hessian(t)
-            ns._factor()
-            L("ipm_lincomb3_f64", ns.nz, -1.0, ws.g.data_ptr(), 0.0, None, 0.0, None, ws.dz.data_ptr())
-            ns._chol_solve_vec(ws.dz)
+            if self.solver == "cg":
+                # spcg(hess, -grad, x0=[x, s], maxiter=max_cg_iters)  (PhaseOne.py:143-150)
+                L("ipm_symmetrize_upper_f64", ws.H.data_ptr(), ws.ldh, ns.nz)
+                L("ipm_gemv_n_f64", ws.H.data_ptr(), ws.ldh, ns.nz, ns.nz, z.data_ptr(), ws.cg_hx0.data_ptr(), 1.0, 0.0)
+                L("ipm_lincomb3_f64", ns.nz, -1.0, ws.g.data_ptr(), 0.0, None, 0.0, None, ws.gtrial.data_ptr())
+                ws.dz.copy_(z)
+                L("ipm_cg_solve_f64", ws.H.data_ptr(), ws.ldh, ns.nz, ws.gtrial.data_ptr(), ws.dz.data_ptr(),
+                  ws.cg_hx0.data_ptr(), 1.0, self.max_iter_cg, 1e-5, ws.cg_ws.data_ptr())
+            else:
+                ns._factor()
+                L("ipm_lincomb3_f64", ns.nz, -1.0, ws.g.data_ptr(), 0.0, None, 0.0, None, ws.dz.data_ptr())
+                ns._chol_solve_vec(ws.dz)
             pairs = ns._objective_pairs(z, None) + [(ws.g, z, ns.nz), (ws.g, ws.dz, ns.nz)]
             ns._dots(pairs)
             lam_sq = -ns._read_terms(5)[4]

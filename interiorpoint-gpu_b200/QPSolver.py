@@ -75,7 +75,9 @@ class QPSolver(BarrierSolverBase):
                 update_slacks_every=update_slacks_every, _data=self.data, _launcher=self.launcher,
                 _newton_cls=newton_cls)
         self.ns = newton_cls(self.data, phase1=False, max_iters=max_inner_iters, epsilon=inner_epsilon, alpha=alpha,
-                               beta=beta, update_slacks_every=update_slacks_every, launcher=self.launcher)
+                               beta=beta, update_slacks_every=update_slacks_every, launcher=self.launcher,
+                               max_cg_iters=max_cg_iters,
+                               linear_solver="cg" if linear_solve_method == "cg" else "cholesky")
 
     def _objective_value(self, x):
         return self.ns.qp_objective(x)

@@ -142,7 +142,8 @@ class SOCPSolver(BarrierSolverBase):
             update_slacks_every=update_slacks_every, _data=self.data, _launcher=self.launcher)
         self.ns = newton_cls(self.data, phase1=False, max_iters=max_inner_iters, epsilon=inner_epsilon, alpha=alpha,
                              beta=beta, use_psd_condition=use_psd_condition, update_slacks_every=update_slacks_every,
-                             launcher=self.launcher)
+                             launcher=self.launcher, max_cg_iters=max_cg_iters,
+                             linear_solver="cg" if linear_solve_method == "cg" else "cholesky")
 
     def _objective_value(self, x):
         if self.P is not None:

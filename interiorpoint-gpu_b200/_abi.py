@@ -39,6 +39,10 @@ SIGNATURES = {
     "ipm_sparse_syrk_f64": (_i, [_i, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp]),
     "ipm_dots_f64": (_i, [_i, C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_i), _dp, _dp]),
     "ipm_axpy_dev_f64": (_i, [_i, _dp, _dp, _dp, _dp]),
+    "ipm_symmetrize_upper_f64": (_i, [_dp, _i, _i, _dp]),
+    "ipm_cg_ws_doubles": (_ll, [_i]),
+    "ipm_cg_descent_x0_f64": (_i, [_i, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "ipm_cg_solve_f64": (_i, [_dp, _i, _i, _dp, _dp, _dp, _d, _i, _d, _dp, _dp]),
     "ipm_potrf_upper_f64": (_i, [_dp, _i, _i, _dp, _dp]),
     "ipm_potrf_upper_dag_f64": (_i, [_dp, _i, _i, _dp, _dp]),
     "ipm_potrf_peer_prog_words": (_i, []),

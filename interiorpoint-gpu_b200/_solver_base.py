@@ -100,13 +100,16 @@ class BarrierSolverBase:
     def _check_method(method, equality_constrained):
         """Newton-class dispatch of the reference (LPSolver.py:371-448).  Every direct method solves the same SPD
         system; the device engine implements them with its Cholesky kernels.  ``cg`` for equality-constrained
-        problems raises NotImplementedError in the reference too (NewtonSolverInfeasibleStart.py:604)."""
+        problems raises NotImplementedError in the reference too (NewtonSolverInfeasibleStart.py:604); without equality
+        constraints it selects the device CG (engine.LinearNewton._cg_direction, NewtonSolver.py:365-400)."""
         if method not in ("cholesky", "np_solve", "np_lstsq", "direct", "cg", "kkt"):
             raise ValueError("Please enter a valid linear solve method!")
         if method == "kkt" and not equality_constrained:
             raise ValueError("No KKT System non-equality-constrained problems! Please choose another solver")
-        if method == "cg":
-            raise NotImplementedError("conjugate-gradient Newton solves are not part of the B200 engine")
+        if method == "cg" and equality_constrained:
+            # NewtonSolverCGInfeasibleStart / ...Diagonal...: NewtonSolverInfeasibleStart.py:604,874
+            raise NotImplementedError("conjugate-gradient Newton solves are not implemented for equality-constrained "
+                                      "problems (neither in the reference)")
 
     # -- helpers on the device -------------------------------------------------------------------------
     def _objective_value(self, x):

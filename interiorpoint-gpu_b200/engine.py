@@ -265,7 +265,8 @@ class LinearNewton:
     method with block elimination."""
 
     def __init__(self, data, phase1=False, max_iters=50, epsilon=1e-5, alpha=0.2, beta=0.6, phase1_tol=0.1,
-                 use_psd_condition=False, update_slacks_every=0, diagonal=False, launcher=None):
+                 use_psd_condition=False, update_slacks_every=0, diagonal=False, launcher=None,
+                 linear_solver="cholesky", max_cg_iters=50):
         self.d = data
         self.phase1 = phase1
         self.nz = data.n + (1 if phase1 else 0)
@@ -275,6 +276,12 @@ class LinearNewton:
         self.update_slacks_every = update_slacks_every
         self.diagonal = diagonal
         self.equality = (data.A is not None) and not phase1
+        # "cg": the reference's NewtonSolverCG (NewtonSolver.py:365-400) -- at most max_cg_iters conjugate-gradient steps
+        # on (-H) dx = g instead of a factorisation (feasible start only; the reference's equality-constrained CG classes
+        # raise NotImplementedError, NewtonSolverInfeasibleStart.py:604,874)
+        self.linear_solver, self.max_cg_iters = linear_solver, max_cg_iters
+        if linear_solver == "cg" and self.equality:
+            raise NotImplementedError("conjugate gradients are not implemented for equality-constrained problems")
         self.L = launcher or Launcher(data.device)
         self.ws = NewtonWorkspace(data, self.nz)
         tab = step_table(beta)
@@ -286,6 +293,10 @@ class LinearNewton:
         self.shift = 0.0
         self.newton_steps = 0
         self.trace = None
+        if linear_solver == "cg":
+            zf = lambda k: torch.zeros(k, dtype=F64, device=data.device)  # noqa: E731
+            self.ws.cg_hx, self.ws.cg_hx0 = zf(self.nz), zf(self.nz)
+            self.ws.cg_ws = zf(_abi.lib().ipm_cg_ws_doubles(self.nz))
 
     # ---------------------------------------------------------------- barrier pieces
     def set_t(self, t):
@@ -397,6 +408,18 @@ class LinearNewton:
         """Quadratic line-search coefficients (second-order cones only)."""
         return None
 
+    def _cg_direction(self, z):
+        """dz = cg(-H, g, x0, maxiter=max_cg_iters) with x0 = -(x.g) x / (x.Hx) if x.g < 0 else 0 (NewtonSolver.py:376-398).
+        All of it stays on the device: no read-back until the line search."""
+        ws, L, nz = self.ws, self.L, self.nz
+        L("ipm_symmetrize_upper_f64", ws.H.data_ptr(), ws.ldh, nz)
+        L("ipm_gemv_n_f64", ws.H.data_ptr(), ws.ldh, nz, nz, z.data_ptr(), ws.cg_hx.data_ptr(), 1.0, 0.0)
+        L("ipm_cg_descent_x0_f64", nz, z.data_ptr(), ws.g.data_ptr(), ws.cg_hx.data_ptr(), ws.dz.data_ptr(),
+          ws.cg_hx0.data_ptr())
+        L("ipm_cg_solve_f64", ws.H.data_ptr(), ws.ldh, nz, ws.g.data_ptr(), ws.dz.data_ptr(), ws.cg_hx0.data_ptr(), -1.0,
+          self.max_cg_iters, 1e-5, ws.cg_ws.data_ptr())
+        ws.info.zero_()
+
     def _factor(self):
         """ws.H (upper) <- U with H = U'U; ws.info[0] = LAPACK-style info (NewtonSolver.py:286,303)."""
         ws = self.ws
@@ -489,6 +512,9 @@ class LinearNewton:
         if self.diagonal:
             # bounds-only LP: H is diagonal, dx = -g / h (NewtonSolver.py:415-420)
             L("ipm_vec_op_f64", 1, d.n, ws.g.data_ptr(), ws.hdiag.data_ptr(), ws.dz.data_ptr(), -1.0)
+        elif self.linear_solver == "cg":
+            self._hessian(t)
+            self._cg_direction(z)
         else:
             self._hessian(t)
             self._factor()

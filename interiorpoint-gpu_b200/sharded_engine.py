@@ -38,7 +38,7 @@ class _RowSharded:
         # Equality constraints (infeasible-start method, NewtonSolverInfeasibleStart.py:386-511): the equality rows A, the
         # dual iterate and the block elimination (TRSM of A', Schur complement, its factorisation) are replicated; only the
         # barrier pieces -- slacks, gradient, Hessian, feasibility back-off -- are sharded, through the same overrides.
-        if self.update_slacks_every > 0 or self.diagonal:
+        if self.update_slacks_every > 0 or self.diagonal or self.linear_solver != "cholesky":
             raise NotImplementedError("row sharding supports the default dense Cholesky path only")
         self.group = group
         self.rank = dist.get_rank(group)

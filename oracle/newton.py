@@ -16,6 +16,7 @@ and the infeasible-start search re-uses stale reciprocal slacks.
 
 import numpy as np
 import scipy.linalg
+import scipy.sparse.linalg
 
 STUCK = 1e-13  # NewtonSolver.py:176,189 ; NewtonSolverInfeasibleStart.py:186,242
 
@@ -23,7 +24,7 @@ STUCK = 1e-13  # NewtonSolver.py:176,189 ; NewtonSolverInfeasibleStart.py:186,24
 class FeasibleNewton:
     def __init__(self, barrier, max_iters=50, epsilon=1e-5, alpha=0.2, beta=0.6, phase1_flag=False,
                  phase1_tol=0.1, use_psd_condition=False, update_slacks_every=0, diagonal=False,
-                 trace=None):
+                 trace=None, linear_solver="cholesky", max_cg_iters=50):
         self.fm = barrier
         self.max_iters, self.eps = max_iters, epsilon
         self.alpha, self.beta = alpha, beta
@@ -33,12 +34,17 @@ class FeasibleNewton:
         self.diagonal = diagonal
         self.use_backup = False  # sticky lstsq fallback, NewtonSolver.py:314-341
         self.trace = trace  # optional list collecting (step_size, decrement) per Newton step
+        self.linear_solver, self.max_cg_iters = linear_solver, max_cg_iters  # "cg": NewtonSolverCG, NewtonSolver.py:365-400
 
     # -- linear solve ------------------------------------------------------------------------------
-    def direction(self, g):
+    def direction(self, g, x=None):
         if self.diagonal:  # NewtonSolver.py:415-420
             return -self.fm.inv_hessian_diag() * g
         H = self.fm.hessian()
+        if self.linear_solver == "cg":  # NewtonSolver.py:374-400
+            dc = np.dot(x, g)
+            x0 = -dc * x / np.dot(x, np.dot(H, x)) if dc < 0 else np.zeros_like(x)
+            return scipy.sparse.linalg.cg(-H, g, x0=x0, maxiter=self.max_cg_iters)[0]
         if not self.use_backup:
             try:
                 if self.use_psd_condition:  # NewtonSolver.py:269-275
@@ -88,7 +94,7 @@ class FeasibleNewton:
             for it in range(self.max_iters):
                 fm.move(x)
                 g = fm.gradient()
-                dx = self.direction(g)
+                dx = self.direction(g, x)
                 a = self.backtrack(x, dx, g)
                 x += a * dx
                 fm.move(x)

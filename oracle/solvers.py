@@ -98,7 +98,9 @@ class _BarrierSolver:
                                     update_slacks_every=self.update_slacks_every, diagonal=diagonal, trace=tr)
         return FeasibleNewton(self.fm, max_iters=self.max_inner_iters, epsilon=self.inner_epsilon, alpha=self.alpha,
                               beta=self.beta, use_psd_condition=self.use_psd_condition,
-                              update_slacks_every=self.update_slacks_every, diagonal=diagonal, trace=tr)
+                              update_slacks_every=self.update_slacks_every, diagonal=diagonal, trace=tr,
+                              linear_solver="cg" if getattr(self, "linear_solve_method", "") == "cg" else "cholesky",
+                              max_cg_iters=getattr(self, "max_cg_iters", 50))
 
     def solve(self, t0=None, max_outer_iters=None):
         t = self.t0 if t0 is None else t0
@@ -157,7 +159,8 @@ class OracleLP(_BarrierSolver):
     def __init__(self, c=None, A=None, b=None, C=None, d=None, lower_bound=0, upper_bound=None, t0=0.1,
                  max_outer_iters=20, max_inner_iters=50, phase1_max_inner_iters=500, epsilon=1e-10,
                  inner_epsilon=1e-5, alpha=0.2, beta=0.6, mu=15, try_diag=True, phase1_tol=0, phase1_t0=0.01,
-                 x0=None, update_slacks_every=0, trace=None):
+                 x0=None, update_slacks_every=0, trace=None, linear_solve_method="cholesky", max_cg_iters=50):
+        self.linear_solve_method, self.max_cg_iters = linear_solve_method, max_cg_iters  # "cg": LPSolver.py:412-420
         n = len(c) if c is not None else (A.shape[1] if A is not None else C.shape[1])
         self._common(n, lower_bound, upper_bound, t0, max_outer_iters, max_inner_iters, phase1_max_inner_iters,
                      epsilon, inner_epsilon, alpha, beta, mu, phase1_tol, phase1_t0, x0, update_slacks_every, False,

@@ -306,6 +306,18 @@ def lasso_full_size():
         json.dump(rec, f, indent=1)
 
 
+def cg_cases():
+    """linear_solve_method="cg" (NewtonSolverCG, NewtonSolver.py:365-400: at most max_cg_iters = 50 conjugate-gradient
+    steps per Newton system) on feasible-start LPs; phase-I stays on the Cholesky class (PhaseOneSolver.py:91-110)."""
+    out = []
+    for gen_kwargs, name in ((dict(seed=0, n=64, warm=True), "lp_dense_n64_warm_cg"),
+                             (dict(seed=0, n=64), "lp_dense_n64_cold_cg"),
+                             (dict(seed=0, n=256, warm=True), "lp_dense_n256_warm_cg")):
+        out.append(run_barrier(LPSolver, "lp_dense_family", gen_kwargs, None, dict(linear_solve_method="cg"), name))
+    with open(os.path.join(HERE, "cg_cases.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 def large_cases():
     """BASELINE cfg-2 family at n = 1024 and n = 2048 (cold and warm) and the cfg-3 family at n = 2048 (p = 512 equalities,
     k = 64 inequalities: the n = 8192, p = 2048, k = 20 shape of tests/test_fullsize_gpu.py scaled down 4x), constructor
@@ -323,6 +335,9 @@ def large_cases():
 
 
 def main():
+    if "--cg-only" in sys.argv:
+        cg_cases()
+        return
     if "--lasso-full-only" in sys.argv:
         lasso_full_size()
         return

@@ -75,6 +75,8 @@ def main():
     out = {"relative_perturbation": REL, "perturbed_runs": SEEDS, "cases": {}}
     with open(os.path.join(HERE, "option_cases.json")) as f:
         options = [c for c in json.load(f) if "update_slacks_every" in c["settings"]]
+    with open(os.path.join(HERE, "cg_cases.json")) as f:  # NewtonSolverCG: 50 CG steps on Hessians with cond > 1e12
+        options += json.load(f)
     for case in options:
         runs = [run(case, None)] + [run(case, sd) for sd in range(SEEDS)]
         assert runs[0]["inner_iters"] == case["inner_iters"], "oracle no longer reproduces the golden"

@@ -79,6 +79,7 @@ def test_method_dispatch_rules():
         chk("kkt", False)
     with pytest.raises(ValueError, match="valid linear solve"):  # LPSolver.py:447-448
         chk("qr", False)
+    chk("cg", False)  # NewtonSolverCG (NewtonSolver.py:365-400): implemented on the device (csrc/cg.cu)
     with pytest.raises(NotImplementedError):  # NewtonSolverInfeasibleStart.py:604
         chk("cg", True)
 

@@ -122,6 +122,26 @@ def test_phase_one_high_dimension(make):
     np.testing.assert_allclose(x, case["x"], rtol=1e-5, atol=1e-6)
 
 
+CG_POLYTOPES = [c for c in KAT if "G" in c and c["linear_solver"] == "cg"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CG_POLYTOPES, ids=[c["name"] for c in CG_POLYTOPES])
+def test_phase_one_polytopes_cg_device(case):
+    """linear_solver="cg" on the device (csrc/cg.cu: SciPy's CG with x0 = [x, s], PhaseOne.py:143-150) against what the
+    real class returned with its CG arm: same verdict, same point."""
+    G, h = np.array(case["G"], dtype=float), np.array(case["h"], dtype=float)
+    x, sv, warn = _device(G, h, case["mu"], x0=case["x0"], linear_solver="cg").solve()
+    x = np.asarray(x)
+    if case["name"].startswith("ref_empty"):
+        assert sv > 0
+    else:
+        assert sv < 0 and np.max(G @ x - h) <= 0
+    assert warn == case["warn"]
+    assert sv == pytest.approx(case["s"], rel=1e-5, abs=1e-8)
+    np.testing.assert_allclose(x, case["x"], rtol=1e-5, atol=1e-7)
+
+
 def test_reference_cg_variant_agrees_with_solve():
     """The reference's ``linear_solver="cg"`` runs (same file, :392-422) end at the same point as ``"solve"`` to the
     accuracy below (recorded from the real class): the basis for comparing a CG-based device run with these goldens."""

@@ -1,13 +1,12 @@
 #!/bin/bash
-# One gpurun call of round 2:  gpurun --timeout 1500 -- 'bash tools/gpu_call.sh > gpurun_out/call.log 2>&1'
+# One gpurun call of round 2 (2 GPUs):  gpurun --gpus 2 --timeout 1800 -- 'bash tools/gpu_call.sh > gpurun_out/call.log 2>&1'
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -m gpu > gpurun_out/pytest_default.log 2>&1; echo "pytest default rc=$?"
-tail -30 gpurun_out/pytest_default.log
-IPM_POTRF_DAG=1 timeout 900 python -m pytest tests -q -m gpu > gpurun_out/pytest_dag.log 2>&1; echo "pytest dag rc=$?"
+nvidia-smi -L
+timeout 1200 python -m pytest tests -q -m gpu > gpurun_out/pytest_default.log 2>&1; echo "pytest default rc=$?"
+tail -40 gpurun_out/pytest_default.log
+IPM_POTRF_DAG=1 timeout 600 python -m pytest tests -q -m gpu -k "not sharded" > gpurun_out/pytest_dag.log 2>&1; echo "pytest dag rc=$?"
 tail -15 gpurun_out/pytest_dag.log
-timeout 600 python bench.py --steps 1 --warmup 1 --sections qp --no-e2e --no-cpu-baseline > gpurun_out/bench_call5.json 2> gpurun_out/bench_call5.err; echo "bench rc=$?"
-cat gpurun_out/bench_call5.json; tail -30 gpurun_out/bench_call5.err
-timeout 600 python tools/lib_context.py > gpurun_out/lib_context.json 2> gpurun_out/lib_context.err; echo "lib_context rc=$?"
-cat gpurun_out/lib_context.json; tail -5 gpurun_out/lib_context.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 2 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "bench n2 rc=$?"
+cat gpurun_out/bench_n2.json; tail -30 gpurun_out/bench_n2.err
