@@ -93,7 +93,7 @@ class _RowSharded:
         if int(ok.item()) == 1:
             self.peer = st
             self.ws.H = st["H"]  # the factorisation runs in the peer-mapped buffer the owners write into
-            self.ws.info = st["info"]
+            self.ws.info = st["info"][:2]  # same layout as the engine's own info pair
             # block columns of the factorisation dealt over the ranks (csrc/chol.cu, struct dag::Peers);
             # IPM_PEER_POTRF=0 keeps the factorisation replicated
             self.peer_potrf = os.environ.get("IPM_PEER_POTRF", "1") != "0" and self.nz > 384

@@ -53,11 +53,23 @@ def _run(name):
     q = ctx.Queue()
     port = 29600 + os.getpid() % 1000
     procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q)) for r in range(2)]
+    import queue
+    import time
+
     for p in procs:
         p.start()
-    out = q.get(timeout=300)
+    out, t0 = None, time.time()
+    while out is None:
+        try:
+            out = q.get(timeout=2)
+        except queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            if dead or time.time() - t0 > 240:  # a crashed rank must not cost the whole timeout
+                for p in procs:
+                    p.kill()
+                pytest.fail(f"worker exit codes {[p.exitcode for p in procs]} after {time.time() - t0:.0f} s")
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=60)
         assert p.exitcode == 0
     return out
 
