@@ -71,8 +71,34 @@ def envelope(runs, key):
     return dict(min=a.min(axis=0).tolist(), max=a.max(axis=0).tolist())
 
 
+LARGE_QP = {"qp_dense_n1024": 8, "qp_dense_n2048": 4}  # case -> perturbed runs (minutes of CPU each at n = 2048)
+
+
+def large_qp(out):
+    """The equality-constrained large cases: their late centering steps stop on a residual norm that sits at the rounding
+    noise of t * grad f0 + A'v (tests/test_solvers_gpu.py: noise_dominated_steps), and the reference's own counts move by
+    up to 4 there.  `--large` recomputes these entries; without it the previous ones are kept."""
+    with open(os.path.join(HERE, "large_cases.json")) as f:
+        cases = {c["name"]: c for c in json.load(f)}
+    for name, seeds in LARGE_QP.items():
+        case = cases[name]
+        runs = [run(case, None)] + [run(case, sd) for sd in range(seeds)]
+        assert runs[0]["inner_iters"] == case["inner_iters"], "oracle no longer reproduces the golden"
+        out["cases"][name] = dict(inner_iters=envelope(runs, "inner_iters"),
+                                  phase1_inner_iters=envelope(runs, "phase1_inner_iters"), perturbed_runs=seeds,
+                                  value_spread=float(max(abs(r["value"] - runs[0]["value"]) for r in runs)))
+        print(name, out["cases"][name])
+
+
 def main():
     out = {"relative_perturbation": REL, "perturbed_runs": SEEDS, "cases": {}}
+    path = os.path.join(HERE, "sensitivity.json")
+    if "--large" in sys.argv:
+        large_qp(out)
+    elif os.path.exists(path):
+        with open(path) as f:
+            old = json.load(f)["cases"]
+        out["cases"].update({k: v for k, v in old.items() if k in LARGE_QP})
     with open(os.path.join(HERE, "option_cases.json")) as f:
         options = [c for c in json.load(f) if "update_slacks_every" in c["settings"]]
     with open(os.path.join(HERE, "cg_cases.json")) as f:  # NewtonSolverCG: 50 CG steps on Hessians with cond > 1e12
