@@ -280,8 +280,13 @@ def test_large_cases_match_reference(case):
     val = s.solve()
     print(case["name"], val, case["value"], s.inner_iters, case["inner_iters"])
     assert val == pytest.approx(case["value"], rel=1e-6, abs=1e-9)
-    assert_iters_close(s.inner_iters, case["inner_iters"], cap=s.max_inner_iters,
-                       noisy=noise_dominated_steps(case, prob, case["settings"]))
+    if case["name"] in SENS:
+        # equality-constrained: the late centering steps stop on a residual at the rounding noise of t grad f0 + A'v and the
+        # reference's own counts move by up to 4 under a 1e-14 perturbation (sensitivity.json) -> its envelope +-2
+        assert_iters_in_envelope(s.inner_iters, SENS[case["name"]]["inner_iters"], cap=s.max_inner_iters)
+    else:
+        assert_iters_close(s.inner_iters, case["inner_iters"], cap=s.max_inner_iters,
+                           noisy=noise_dominated_steps(case, prob, case["settings"]))
     if case["phase1_inner_iters"] is not None:
         assert_iters_close(s.phase1_solver.inner_iters, case["phase1_inner_iters"])
     x = np.asarray(s.xstar)

@@ -1,9 +1,10 @@
 #!/bin/bash
-# One gpurun call of round 2 (2 GPUs):  gpurun --gpus 2 --timeout 900 -- 'bash tools/gpu_call.sh > gpurun_out/call.log 2>&1'
+# One gpurun call of round 2 (8 GPUs):  gpurun --gpus 8 --timeout 700 -- 'bash tools/gpu_call.sh > gpurun_out/call.log 2>&1'
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 420 python -m pytest tests/test_sharded_gpu.py -q -x > gpurun_out/pytest_sharded.log 2>&1; echo "pytest sharded rc=$?"
-tail -40 gpurun_out/pytest_sharded.log
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 1 --sections socp,lasso,replicas > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "bench n2 rc=$?"
-cat gpurun_out/bench_n2.json; grep -v "^\s*$" gpurun_out/bench_n2.err | grep -v Warning | tail -25
+N=$(nvidia-smi -L | wc -l)
+timeout 330 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 2 --warmup 1 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench n$N rc=$?"
+cat gpurun_out/bench_n$N.json; grep -v "^\s*$" gpurun_out/bench_n$N.err | grep -v Warning | tail -15
+IPM_PEER_POTRF=0 timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 2 --warmup 1 --sections none --no-e2e > gpurun_out/bench_n${N}_replicated_potrf.json 2> gpurun_out/bench_n${N}_replicated_potrf.err; echo "bench replicated rc=$?"
+cat gpurun_out/bench_n${N}_replicated_potrf.json; grep -v "^\s*$" gpurun_out/bench_n${N}_replicated_potrf.err | grep -v Warning | tail -8
