@@ -729,6 +729,10 @@ struct Peers {
   int R, me;
 };
 
+struct EmuMaps {
+  CUtensorMap m[kMaxRanks];  // tensor map of every emulated rank's matrix copy (emulation mode only)
+};
+
 __device__ __forceinline__ int column_progress_sys(const unsigned long long* p, unsigned epoch) {
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -865,24 +869,57 @@ __device__ __forceinline__ void store_rows(const double* __restrict__ S, double*
   }
 }
 
-// The same rows into every rank's copy of the matrix (R == 1: the local one).
+// Distributed factorisation: the finished rows go into every rank's copy of the matrix.  One SM stores to a peer at only
+// ~15 GB/s (measured: a 32-row step to 7 peers, 224 KB, took ~15 us and put ~200 us per block row on the dependent chain
+// when all copies were stored before anything was published), so the copies are served in order of urgency, in two
+// groups with one system fence each:  group 1 = the local copy and the copy of rank `first` -- the owner of the task
+// that consumes these rows next on the dependent chain -- published at once;  group 2 = the other ranks, after the
+// caller's own next piece of work.
 template <bool UPPER>
-__device__ __forceinline__ void store_rows_all(const Peers& pr, const double* __restrict__ S, double* __restrict__ G,
-                                               long long ld, int r_begin, int nrows, int ncols) {
-  if (pr.R == 1) {
-    store_rows<UPPER>(S, G, ld, r_begin, nrows, ncols);
-    return;
+__device__ __forceinline__ void store_rows_urgent(const Peers& pr, int me, int first, const double* __restrict__ S,
+                                                  double* __restrict__ G, long long ld, int r_begin, int nrows,
+                                                  int ncols) {
+  store_rows<UPPER>(S, G, ld, r_begin, nrows, ncols);
+  if (pr.R > 1 && first != me) store_rows<UPPER>(S, pr.H[first] + (G - pr.H[me]), ld, r_begin, nrows, ncols);
+}
+// after the caller's fence + CTA barrier (thread 0 only)
+__device__ __forceinline__ void publish_urgent(const Peers& pr, int me, int first, unsigned long long* prog, int idx,
+                                               unsigned epoch, int count) {
+  publish(prog + idx, epoch, count);
+  if (pr.R > 1 && first != me) {
+    const unsigned long long v = ((unsigned long long)epoch << 32) | (unsigned)count;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pr.prog[first] + idx), "l"(v) : "memory");
   }
-  const long long off = G - pr.H[pr.me];
-  for (int r = 0; r < pr.R; ++r) store_rows<UPPER>(S, pr.H[(r + pr.me) % pr.R] + off, ld, r_begin, nrows, ncols);
+}
+// group 2: every rank except this one and `first`; ends with a CTA barrier (all threads call it)
+template <bool UPPER>
+__device__ __forceinline__ void push_rest(const Peers& pr, int me, int first, const double* __restrict__ S,
+                                          double* __restrict__ G, long long ld, int r_begin, int nrows, int ncols, int idx,
+                                          unsigned epoch, int count) {
+  if (pr.R <= 2 && (pr.R == 1 || first != me)) return;  // nobody left
+  const long long off = G - pr.H[me];
+  for (int r = 1; r < pr.R; ++r) {
+    const int dest = (me + r) % pr.R;
+    if (dest != first) store_rows<UPPER>(S, pr.H[dest] + off, ld, r_begin, nrows, ncols);
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long v = ((unsigned long long)epoch << 32) | (unsigned)count;
+    for (int r = 1; r < pr.R; ++r) {
+      const int dest = (me + r) % pr.R;
+      if (dest != first)
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pr.prog[dest] + idx), "l"(v) : "memory");
+    }
+  }
 }
 
 // Diagonal task: potf2 of the tile in S, publishing every 32-row step (rows final after the pivot block and its row
 // panel) before the trailing update of the step.
-__device__ __forceinline__ void potf2_pipelined(const Peers& pr, double* __restrict__ S, double* __restrict__ rs,
+__device__ __forceinline__ void potf2_pipelined(const Peers& pr, int me, double* __restrict__ S, double* __restrict__ rs,
                                                 double* __restrict__ G, long long ld, int nb, int k0,
                                                 int* __restrict__ info, unsigned long long* prog, int diag_idx,
-                                                unsigned epoch) {
+                                                unsigned epoch, int first) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll 1
   for (int base = 0; base < nb; base += 32) {
@@ -928,25 +965,28 @@ __device__ __forceinline__ void potf2_pipelined(const Peers& pr, double* __restr
       for (int l = 0; l < 32; ++l) S[(base + l) * TILE_LD + c] = v[l];
     }
     __syncthreads();
-    store_rows_all<true>(pr, S, G, ld, base, nb, nb);
+    store_rows_urgent<true>(pr, me, first, S, G, ld, base, nb, nb);
     if (pr.R == 1) __threadfence(); else __threadfence_system();
     __syncthreads();
-    if (tid == 0) publish_all(pr, prog, diag_idx, epoch, (base >> 5) + 1);
+    if (tid == 0) publish_urgent(pr, me, first, prog, diag_idx, epoch, (base >> 5) + 1);
     if (W > 0) {
       potf2_trailing_update(S, base, W, warp, lane);
       __syncthreads();
     }
+    push_rest<true>(pr, me, first, S, G, ld, base, nb, nb, diag_idx, epoch, (base >> 5) + 1);
   }
 }
 
 // Off-diagonal task (ti, tj): X = U(ti, ti)^{-T} B for the B tile in Ps (all 128 columns), one 32-row step behind the
 // factorisation of U(ti, ti); every finished step is stored and published.
-__device__ __forceinline__ void solve_pipelined(const Peers& pr, double* __restrict__ Ps, double* __restrict__ Us,
+__device__ __forceinline__ void solve_pipelined(const Peers& pr, int me, double* __restrict__ Ps, double* __restrict__ Us,
                                                 double* __restrict__ rinv, const double* __restrict__ Uii,
                                                 long long ld, double* __restrict__ G, long long ldg, int nrows,
                                                 int ncols, unsigned long long* prog, int ti, int tj, unsigned epoch,
                                                 int* __restrict__ info, unsigned int* fault) {
   const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5, l4 = lane & 3, g8 = lane >> 2;
+  // rows of U(ti, tj) are the A operand of block row tj: its diagonal task is ours, (tj, tj + 1) is rank (tj + 1) % R's
+  const int first = pr.R > 1 ? (tj + 1) % pr.R : 0;
   const bool vecU = !(ld & 1) && !(((uintptr_t)Uii) & 15);
   int dready = 0;
 #pragma unroll 1
@@ -992,7 +1032,7 @@ __device__ __forceinline__ void solve_pipelined(const Peers& pr, double* __restr
       for (int l = 0; l < 32; ++l) Ps[(b0 + l) * TILE_LD + c] = v[l];
     }
     __syncthreads();
-    store_rows_all<false>(pr, Ps, G, ldg, b0, nrows, ncols);  // rows b0 .. b0+31 of X are final
+    store_rows_urgent<false>(pr, me, first, Ps, G, ldg, b0, nrows, ncols);  // rows b0 .. b0+31 of X are final
     // rows below:  Ps[r0.., :] -= U[b0..b0+32, r0..]^T X[b0..b0+32, :]; warp wp owns columns 16 wp .. 16 wp + 15
     {
       double bf[2][8];
@@ -1031,15 +1071,29 @@ __device__ __forceinline__ void solve_pipelined(const Peers& pr, double* __restr
     if (pr.R == 1) __threadfence(); else __threadfence_system();
     asm volatile("fence.proxy.async;" ::: "memory");  // the rows will be read by TMA
     __syncthreads();
-    if (tid == 0) publish_all(pr, prog, tj, epoch, 4 * ti + g + 1);
+    if (tid == 0) publish_urgent(pr, me, first, prog, tj, epoch, 4 * ti + g + 1);
+    push_rest<false>(pr, me, first, Ps, G, ldg, b0, nrows, ncols, tj, epoch, 4 * ti + g + 1);
   }
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-potrf_dag2_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmB,
+potrf_dag2_kernel(const __grid_constant__ CUtensorMap tm_, const __grid_constant__ CUtensorMap tmB,
                   double* __restrict__ H, long long ld, int n, int T, double* __restrict__ Bm, long long ldb, int p,
                   int TB, int* __restrict__ info, unsigned long long* __restrict__ prog, unsigned epoch,
-                  unsigned int* __restrict__ fault, const Peers pr) {
+                  unsigned int* __restrict__ fault, const __grid_constant__ Peers pr,
+                  const __grid_constant__ EmuMaps emu, int emu_ctas) {
+  // emu_ctas > 0 (single-GPU test of the distributed code, ipm_internal_potrf_peer_emulated_f64): ONE cooperative grid
+  // holds all R ranks -- CTAs [r * emu_ctas, (r + 1) * emu_ctas) act as rank r on rank r's copy of everything.  (Ranks
+  // as separate launches on one device may never be co-resident.)
+  const CUtensorMap* tmp = &tm_;
+  int cta = blockIdx.x, ncta = gridDim.x, me = pr.me;
+  if (emu_ctas > 0) {
+    me = blockIdx.x / emu_ctas;
+    cta = blockIdx.x - me * emu_ctas, ncta = emu_ctas;
+    H = pr.H[me], prog = pr.prog[me], info = pr.info[me];
+    tmp = &emu.m[me];
+  }
+  const CUtensorMap& tm = *tmp;
   extern __shared__ uint8_t smem_raw[];
   __shared__ double rinv[SLAB_ROWS];
   __shared__ double rs[32];
@@ -1065,10 +1119,10 @@ potrf_dag2_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant_
   uint32_t it = 0;
   // Task list of this rank, row-major: R == 1: all (ti, tj), tj in [ti, T + TB); R > 1: the columns tj = me (mod R).
   // The CTA runs tasks blockIdx.x, blockIdx.x + gridDim.x, ... of that list; `row` / `row_base` walk the rows.
-  const int R = pr.R, me = pr.me;
+  const int R = pr.R;
   const int ntasks = T * (T + 1) / 2 + T * TB;  // R == 1
   int row = 0, row_base = 0;
-  for (int lin = blockIdx.x;; lin += gridDim.x) {
+  for (int lin = cta;; lin += ncta) {
     int ti, tj;
     if (R == 1) {
       if (lin >= ntasks) break;
@@ -1104,11 +1158,12 @@ potrf_dag2_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant_
     stage_tile(tile, M, ldm, n, mcols, k0, c0, diag, acc, lm);
     __syncthreads();
     if (diag) {
-      potf2_pipelined(pr, tile, rs, H + (long long)k0 * ld + k0, ld, min(NB, n - k0), k0, info, prog, MAX_COLS + ti,
-                      epoch);
+      // rows of U(ti, ti) are consumed first by the solve of (ti, ti + 1): rank (ti + 1) % R
+      potf2_pipelined(pr, me, tile, rs, H + (long long)k0 * ld + k0, ld, min(NB, n - k0), k0, info, prog, MAX_COLS + ti,
+                      epoch, pr.R > 1 ? (ti + 1) % pr.R : 0);
       if (tid == 0) publish_all(pr, prog, MAX_COLS + ti, epoch, 4);  // a ragged last tile has fewer than four steps
     } else {
-      solve_pipelined(pr, tile, slab, rinv, H + (long long)k0 * ld + k0, ld, M + (long long)k0 * ldm + c0, ldm,
+      solve_pipelined(pr, me, tile, slab, rinv, H + (long long)k0 * ld + k0, ld, M + (long long)k0 * ldm + c0, ldm,
                       min(NB, n - k0), min(NB, mcols - c0), prog, ti, tj, epoch, info, fault);
     }
     // this task's generic accesses to the tile / slab precede the next task's TMA writes into the same bytes
@@ -1117,7 +1172,7 @@ potrf_dag2_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant_
   }
   // Distributed: the kernel -- and with it everything the stream runs next on this rank's copy of U -- ends only when
   // the other ranks' columns have arrived in full (off-diagonal tiles of column c: 4 c groups, diagonal tile: 4 steps).
-  if (R > 1 && blockIdx.x == 0) {
+  if (R > 1 && cta == 0) {
     for (int c = tid; c < T; c += THREADS) {
       wait_progress(prog, c, epoch, 4 * c, info, fault, true);
       wait_progress(prog, MAX_COLS + c, epoch, 4, info, fault, true);
@@ -1176,7 +1231,8 @@ bool enabled(int n) {
 // peers / peer_epoch / max_ctas: distributed factorisation (see struct Peers): counters, info and the matrix live in
 // peer-mapped memory owned by the caller, the epoch is the caller's (identical on every rank).
 int potrf(double* H, int ld, int n, int* info_dev, cudaStream_t st, bool pipelined = true, double* Bm = nullptr,
-          int ldb = 0, int p = 0, const Peers* peers = nullptr, unsigned peer_epoch = 0, int max_ctas = 0) {
+          int ldb = 0, int p = 0, const Peers* peers = nullptr, unsigned peer_epoch = 0, int max_ctas = 0,
+          bool emulate = false) {
   const int T = ceil_div(n, NB), TB = Bm ? ceil_div(p, NB) : 0;
   if (T < 3 || T > MAX_T || T + TB > MAX_COLS || (Bm && !pipelined) || (peers && (Bm || !pipelined))) return 1;
   int dev = 0, rc = IPM_OK;
@@ -1219,6 +1275,16 @@ int potrf(double* H, int ld, int n, int* info_dev, cudaStream_t st, bool pipelin
   }
   int grid = ntasks < g_sms[dev] ? ntasks : g_sms[dev];
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  static EmuMaps emu;  // only filled in emulation mode (a kernel parameter either way)
+  int emu_ctas = 0;
+  if (emulate) {
+    if (!peers) return IPM_ERR_ARG;
+    emu_ctas = g_sms[dev] / pr.R;
+    if (emu_ctas < 1) return IPM_ERR_ARG;
+    grid = emu_ctas * pr.R;
+    for (int r = 0; r < pr.R; ++r)
+      if (make_operand_map(&emu.m[r], pr.H[r], ld, n, n)) return IPM_ERR_ARG;
+  }
   // cooperative: the CTAs wait for each other's tiles, so all of them must be resident (a second persistent kernel on
   // another stream, MPS SM limits or green contexts would otherwise leave round >= 1 tasks waiting for CTAs that are
   // never scheduled); every wait is additionally bounded by the watchdog
@@ -1227,7 +1293,7 @@ int potrf(double* H, int ld, int n, int* info_dev, cudaStream_t st, bool pipelin
     IPM_CUDA_CHECK(ensure_dynamic_smem(potrf_dag2_kernel, SMEM2, attr2_set));
     IPM_CUDA_CHECK(launch_cooperative(potrf_dag2_kernel, dim3(grid), dim3(THREADS), SMEM2, st, tm, tmB, H, (long long)ld,
                                       n, T, Bm, (long long)ldb, p, TB, info_dev, done, epoch,
-                                      ipm_internal_fault_word(), pr));
+                                      ipm_internal_fault_word(), pr, emu, emu_ctas));
   } else {
     IPM_CUDA_CHECK(launch_cooperative(potrf_dag_kernel, dim3(grid), dim3(THREADS), SMEM, st, tm, H, (long long)ld, n, T,
                                       info_dev, done, epoch, ipm_internal_fault_word()));
@@ -1343,6 +1409,23 @@ extern "C" int ipm_potrf_upper_peer_f64(void* const* peer_H, int ld, int n, void
   }
   const int rc = dag::potrf(pr.H[me], ld, n, pr.info[me], (cudaStream_t)stream, true, nullptr, 0, 0, &pr, epoch, max_ctas);
   return rc == 1 ? IPM_ERR_ARG : rc;  // sizes the tile-DAG kernel does not take (n <= 256): the caller factors replicated
+}
+
+// Library-internal (kernel tests on ONE GPU): the distributed factorisation with all R ranks inside one cooperative
+// grid, each rank's CTAs working on that rank's copy of the matrix / counters / info.
+extern "C" int ipm_internal_potrf_peer_emulated_f64(void* const* peer_H, int ld, int n, void* const* peer_info,
+                                                    void* const* peer_prog, int R, unsigned int epoch, void* stream) {
+  if (!peer_H || !peer_info || !peer_prog || n < 0 || ld < n || (ld & 1) || R < 2 || R > dag::kMaxRanks || epoch == 0)
+    return IPM_ERR_ARG;
+  dag::Peers pr;
+  pr.R = R, pr.me = 0;
+  for (int r = 0; r < dag::kMaxRanks; ++r) {
+    pr.H[r] = r < R ? (double*)peer_H[r] : nullptr;
+    pr.prog[r] = r < R ? (unsigned long long*)peer_prog[r] : nullptr;
+    pr.info[r] = r < R ? (int*)peer_info[r] : nullptr;
+  }
+  const int rc = dag::potrf(pr.H[0], ld, n, pr.info[0], (cudaStream_t)stream, true, nullptr, 0, 0, &pr, epoch, 0, true);
+  return rc == 1 ? IPM_ERR_ARG : rc;
 }
 
 // Library-internal (kernel tests): the fused launch for every admissible size, whatever the size policy says.

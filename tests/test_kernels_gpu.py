@@ -420,13 +420,18 @@ def test_potrf_trsm_fused_tile_dag(n, p):
         assert torch.equal(Bd[:, p:], guard[:, p:])  # padding columns untouched
 
 
-@pytest.mark.parametrize("n,R", [(1000, 2), (1537, 3)])
+@pytest.mark.parametrize("n,R", [(1000, 2), (1537, 3), (2500, 8)])
 def test_potrf_peer_emulated_ranks(n, R):
-    """ipm_potrf_upper_peer_f64 with R emulated ranks on ONE device: R copies of the matrix, R streams, each launch limited
-    to #SMs / R CTAs so that the R cooperative grids are resident together; every copy must end with the whole factor.
-    (The real multi-GPU run is tests/test_sharded_gpu.py.)"""
+    """The distributed tile-DAG factorisation (ipm_potrf_upper_peer_f64: block column j on rank j % R, finished rows pushed
+    into every rank's copy, system-scope counters) with R emulated ranks on ONE device: a single cooperative grid whose
+    CTAs [r * G, (r + 1) * G) act as rank r on rank r's copy of the matrix, counters and info word -- ranks as separate
+    launches on one GPU are not guaranteed to be co-resident.  Every copy must end with the whole factor.  (The real
+    multi-GPU run is tests/test_sharded_gpu.py.)"""
     L = _abi.lib()
-    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    fn = L.ipm_internal_potrf_peer_emulated_f64
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_uint,
+                   C.c_void_p]
     H = spd(n, n + 3, cond_pow=2)
     words = L.ipm_potrf_peer_prog_words()
     copies = [padded(H) for _ in range(R)]
@@ -436,29 +441,28 @@ def test_potrf_peer_emulated_ranks(n, R):
     pH = (C.c_void_p * R)(*[c[0].data_ptr() for c in copies])
     pP = (C.c_void_p * R)(*[t.data_ptr() for t in progs])
     pI = (C.c_void_p * R)(*[t.data_ptr() for t in infos])
-    streams = [torch.cuda.Stream() for _ in range(R)]
     L.ipm_clear_device_fault()
-    old = L.ipm_set_spin_limit(600)  # ~0.3 s: fail fast if the grids cannot be co-resident
-    try:
-        for epoch in (1, 2):
-            for c in copies:
-                c[0][:, :n] = torch.as_tensor(H, device="cuda")
-            torch.cuda.synchronize()
-            for r in range(R):
-                _abi.call("ipm_potrf_upper_peer_f64", pH, ld, n, pI, pP, r, R, epoch, sms // R, streams[r].cuda_stream)
-            torch.cuda.synchronize()
-            fault = L.ipm_device_fault()
-            if fault == 7:
-                L.ipm_clear_device_fault()
-                pytest.skip("the R cooperative grids were not co-resident on this device (peer wait timed out)")
-            assert fault == 0
-            for r in range(R):
-                assert int(infos[r][0]) == 0
-                U = torch.triu(copies[r][0][:, :n]).cpu().numpy()
-                assert np.max(np.abs(U.T @ U - H)) / np.max(np.abs(H)) < 1e-13, r
-    finally:
-        L.ipm_set_spin_limit(old)
-        L.ipm_clear_device_fault()
+    for epoch in (1, 2):
+        for c in copies:
+            c[0][:, :n] = torch.as_tensor(H, device="cuda")
+        _abi.check(fn(pH, ld, n, pI, pP, R, epoch, None), "potrf_peer_emulated")
+        torch.cuda.synchronize()
+        assert L.ipm_device_fault() == 0
+        for r in range(R):
+            assert int(infos[r][0]) == 0
+            U = torch.triu(copies[r][0][:, :n]).cpu().numpy()
+            assert np.max(np.abs(U.T @ U - H)) / np.max(np.abs(H)) < 1e-13, r
+    # a non-positive pivot is reported to every rank
+    Hbad = H.copy()
+    Hbad[700, 700] = -1.0
+    for c in copies:
+        c[0][:, :n] = torch.as_tensor(Hbad, device="cuda")
+    for t in infos:
+        t.zero_()
+    _abi.check(fn(pH, ld, n, pI, pP, R, 3, None), "potrf_peer_emulated")
+    torch.cuda.synchronize()
+    assert [int(t[0]) for t in infos] == [701] * R
+    L.ipm_clear_device_fault()
 
 
 def _admm_numpy(Qt, bA, eta, rho, alpha, u, add_bias, positive, iters):
