@@ -37,7 +37,7 @@ class PhaseOneSolver:
         self.data = LinearProblemData(n, device, C=G, d=np.asarray(h, dtype=np.float64).ravel())
         self.ns = LinearNewton(self.data, phase1=True, max_iters=max_iter_newton, epsilon=eps, alpha=0.2, beta=0.7,
                                linear_solver="cg" if linear_solver == "cg" else "cholesky", max_cg_iters=max_cg_iters)
-        self.ns.shift = 0.01  # "some conditioning", PhaseOne.py:123-127
+        self.ns.base_shift = self.ns.shift = 0.01  # "some conditioning", PhaseOne.py:123-127
         self.z = torch.zeros(n + 1, dtype=F64, device=device)
         self.z[:n].copy_(torch.as_tensor(np.ones(n) if x0 is None else np.asarray(x0, dtype=np.float64)))
         # s = max(Gx - h) + 1 (PhaseOne.py:96): min slack of the s = 0 problem is -max(Gx - h)

@@ -161,6 +161,7 @@ class BarrierSolverBase:
         self.inner_iters = []
         ns = self.ns
         ns.set_t(t)
+        ns.shift = ns.base_shift  # a regularisation found necessary in an earlier solve() does not carry over
         if ns.equality:
             ns.reset_dual()
         dual_gap = self.num_constraints

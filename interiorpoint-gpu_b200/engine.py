@@ -290,7 +290,13 @@ class LinearNewton:
         self.t = 1.0
         self.use_backup = False  # sticky, like the reference (NewtonSolver.py:319)
         self.direct_trial = False  # cones: re-evaluate the barrier AT the proposed trial point
+        # diagonal shift of the Newton systems: base_shift = deliberate conditioning (0.01 in the stand-alone phase-I,
+        # PhaseOne.py:123-127); shift grows from it only after a failed factorisation (_retry_regularised), is capped
+        # relative to diag(H) and returns to base_shift at the start of every front-end solve()
+        self.base_shift = 0.0
         self.shift = 0.0
+        self._zsave = torch.zeros(self.nz, dtype=F64, device=data.device)
+        self._vsave = torch.zeros(max(data.p, 1), dtype=F64, device=data.device)
         self.newton_steps = 0
         self.trace = None
         if linear_solver == "cg":
@@ -565,7 +571,10 @@ class LinearNewton:
         nd = None
         it = 0
         for it in range(self.max_iters):
-            zsave = z.clone() if not self.diagonal else None
+            zsave = None
+            if not self.diagonal:
+                zsave = self._zsave  # persistent buffer: only read if the factorisation fails
+                zsave.copy_(z)
             r = self._iterate_feasible(z)
             if r["info"] != 0 and not self.diagonal:
                 r = self._retry_regularised(z, zsave)
@@ -586,7 +595,7 @@ class LinearNewton:
         (NewtonSolver.py:314-341); the device engine re-factorises H + shift*I with a growing shift instead
         (documented deviation: this path is only reached on numerically singular Hessians)."""
         self.use_backup = True
-        if self.shift == 0.0:
+        if self.shift == self.base_shift:
             # scale of the shift from a fresh (unfactored) Hessian: the failed potrf left NaNs in ws.H
             z.copy_(zsave)
             self._eval(z, self.ws.cur)
@@ -594,17 +603,20 @@ class LinearNewton:
             self._hessian(self.t)
             diag = torch.diagonal(self.ws.H[:, : self.nz])
             base = float(diag[torch.isfinite(diag)].abs().mean())
+            scale = base if base > 0 else 1.0
+            self._shift_cap = max(1e-6 * scale, 1e4 * self.base_shift)  # beyond this it is no longer the Newton system
+            shift = max(100.0 * self.base_shift, 1e-14 * scale)
         else:
-            base = self.shift
-        shift = max(self.shift, 1e-14 * (base if base > 0 else 1.0))
-        for _ in range(40):
+            shift = 100.0 * self.shift  # the step that just failed already used self.shift
+        while shift <= self._shift_cap:
             self.shift = shift
             z.copy_(zsave)
             r = self._iterate_feasible(z)
             if r["info"] == 0:
                 return r
             shift *= 100.0
-        raise np.linalg.LinAlgError("Hessian is not positive definite even after regularisation")
+        raise np.linalg.LinAlgError("Hessian is not positive definite even after a regularisation of 1e-6 of its "
+                                    "diagonal")
 
     # ---------------------------------------------------------------- infeasible-start (equality constrained)
     def _direction_infeasible(self, z, lin):
@@ -727,7 +739,9 @@ class LinearNewton:
         rn = None
         it = 0
         for it in range(self.max_iters):
-            zsave, vsave = z.clone(), self.ws.v.clone()
+            zsave, vsave = self._zsave, self._vsave[: self.d.p]
+            zsave.copy_(z)
+            vsave.copy_(self.ws.v)
             r = self._iterate_infeasible(z)
             if r["info"] != 0:
                 r = self._retry_regularised_infeasible(z, zsave, vsave)
@@ -746,13 +760,15 @@ class LinearNewton:
         regularised re-factorisation (same documented deviation as the feasible-start path)."""
         self.use_backup = True
         ws = self.ws
-        if self.shift == 0.0:
+        if self.shift == self.base_shift:
             hd = ws.hdiag[torch.isfinite(ws.hdiag)]
             base = float(hd.abs().mean()) if hd.numel() else 1.0
+            scale = base if base > 0 else 1.0
+            self._shift_cap = max(1e-6 * scale, 1e4 * self.base_shift)
+            shift = max(100.0 * self.base_shift, 1e-14 * scale)
         else:
-            base = self.shift
-        shift = max(self.shift, 1e-14 * (base if base > 0 else 1.0))
-        for _ in range(40):
+            shift = 100.0 * self.shift
+        while shift <= self._shift_cap:
             self.shift = shift
             z.copy_(zsave)
             ws.v.copy_(vsave)
@@ -760,4 +776,4 @@ class LinearNewton:
             if r["info"] == 0:
                 return r
             shift *= 100.0
-        raise np.linalg.LinAlgError("KKT system is not solvable even after regularisation")
+        raise np.linalg.LinAlgError("KKT system is not solvable even after a regularisation of 1e-6 of its diagonal")

@@ -30,6 +30,13 @@ except ImportError:  # flat-module use
     from engine import F64, LinearNewton
 
 
+_PEER_CACHE = {}  # (H shape, world, group, device) -> peer-mapped buffers and their bookkeeping
+
+
+class _UseCached(Exception):
+    pass
+
+
 class _RowSharded:
     """Mixin (placed before the engine class in the MRO): wraps the barrier pieces of the single-GPU engine with the
     collectives that make their outputs global."""
@@ -58,7 +65,14 @@ class _RowSharded:
         no symmetric memory (all ranks take the same decision: the probe result is MIN-reduced)."""
         ok = torch.ones(1, dtype=torch.int32, device=self.d.device)
         st = None
+        # The peer-mapped buffers are kept per (shape, group) for the life of the process and handed to the next engine
+        # of the same shape: allocating and exchanging handles costs ~0.1 s per buffer, which is what a user who builds
+        # a new solver object per problem would otherwise pay every time.  Epochs and counters simply run on.
+        key = (tuple(self.ws.H.shape), self.world, id(self.group), self.d.device.index)
+        cached = _PEER_CACHE.get(key)
         try:
+            if cached is not None:
+                raise _UseCached
             import torch.distributed._symmetric_memory as symm
 
             grp = self.group if self.group is not None else dist.group.WORLD
@@ -86,11 +100,14 @@ class _RowSharded:
             st["p_done"] = (C.c_void_p * R)(*[int(p) + 4 * st["done_off"] for p in hS.buffer_ptrs])
             st["p_prog"] = (C.c_void_p * R)(*[int(p) for p in hP.buffer_ptrs])
             st["p_info"] = (C.c_void_p * R)(*[int(p) for p in hN.buffer_ptrs])
+        except _UseCached:
+            st = cached
         except Exception as e:  # noqa: BLE001 -- any failure means "no peer path on this box"
             ok.zero_()
             self.peer_error = repr(e)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
         if int(ok.item()) == 1:
+            _PEER_CACHE[key] = st
             self.peer = st
             self.ws.H = st["H"]  # the factorisation runs in the peer-mapped buffer the owners write into
             self.ws.info = st["info"][:2]  # same layout as the engine's own info pair
