@@ -632,7 +632,9 @@ def main():
     cfg = workload_config(n, m)
     cfg["per_rank"] = ("single GPU" if D.world == 1 else
                        "ONE problem, constraint rows sharded over the GPUs; partial Hessian exchanged tile by tile over "
-                       "peer memory (NCCL all-reduce fallback), replicated factorisation" if rows_mode else
+                       "peer memory (NCCL all-reduce fallback), " + ("factorisation distributed over the GPUs" if
+                       r.get("potrf_distributed") else "replicated factorisation (the distributed one is the default "
+                       "from n = 12288)") if rows_mode else
                        "one copy of the instance per GPU (independent solves), no collective")
     line = {
         "metric": "newton_steps_per_s", "value": newton / (ms * 1e-3), "unit": "Newton steps/s", "n_gpus": D.world,

@@ -33,6 +33,9 @@ except ImportError:  # flat-module use
 _PEER_CACHE = {}  # (H shape, world, group, device) -> peer-mapped buffers and their bookkeeping
 
 
+PEER_POTRF_MIN_N = 12288  # crossover of the two measured sizes, see _setup_peer
+
+
 class _UseCached(Exception):
     pass
 
@@ -111,9 +114,13 @@ class _RowSharded:
             self.peer = st
             self.ws.H = st["H"]  # the factorisation runs in the peer-mapped buffer the owners write into
             self.ws.info = st["info"][:2]  # same layout as the engine's own info pair
-            # block columns of the factorisation dealt over the ranks (csrc/chol.cu, struct dag::Peers);
-            # IPM_PEER_POTRF=0 keeps the factorisation replicated
-            self.peer_potrf = os.environ.get("IPM_PEER_POTRF", "1") != "0" and self.nz > 384
+            # block columns of the factorisation dealt over the ranks (csrc/chol.cu, struct dag::Peers).  Measured on
+            # 8 B200s (profiles/scale_r02_n8_*.json): 26.1 ms against 45.7 ms replicated at n = 16384, but 11.8 ms
+            # against 7.0 ms at n = 8192, where one block column's panel latency plus its NVLink pushes exceed the
+            # trailing update they overlap with -- so the replicated factorisation stays the default below
+            # PEER_POTRF_MIN_N.  IPM_PEER_POTRF=1 / 0 forces it on / off.
+            env = os.environ.get("IPM_PEER_POTRF", "")
+            self.peer_potrf = self.nz > 384 and (env == "1" or (env != "0" and self.nz >= PEER_POTRF_MIN_N))
             torch.cuda.synchronize()
             dist.barrier(group=self.group)
 

@@ -21,7 +21,9 @@ CASES = {c["name"]: c for f in ("barrier_cases.json", "dual_cases.json", "large_
 def _worker(rank, world, port, name, q):
     import torch.distributed as dist
 
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    # the distributed factorisation is off by default below n = 12288 (sharded_engine.PEER_POTRF_MIN_N): force it on so
+    # that the n >= 512 cases here run ipm_potrf_upper_peer_f64
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), IPM_PEER_POTRF="1")
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from ipm_b200.LPSolver import LPSolver
@@ -40,7 +42,8 @@ def _worker(rank, world, port, name, q):
     val = s.solve()
     p1 = s.phase1_solver.inner_iters if case.get("phase1_inner_iters") is not None else None
     if rank == 0:
-        q.put((val, s.inner_iters, p1, np.asarray(s.xstar), s.ns.peer is not None, getattr(s.ns, "peer_error", None),
+        q.put((val, s.inner_iters, p1, np.asarray(s.xstar),
+               (s.ns.peer is not None, bool(getattr(s.ns, "peer_potrf", False))), getattr(s.ns, "peer_error", None),
                np.asarray(s.lam_star) if duals else None, np.asarray(s.v_star) if duals and s.v_star is not None else None))
     dist.barrier()
     dist.destroy_process_group()
@@ -84,7 +87,8 @@ def test_row_sharded_matches_reference(name):
     val, iters, p1, x, peer, peer_error, _, _ = _run(name)
     # the Hessian exchange ran over peer memory (fused SYRK + reduce-scatter + all-gather), not the NCCL fallback; the
     # n = 1024 cases also run the factorisation distributed over the two GPUs (ipm_potrf_upper_peer_f64)
-    assert peer, peer_error
+    assert peer[0], peer_error
+    assert peer[1] == (len(case["xstar"]) > 384), "distributed factorisation not exercised"
     assert val == pytest.approx(case["value"], rel=1e-6, abs=1e-9)
     prob = getattr(problems, case["generator"])(**case["generator_kwargs"])
     if isinstance(prob, list):
