@@ -14,9 +14,17 @@
 //   colmax_kernel      amax_i = max_k sqrt(w_k) |C_ki|                       (HBM: reads C once)
 //   slice_kernel       Q[t][i][k] (int8, K-major = transposed), sigma_i     (HBM: reads C once, writes s bytes / entry)
 //   ozaki_syrk_kernel  persistent, 1 CTA / SM, warp roles: TMA producer / MMA issuer / 4 epilogue warps.
-//                      Per 32-byte k-block one stage = s slices of the 128 A rows + s slices of the 64 B rows (48 KB at
-//                      s = 8, SWIZZLE_32B both in the tensor map and in the UMMA descriptors), 4 stages; s(s+1)/2 MMAs
-//                      (M128 N64 K32) per stage; epilogue: tcgen05.ld, Horner in FP64, scale by sigma_i sigma_j, store.
+//                      v1 (32-byte k-blocks, one 128x64x32 MMA per slice pair) was exact but ran at 1.5 POP/s: every MMA
+//                      re-read its 4 KB A operand from shared memory (6 KB per 32 clk > the 128 B/clk of the SM) and the
+//                      TMA wrote 32-byte rows at ~1 row / clk.  v2:
+//                        * 128-byte rows (SWIZZLE_128B), k-chunks of 128 bytes = 4 MMA k-steps (descriptor start + 32 B);
+//                        * the B side of a chunk -- all s slices of the 64 rows, [s][64][128 B] = one contiguous K-major
+//                          operand of 64 s rows -- sits in one of 2 stages; the A slices stream through a ring of 16 KB
+//                          slots;
+//                        * slice t of A meets slices 0..s-1-t of B, whose accumulators (diagonals t..s-1) are adjacent
+//                          TMEM columns: ONE wide MMA (N = 64 (s - t), split at 256) instead of s - t narrow ones, so A
+//                          is read once per wide MMA: 12 instead of 36 A reads per k-step at s = 8;
+//                      epilogue: tcgen05.ld, Horner in FP64, scale by sigma_i sigma_j, store.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,11 +33,11 @@
 #include <vector>
 
 namespace {
-constexpr int TM = 128, TN = 64, KB = 32, STAGES = 4, SMAX = 8;
-constexpr int A_SLICE = TM * KB, B_SLICE = TN * KB;                   // 4096, 2048 bytes
-constexpr int STAGE_BYTES = SMAX * (A_SLICE + B_SLICE);               // 49152
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;         // + alignment slack + barriers
-constexpr int THREADS = 192;
+constexpr int TM = 128, TN = 64, KC = 128, KSTEP = 32, SMAX = 8;    // k-chunk of 128 bytes = 4 MMA k-steps
+constexpr int NA = 6, NB = 2;                                         // A ring slots, B stages
+constexpr int A_SLOT = TM * KC, B_SLICE = TN * KC, B_STAGE = SMAX * B_SLICE;  // 16 KB, 8 KB, 64 KB
+constexpr int SMEM_BYTES = NA * A_SLOT + NB * B_STAGE + 1024 + 256;   // + alignment slack + barriers
+constexpr int THREADS = 224;  // warps: 0 A producer, 1 MMA issuer, 2-5 epilogue, 6 B producer
 
 // ---------------------------------------------------------------- slicing
 __global__ void __launch_bounds__(128) colmax_kernel(const double* __restrict__ C, long long ldc, int m, int n,
@@ -118,6 +126,12 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* fa
     }
   }
 }
+__device__ __forceinline__ bool mbar_wait_timed(uint32_t bar, uint32_t parity, int* fail, int code, long long& acc) {
+  const long long t0 = clock64();
+  const bool ok = mbar_wait(bar, parity, fail, code);
+  acc += clock64() - t0;
+  return ok;
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
@@ -146,31 +160,41 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 struct Args {
   const int2* tiles;  // (row block of 128, column block of 64)
-  int ntiles, nkb, s, n;
+  int ntiles, nkc, s, n;
   const double* sigma;
   double* H;
   long long ldh;
   uint64_t desc_template;  // UMMA shared-memory descriptor without the start address
-  uint32_t idesc;
+  uint32_t idesc;          // instruction descriptor without N
   int* fail;        // 0 = ok; otherwise the code of the wait that timed out
   int* dbg;         // raw accumulators [s][128][64] of tile `dbg_tile`, or NULL
   int dbg_tile;
+  long long* prof;  // per CTA: cycles the MMA thread waited for [A slot, B stage, TMEM], its total, producer waits [A, B]
 };
+
+__device__ __forceinline__ uint64_t smem_desc(uint64_t tmpl, uint32_t addr) {
+  return tmpl | (uint64_t)((addr & 0x3FFFFu) >> 4);
+}
 
 __global__ void __launch_bounds__(THREADS, 1)
 ozaki_syrk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = base + STAGES * STAGE_BYTES;  // full[STAGES], empty[STAGES], tmem_full, tmem_empty, tmem_ptr
-  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull = bars + 16 * STAGES, tempty = tfull + 8,
-                 tptr = tfull + 16;
+  const uint32_t smB = base, smA = base + NB * B_STAGE;
+  const uint32_t bars = smA + NA * A_SLOT;
+  const uint32_t a_full = bars, a_empty = bars + 8 * NA, b_full = bars + 16 * NA, b_empty = b_full + 8 * NB,
+                 tfull = b_empty + 8 * NB, tempty = tfull + 8, tptr = tfull + 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = a.s;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) {
-      mbar_init(full0 + 8 * i, 1);
-      mbar_init(empty0 + 8 * i, 1);
+    for (int i = 0; i < NA; ++i) {
+      mbar_init(a_full + 8 * i, 1);
+      mbar_init(a_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < NB; ++i) {
+      mbar_init(b_full + 8 * i, 1);
+      mbar_init(b_empty + 8 * i, 1);
     }
     mbar_init(tfull, 1);
     mbar_init(tempty, 128);
@@ -186,50 +210,86 @@ ozaki_syrk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint32_t tmem;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tptr));
 
-  if (warp == 0) {
+  if (warp == 0) {  // A slices: one 16 KB slot per (chunk, slice), in the order the MMA thread consumes them
     if (lane == 0) {
-      long long it = 0;
+      long long ia = 0, wa = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < a.ntiles && ok; tile += gridDim.x) {
         const int2 tl = a.tiles[tile];
-        for (int kb = 0; kb < a.nkb && ok; ++kb, ++it) {
-          const int st = (int)(it % STAGES);
-          if (it >= STAGES) ok = mbar_wait(empty0 + 8 * st, (uint32_t)((it / STAGES) - 1) & 1u, a.fail, 1);
-          if (!ok) break;
-          const uint32_t sa = base + st * STAGE_BYTES, sb = sa + SMAX * A_SLICE;
-          mbar_expect_tx(full0 + 8 * st, (uint32_t)s * (A_SLICE + B_SLICE));
-          tma_load_3d(sa, &tmA, kb * KB, tl.x * TM, 0, full0 + 8 * st);
-          tma_load_3d(sb, &tmB, kb * KB, tl.y * TN, 0, full0 + 8 * st);
+        for (int kc = 0; kc < a.nkc && ok; ++kc) {
+          for (int t = 0; t < s && ok; ++t, ++ia) {
+            const int sl = (int)(ia % NA);
+            if (ia >= NA) ok = mbar_wait_timed(a_empty + 8 * sl, (uint32_t)((ia / NA) - 1) & 1u, a.fail, 5, wa);
+            if (!ok) break;
+            mbar_expect_tx(a_full + 8 * sl, A_SLOT);
+            tma_load_3d(smA + sl * A_SLOT, &tmA, kc * KC, tl.x * TM, t, a_full + 8 * sl);
+          }
         }
       }
+      if (a.prof) a.prof[blockIdx.x * 8 + 4] = wa;
+    }
+  } else if (warp == 6) {  // B side of a chunk: its own thread, so that a stage is refilled the moment it is released
+    if (lane == 0) {
+      long long ib = 0, wb = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < a.ntiles && ok; tile += gridDim.x) {
+        const int2 tl = a.tiles[tile];
+        for (int kc = 0; kc < a.nkc && ok; ++kc, ++ib) {
+          const int st = (int)(ib % NB);
+          if (ib >= NB) ok = mbar_wait_timed(b_empty + 8 * st, (uint32_t)((ib / NB) - 1) & 1u, a.fail, 1, wb);
+          if (!ok) break;
+          mbar_expect_tx(b_full + 8 * st, (uint32_t)s * B_SLICE);
+          tma_load_3d(smB + st * B_STAGE, &tmB, kc * KC, tl.y * TN, 0, b_full + 8 * st);
+        }
+      }
+      if (a.prof) a.prof[blockIdx.x * 8 + 5] = wb;
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      long long it = 0;
+      long long ia = 0, ib = 0;
+      long long wa = 0, wb = 0, wt = 0;
+      const long long tstart = clock64();
       int tcount = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < a.ntiles && ok; tile += gridDim.x, ++tcount) {
         if (tcount > 0) {
-          ok = mbar_wait(tempty, (uint32_t)(tcount - 1) & 1u, a.fail, 2);
+          ok = mbar_wait_timed(tempty, (uint32_t)(tcount - 1) & 1u, a.fail, 2, wt);
           if (!ok) break;
           tc_fence_after();
         }
-        for (int kb = 0; kb < a.nkb && ok; ++kb, ++it) {
-          const int st = (int)(it % STAGES);
-          ok = mbar_wait(full0 + 8 * st, (uint32_t)(it / STAGES) & 1u, a.fail, 3);
+        for (int kc = 0; kc < a.nkc && ok; ++kc, ++ib) {
+          const int st = (int)(ib % NB);
+          ok = mbar_wait_timed(b_full + 8 * st, (uint32_t)(ib / NB) & 1u, a.fail, 3, wb);
           if (!ok) break;
-          tc_fence_after();
-          const uint32_t sa = base + st * STAGE_BYTES, sb = sa + SMAX * A_SLICE;
-          for (int d = 0; d < s; ++d) {
-            for (int t = 0; t <= d; ++t) {
-              const uint64_t da = a.desc_template | (uint64_t)(((sa + t * A_SLICE) & 0x3FFFFu) >> 4);
-              const uint64_t db = a.desc_template | (uint64_t)(((sb + (d - t) * B_SLICE) & 0x3FFFFu) >> 4);
-              umma_i8(tmem + d * TN, da, db, a.idesc, (kb > 0 || t > 0) ? 1u : 0u);
+          const uint32_t sb = smB + st * B_STAGE;
+          for (int t = 0; t < s && ok; ++t, ++ia) {
+            const int sl = (int)(ia % NA);
+            ok = mbar_wait_timed(a_full + 8 * sl, (uint32_t)(ia / NA) & 1u, a.fail, 6, wa);
+            if (!ok) break;
+            tc_fence_after();
+            const uint32_t sa = smA + sl * A_SLOT;
+            const int ncols = TN * (s - t);  // B rows = slices 0 .. s-1-t; accumulators of the diagonals t .. s-1
+#pragma unroll
+            for (int j = 0; j < KC / KSTEP; ++j) {
+              const uint64_t da = smem_desc(a.desc_template, sa + j * KSTEP);
+              for (int n0 = 0; n0 < ncols; n0 += 256) {
+                const int nn = min(256, ncols - n0);
+                const uint64_t db = smem_desc(a.desc_template, sb + n0 * KC + j * KSTEP);
+                umma_i8(tmem + t * TN + n0, da, db, a.idesc | ((uint32_t)(nn >> 3) << 17),
+                        (kc > 0 || t > 0 || j > 0) ? 1u : 0u);
+              }
             }
+            umma_commit(a_empty + 8 * sl);  // frees the A slot once these MMAs have read it
           }
-          umma_commit(empty0 + 8 * st);  // frees the stage once these MMAs have read it
+          if (ok) umma_commit(b_empty + 8 * st);
         }
         if (ok) umma_commit(tfull);
+      }
+      if (a.prof) {
+        a.prof[blockIdx.x * 8 + 0] = wa;
+        a.prof[blockIdx.x * 8 + 1] = wb;
+        a.prof[blockIdx.x * 8 + 2] = wt;
+        a.prof[blockIdx.x * 8 + 3] = clock64() - tstart;
       }
     }
   } else {
@@ -313,15 +373,15 @@ EncodeTiledFn encode_fn() {
   }
   return fn;
 }
-int slice_map(CUtensorMap* tm, const int8_t* Q, long long n_pad, long long k_pad, int s, int box_rows) {
+int slice_map(CUtensorMap* tm, const int8_t* Q, long long n_pad, long long k_pad, int s, int box_rows, int box_slices) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return -1;
   cuuint64_t gdim[3] = {(cuuint64_t)k_pad, (cuuint64_t)n_pad, (cuuint64_t)s};
   cuuint64_t gstride[2] = {(cuuint64_t)k_pad, (cuuint64_t)(n_pad * k_pad)};
-  cuuint32_t box[3] = {KB, (cuuint32_t)box_rows, (cuuint32_t)s};
+  cuuint32_t box[3] = {KC, (cuuint32_t)box_rows, (cuuint32_t)box_slices};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)Q, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -2;
 }
 }  // namespace
@@ -366,13 +426,13 @@ extern "C" int ozaki_slice_f64(const double* C, long long ldc, int m, int n, con
 
 extern "C" int ozaki_syrk_i8(const int8_t* Q, int m, int n, int s, const double* sigma, const int* tiles, int ntiles,
                              double* H, long long ldh, unsigned long long desc_template, int* fail, int* dbg, int dbg_tile,
-                             int max_ctas, void* stream) {
+                             int max_ctas, long long* prof, void* stream) {
   if (s < 1 || s > SMAX) return -1;
   const long long n_pad = ozaki_n_pad(n), k_pad = ozaki_k_pad(m);
   CUtensorMap tmA, tmB;
-  int rc = slice_map(&tmA, Q, n_pad, k_pad, s, TM);
+  int rc = slice_map(&tmA, Q, n_pad, k_pad, s, TM, 1);
   if (rc) return rc;
-  rc = slice_map(&tmB, Q, n_pad, k_pad, s, TN);
+  rc = slice_map(&tmB, Q, n_pad, k_pad, s, TN, s);
   if (rc) return rc;
   static bool attr = false;
   if (!attr) {
@@ -388,17 +448,18 @@ extern "C" int ozaki_syrk_i8(const int8_t* Q, int m, int n, int s, const double*
   Args a;
   a.tiles = reinterpret_cast<const int2*>(tiles);
   a.ntiles = ntiles;
-  a.nkb = (int)(k_pad / KB);
+  a.nkc = (int)(k_pad / KC);
   a.s = s;
   a.n = n;
   a.sigma = sigma;
   a.H = H;
   a.ldh = ldh;
   a.desc_template = desc_template;
-  a.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+  a.idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TM >> 4) << 24);  // S32 accumulate, signed int8 A and B, K-major
   a.fail = fail;
   a.dbg = dbg;
   a.dbg_tile = dbg_tile;
+  a.prof = prof;
   ozaki_syrk_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(tmA, tmB, a);
   return cudaGetLastError() == cudaSuccess ? 0 : -5;
 }

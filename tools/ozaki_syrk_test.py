@@ -24,10 +24,9 @@ def template(lbo, sbo, version, layout):
     return (lbo << 16) | (sbo << 32) | (version << 46) | (layout << 61)
 
 
-CANDIDATES = [
-    ("sw32_lbo1_sbo256_v1", template(1, 16, 1, 6)),
-    ("sw32_lbo0_sbo256_v1", template(0, 16, 1, 6)),
-    ("sw32_lbo1_sbo256_v0", template(1, 16, 0, 6)),
+CANDIDATES = [  # 128-byte rows, SWIZZLE_128B: 8-row groups 1024 bytes apart
+    ("sw128_lbo1_sbo1024_v1", template(1, 64, 1, 2)),
+    ("sw128_lbo0_sbo1024_v1", template(0, 64, 1, 2)),
 ]
 
 
@@ -58,11 +57,12 @@ class Plan:
                                     C.c_void_p(self.Q.data_ptr()), C.c_void_p(self.sigma.data_ptr()), None)
         assert rc == 0, rc
 
-    def syrk(self, H, tmpl, dbg=None, dbg_tile=0, max_ctas=0):
+    def syrk(self, H, tmpl, dbg=None, dbg_tile=0, max_ctas=0, prof=None):
         rc = self.L.ozaki_syrk_i8(C.c_void_p(self.Q.data_ptr()), self.m, self.n, self.s, C.c_void_p(self.sigma.data_ptr()),
                                   C.c_void_p(self.tiles.data_ptr()), len(self.tiles_host), C.c_void_p(H.data_ptr()),
                                   C.c_longlong(H.stride(0)), C.c_ulonglong(tmpl), C.c_void_p(self.fail.data_ptr()),
-                                  C.c_void_p(dbg.data_ptr()) if dbg is not None else None, dbg_tile, max_ctas, None)
+                                  C.c_void_p(dbg.data_ptr()) if dbg is not None else None, dbg_tile, max_ctas,
+                                  C.c_void_p(prof.data_ptr()) if prof is not None else None, None)
         assert rc == 0, rc
 
 
@@ -161,10 +161,10 @@ def cmd_full(cand, n, m, s, decades=16):
                       "max_err_vs_dmma_rel_to_sum_abs": float(err.max()), "tiles": len(P.tiles_host)}))
 
 
-def cmd_time(cand, n, m, s):
+def cmd_time(cand, n, m, s, panel=16):
     name, tmpl = CANDIDATES[cand]
     L = lib()
-    P = Plan(L, n, m, s)
+    P = Plan(L, n, m, s, panel=panel)
     Cm, w = problem(n, m)
     H = torch.zeros((n, n + (-n) % 16), dtype=torch.float64, device="cuda")
     t_slice = timed(lambda: P.slice(Cm, w))
@@ -173,12 +173,18 @@ def cmd_time(cand, n, m, s):
     from ipm_b200 import _abi
     t_dmma = timed(lambda: _abi.call("ipm_gemm_tn_f64", Cm.data_ptr(), n, Cm.data_ptr(), n, w.data_ptr(), 1.0, 0.0,
                                      Href.data_ptr(), H.stride(0), n, n, m, 1, None))
+    prof = torch.zeros((148, 8), dtype=torch.int64, device="cuda")
+    P.syrk(H, tmpl, prof=prof)
+    torch.cuda.synchronize()
+    pm = prof.double().mean(dim=0).tolist()
+    waits = {"mma_wait_A_frac": pm[0] / pm[3], "mma_wait_B_frac": pm[1] / pm[3], "mma_wait_tmem_frac": pm[2] / pm[3],
+             "mma_thread_cycles": pm[3], "producer_wait_A_frac": pm[4] / pm[3], "producer_wait_B_frac": pm[5] / pm[3]}
     pairs = s * (s + 1) // 2
     ops = 2.0 * len(P.tiles_host) * 128 * 64 * P.k_pad * pairs
-    print(json.dumps({"mode": "time", "candidate": name, "n": n, "m": m, "s": s, "fail_code": int(P.fail.item()),
+    print(json.dumps({"mode": "time", "candidate": name, "n": n, "m": m, "s": s, "panel": panel, "fail_code": int(P.fail.item()),
                       "slice_ms": t_slice, "syrk_i8_ms": t_syrk, "total_ms": t_slice + t_syrk, "dmma_syrk_ms": t_dmma,
                       "speedup": t_dmma / (t_slice + t_syrk), "int8_tops": ops / (t_syrk * 1e-3) / 1e12,
-                      "slice_GBps": (8.0 * n * m * 2 + s * n * m) / (t_slice * 1e-3) / 1e9}))
+                      "slice_GBps": (8.0 * n * m * 2 + s * n * m) / (t_slice * 1e-3) / 1e9, "waits": waits}))
 
 
 def sub(*args, timeout=120):
@@ -227,5 +233,9 @@ if __name__ == "__main__":
     elif mode == "full":
         cmd_full(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]),
                  int(sys.argv[6]) if len(sys.argv) > 6 else 16)
+    elif mode == "panels":
+        for panel in (2, 4, 8, 16, 32, 128):
+            sub("time", 0, 8192, 16384, 8, panel, timeout=300)
     else:
-        cmd_time(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]))
+        cmd_time(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]),
+                 int(sys.argv[6]) if len(sys.argv) > 6 else 16)
