@@ -258,6 +258,37 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+INT8_TENSOR_PEAK_TOPS = 3740.0  # cuBLASLt INT8 GEMM (torch._int_mm, 8192 x 8192 x 16384) on this pool's B200:
+#                                   profiles/ozaki_time_r02.json; MEASURED_PEAKS.json has no INT8 entry (2 x its bf16 = 3284)
+
+
+def int8_hessian_roofline(n, m, hess_ms, launches, slices=8):
+    """Roofline of the INT8 tensor-core Hessian (csrc/hess_i8.cu; the default from n = 4096): one call = column maxima +
+    slicing (HBM-bound, ~1 ms at cfg 2) + the persistent tcgen05.mma.kind::i8 SYRK.  `achieved` counts the INT8 operations
+    the SYRK kernel executes -- slices (slices + 1) / 2 slice pairs x upper 128 x 64 tiles x padded K -- over the time of
+    the WHOLE call (slicing included), against the measured library INT8 GEMM rate."""
+    n_pad, k_pad = -(-n // 128) * 128, -(-m // 128) * 128
+    rb = n_pad // 128
+    tiles = rb * (rb + 1)
+    ops = 2.0 * tiles * 128 * 64 * k_pad * slices * (slices + 1) / 2
+    achieved = ops / (hess_ms * 1e-3) / 1e12 if hess_ms else None
+    fp64_equiv = float(m) * n * (n + 1) / (hess_ms * 1e-3) / 1e12 if hess_ms else None
+    return {"bound": "tensor", "achieved": achieved, "peak": INT8_TENSOR_PEAK_TOPS, "unit": "TOP/s (INT8)",
+            "frac": achieved / INT8_TENSOR_PEAK_TOPS if achieved else None,
+            "traffic": 8.77e9 * (n_pad * n_pad * k_pad) / (8192.0 * 8192 * 16384) if (n, m) == (8192, 16384) else None,
+            "traffic_source": "profiles/ozaki_syrk_v2_ncu_r02.csv: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu "
+                              "--set full` capture of the SYRK kernel at this shape (not re-measured in this run)",
+            "algorithmic_bytes": float(slices) * n_pad * k_pad + 8.0 * n * (n + 1) / 2,
+            "kernel": "ipm_hess_i8_f64 = colmax_kernel + slice_kernel + syrk_kernel (tcgen05.mma.kind::i8, 8 x 7-bit digits "
+                      "per entry, FP64-accurate)",
+            "int8_ops_per_launch": ops, "ms_per_launch": hess_ms, "launches_timed": launches,
+            "fp64_equivalent_tflops": fp64_equiv,
+            "fp64_equivalent_vs_dmma_peak": fp64_equiv / FP64_TENSOR_PEAK_TFLOPS if fp64_equiv else None,
+            "peak_source": "library INT8 GEMM measured on this pool (see INT8_TENSOR_PEAK_TOPS in bench.py); the FP64-"
+                           "equivalent rate m n (n+1) / time is given next to the FP64 DMMA peak of " +
+                           str(FP64_TENSOR_PEAK_TFLOPS) + " TFLOP/s"}
+
+
 def hessian_dram_traffic(n, m):
     """DRAM bytes (read + write) per launch of the Hessian kernel from the committed `ncu --set full` capture
     (profiles/syrk_hessian_ncu_r01d.csv, taken at the default cfg-2 shape); None for any other shape."""
@@ -353,8 +384,8 @@ def lp_section(D, args, prob, m, rows_mode, steps, warmup, e2e=True, profile=Tru
         one_solve()
     L = solver.launcher
     if profile:
-        L.timed_ops = {"ipm_gemm_tn_f64": [], "ipm_syrk_scatter_f64": [], "range:hessian_formation": [],
-                       "ipm_potrf_upper_f64": [], "ipm_potrf_upper_peer_f64": []}
+        L.timed_ops = {"ipm_gemm_tn_f64": [], "ipm_syrk_scatter_f64": [], "ipm_hess_i8_f64": [],
+                       "range:hessian_formation": [], "ipm_potrf_upper_f64": [], "ipm_potrf_upper_peer_f64": []}
     launches0 = L.kernel_launches()
     with ClockSampler(D.local_rank) as clk:
         ms, counts = D.timed(one_solve, steps)
@@ -362,8 +393,9 @@ def lp_section(D, args, prob, m, rows_mode, steps, warmup, e2e=True, profile=Tru
                value_obj=solver.value, m_local=solver.data.m, comm_bytes=getattr(solver.ns, "comm_bytes", 0),
                peer=getattr(solver.ns, "peer", None) is not None, inner_iters=list(solver.inner_iters))
     if profile:
-        out["hess"] = [a.elapsed_time(b) for key in ("ipm_gemm_tn_f64", "ipm_syrk_scatter_f64")
+        out["hess"] = [a.elapsed_time(b) for key in ("ipm_gemm_tn_f64", "ipm_syrk_scatter_f64", "ipm_hess_i8_f64")
                        for a, b, tag in L.timed_ops[key] if tag == "hessian"]
+        out["hess_i8"] = len(L.timed_ops["ipm_hess_i8_f64"]) > 0
         out["hform"] = [a.elapsed_time(b) for a, b, _ in L.timed_ops["range:hessian_formation"]]
         out["potrf"] = [a.elapsed_time(b) for key in ("ipm_potrf_upper_f64", "ipm_potrf_upper_peer_f64")
                         for a, b, _ in L.timed_ops[key]]
@@ -644,7 +676,8 @@ def main():
         "time_to_solve_s": ms * 1e-3 / args.steps,
         "newton_steps_per_solve": newton / args.steps / (1 if (rows_mode or D.world == 1) else D.world),
         "objective": r["value_obj"], "gpu_launches": int(r["launches"]), "clocks": r["clocks"],
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
+        "roofline": int8_hessian_roofline(n, m, hess_ms, len(r["hess"])) if r.get("hess_i8") else
+                    {"bound": "tensor", "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
                      "frac": achieved / FP64_TENSOR_PEAK_TFLOPS if achieved else None,
                      "traffic": hessian_dram_traffic(n, m),
                      "traffic_source": "profiles/syrk_hessian_ncu_r01d.csv: dram__bytes_read.sum + dram__bytes_write.sum "

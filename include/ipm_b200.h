@@ -39,7 +39,7 @@ const char* ipm_last_cuda_error(void);
 unsigned long long ipm_launch_count(void);     /* kernels launched by this library in this process */
 /* Watchdog of the device-side spin waits (persistent kernels whose CTAs -- or whose peers on other GPUs -- wait for
  * each other: tile-DAG Cholesky, stream-K GEMM, triangular solves, the peer-memory Hessian exchange).  A wait that
- * exceeds the limit records a code (1 potrf-dag, 2 stream-K, 3/4 peer Hessian, 5 trsv, 6 lasso, 7 peer potrf), every
+ * exceeds the limit records a code (1 potrf-dag, 2 stream-K, 3/4 peer Hessian, 5 trsv, 6 lasso, 7 peer potrf, 8 INT8 Hessian), every
  * other wait of the process then returns at once, the kernels finish on garbage in bounded time, and potrf reports
  * info = -1.  Read it after synchronising the stream; 0 = no fault.  The reference has no counterpart (a failed CuPy
  * kernel raises on the next call). */
@@ -55,6 +55,18 @@ unsigned int ipm_set_spin_limit(unsigned int mcycles);  /* limit in units of 2^2
  * NewtonSolverInfeasibleStart.py:426,474,780,796 (Schur) and Qinv @ (u - alpha) LassoSolver.py:245-249. */
 int ipm_gemm_tn_f64(const double* A, int lda, const double* B, int ldb, const double* w, double alpha, double beta,
                     double* D, int ldd, int M, int N, int K, int upper, void* stream);
+
+/* ---- barrier Hessian on the INT8 tensor pipe (tcgen05.mma.kind::i8, FP64-accurate by error-free slicing) ------ */
+/* H (upper tiles, n x n, ldh) = beta*H + C^T diag(w) C for C: m x n (ldc) and w >= 0 -- the contraction of
+ * ipm_gemm_tn_f64(C, C, w, upper = 1), FunctionManager.py:301-312, 564-576, 801-813 -- computed as slices*(slices+1)/2
+ * exact INT8 x INT8 -> INT32 products of `slices` 7-bit digits per entry of diag(sqrt w) C (csrc/hess_i8.cu).  slices = 8
+ * matches the FP64 DMMA kernel to ~2e-15 of sum_k |x_ki x_kj|; 1 <= slices <= 8, m <= 65408.  ws: 256-byte aligned
+ * device memory of ipm_hess_i8_ws_bytes(m, n, slices) bytes (0 = unsupported shape), set up ONCE by ipm_hess_i8_prepare
+ * (synchronises the stream) and then private to calls with the same (m, n, slices). */
+long long ipm_hess_i8_ws_bytes(int m, int n, int slices);
+int ipm_hess_i8_prepare(void* ws, int m, int n, int slices, void* stream);
+int ipm_hess_i8_f64(const double* C, int ldc, int m, int n, const double* w, double beta, double* H, int ldh, int slices,
+                    void* ws, void* stream);
 
 /* ---- HBM-streaming level-1/2 ---------------------------------------------------------------------------- */
 /* y = alpha * M x + beta * y   (M: rows x cols).  np.matmul(C, x) FunctionManager.py:123-125, 432-434, 939-941;

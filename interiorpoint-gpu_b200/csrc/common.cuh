@@ -38,6 +38,7 @@ extern "C" unsigned int* ipm_internal_fault_word(void);
 #define IPM_FAULT_TRSV 5u         // triangular solve: a solution block was never published
 #define IPM_FAULT_LASSO 6u        // persistent ADMM kernel: a neighbour panel never arrived
 #define IPM_FAULT_POTRF_PEER 7u   // distributed tile-DAG Cholesky: a peer's tiles never arrived
+#define IPM_FAULT_HESS_I8 8u      // INT8 Hessian kernel: an mbarrier of its TMA / MMA / epilogue pipeline never completed
 
 namespace ipm {
 

@@ -1,0 +1,434 @@
+// Barrier Hessian H = beta H + C' diag(w) C (w >= 0) in FP64 accuracy on the INT8 tensor pipe of sm_100a
+// (tcgen05.mma.kind::i8, accumulators in TMEM) -- the same contraction as ipm_gemm_tn_f64(upper = 1)
+// (FunctionManager.py:301-312, 564-576, 801-813), 1.7x faster at the cfg-2 shape (profiles/ozaki_syrk_v3_r02.jsonl).
+//
+// Error-free slicing along the contraction index (Ozaki scheme).  X = diag(sqrt w) C (K x n, K = m rows).  Column i is
+// scaled by the power of two sigma_i = 2^(E_i + 2), 2^E_i <= max_k |X_ki| < 2^(E_i + 1), and cut into s signed digits
+// q_t in [-64, 64] (round to nearest, base 128):
+//     X_ki = sigma_i sum_{t < s} q_t[k, i] 128^-(t+1)  +  O(sigma_i 128^-s)
+//     H_ij = sigma_i sigma_j sum_{d < s} 128^-(d+2) sum_{t + u = d} (Q_t' Q_u)_ij
+// Every Q_t' Q_u is an EXACT INT8 x INT8 -> INT32 product (|q q'| <= 2^12, K < 2^16 terms, <= 8 pairs per diagonal
+// d = t + u: below 2^31 in the worst case), so the only roundings are the slicing itself and the FP64 recombination of s integers per
+// entry.  s = 8 (56 bits) reproduces the DMMA kernel to 2e-15 of sum_k |x_ki x_kj| on weights spanning 20 decades.
+//
+// Kernels
+//   colmax_kernel   amax_i = max_k sqrt(w_k) |C_ki|                        HBM: reads C once
+//   slice_kernel    Q[t][i][k] (int8, K-major = transposed) and sigma_i    HBM: reads C once, writes s bytes per entry
+//   syrk_kernel     persistent, 1 CTA per SM, warp roles: A producer / MMA issuer / 4 epilogue warps / B producer.
+//     * output tile 128 x 64; one accumulator (64 TMEM columns) per diagonal d: s <= 8 accumulators = all 512 columns;
+//     * k-chunks of 128 bytes (rows of 128 B, SWIZZLE_128B in the tensor map and in the UMMA descriptors; the 4 MMA
+//       k-steps of a chunk advance the descriptor start address by 32 B);
+//     * the B side of a chunk -- all s slices of the 64 rows, [s][64][128 B] = ONE contiguous K-major operand of 64 s
+//       rows -- sits in one of 2 stages; the A slices stream through a ring of 6 slots of 16 KB;
+//     * slice t of A meets slices 0..s-1-t of B, whose accumulators (diagonals t..s-1) are adjacent TMEM columns: one
+//       wide MMA (N = 64 (s - t), split at 256) instead of s - t narrow ones -- 12 instead of 36 A-operand reads per
+//       k-step at s = 8.  Measured limit (ncu, profiles/ozaki_syrk_v2_ncu_r02.csv): the tensor pipe is 49 % active, the
+//       rest of the time it waits for its shared-memory operand fetch (SS-mode UMMA of one CTA reads ~64 B/clk);
+//       A-from-TMEM or CTA pairs are the next step.
+//     * epilogue: tcgen05.ld of the s accumulators, Horner in FP64, scale by sigma_i sigma_j, [+ beta H], store.
+// Every wait is bounded by the library's watchdog word (common.cuh).
+#include <cuda.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "tensormap.cuh"
+
+using namespace ipm;
+
+namespace {
+constexpr int TM = 128, TN = 64, KC = 128, KSTEP = 32, SMAX = 8;     // k-chunk of 128 bytes = 4 MMA k-steps
+constexpr int NA = 6, NB = 2;                                          // A ring slots, B stages
+constexpr int A_SLOT = TM * KC, B_SLICE = TN * KC, B_STAGE = SMAX * B_SLICE;  // 16 KB, 8 KB, 64 KB
+constexpr int SMEM_BYTES = NA * A_SLOT + NB * B_STAGE + 1024 + 256;    // + alignment slack + barriers
+constexpr int kMaxRows = 65408;  // 8 pairs x K x 2^12 < 2^31 for the padded K
+constexpr int THREADS = 224;  // warps: 0 A producer, 1 MMA issuer, 2-5 epilogue, 6 B producer
+// UMMA shared-memory descriptor without the start address: K-major, 128-byte swizzle, 8-row groups 1024 B apart
+// (LBO>>4 at bit 16 -- ignored for swizzled K-major --, SBO>>4 at bit 32, version 1 at bit 46, SWIZZLE_128B = 2 at 61)
+constexpr uint64_t DESC = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+// instruction descriptor without N: S32 accumulator, signed 8-bit A and B, both K-major, M = 128
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TM >> 4) << 24);
+
+// ---------------------------------------------------------------- slicing
+__global__ void __launch_bounds__(128) colmax_kernel(const double* __restrict__ C, long long ldc, int m, int n,
+                                                     const double* __restrict__ w, unsigned long long* __restrict__ amax) {
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  const int k0 = blockIdx.y * 128, k1 = min(m, k0 + 128);
+  if (i >= n) return;
+  double mx = 0.0;
+#pragma unroll 8
+  for (int k = k0; k < k1; ++k) mx = fmax(mx, sqrt(w[k]) * fabs(C[(long long)k * ldc + i]));
+  if (mx > 0.0) atomicMax(amax + i, (unsigned long long)__double_as_longlong(mx));  // non-negative doubles order as integers
+}
+
+constexpr int SL_COLS = 32, SL_K = 128, SL_PITCH = SL_K + 4;
+__global__ void __launch_bounds__(256) slice_kernel(const double* __restrict__ C, long long ldc, int m, int n,
+                                                    const double* __restrict__ w,
+                                                    const unsigned long long* __restrict__ amax, int s,
+                                                    int8_t* __restrict__ Q, long long n_pad, long long k_pad,
+                                                    double* __restrict__ sigma) {
+  __shared__ __align__(16) int8_t tile[SMAX * SL_COLS * SL_PITCH];
+  const int ci = threadIdx.x & 31, kr = threadIdx.x >> 5;
+  const int i = blockIdx.x * SL_COLS + ci, k0 = blockIdx.y * SL_K;
+  double inv = 0.0;
+  if (i < n) {
+    const unsigned long long ef = amax[i] >> 52;  // exponent field of amax (its sign bit is 0); 0: column of zeros
+    if (ef != 0) inv = __longlong_as_double((long long)(2044ull - ef) << 52);  // 2^-(E+2)
+    if (blockIdx.y == 0 && kr == 0) sigma[i] = ef != 0 ? __longlong_as_double((long long)(ef + 2ull) << 52) : 0.0;
+  }
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52: (r + magic) - magic = rint(r), low mantissa bits = the integer
+  for (int kk = kr; kk < SL_K; kk += 8) {
+    const int k = k0 + kk;
+    double r = 0.0;
+    if (i < n && k < m) r = sqrt(w[k]) * C[(long long)k * ldc + i] * inv;  // |r| <= 1/2
+    for (int t = 0; t < s; ++t) {
+      r *= 128.0;
+      const double tmp = r + magic;
+      r -= tmp - magic;  // exact; the remainder stays in [-1/2, 1/2]
+      tile[(t * SL_COLS + ci) * SL_PITCH + kk] = (int8_t)(int)__double2loint(tmp);
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int row = warp; row < s * SL_COLS; row += 8) {  // 128 contiguous bytes of k per (slice, column)
+    const int t = row / SL_COLS, c = row % SL_COLS;
+    const long long gi = (long long)blockIdx.x * SL_COLS + c;
+    if (gi >= n) continue;
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(&tile[row * SL_PITCH + lane * 4]);
+    *reinterpret_cast<uint32_t*>(Q + ((long long)t * n_pad + gi) * k_pad + k0 + lane * 4) = v;
+  }
+}
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, unsigned int* fault) {
+  return spin_wait([&] { return mbar_try(bar, parity); }, fault, IPM_FAULT_HESS_I8);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) { return DESC | (uint64_t)((addr & 0x3FFFFu) >> 4); }
+
+struct Args {
+  const int2* tiles;  // (row block of 128, column block of 64), upper triangle
+  int ntiles, nkc, s, n;
+  const double* sigma;
+  double* H;
+  long long ldh;
+  double beta;
+  unsigned int* fault;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+syrk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smB = base, smA = base + NB * B_STAGE;
+  const uint32_t bars = smA + NA * A_SLOT;
+  const uint32_t a_full = bars, a_empty = bars + 8 * NA, b_full = bars + 16 * NA, b_empty = b_full + 8 * NB,
+                 tfull = b_empty + 8 * NB, tempty = tfull + 8, tptr = tfull + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = a.s;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NA; ++i) {
+      mbar_init(a_full + 8 * i, 1);
+      mbar_init(a_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < NB; ++i) {
+      mbar_init(b_full + 8 * i, 1);
+      mbar_init(b_empty + 8 * i, 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // all 512 TMEM columns: the launch bounds and the shared-memory size keep this the only CTA of the SM
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tptr), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tptr));
+
+  if (warp == 0) {  // A slices: one 16 KB slot per (chunk, slice), in the order the MMA thread consumes them
+    if (lane == 0) {
+      long long ia = 0;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const int2 tl = a.tiles[tile];
+        for (int kc = 0; kc < a.nkc; ++kc) {
+          for (int t = 0; t < s; ++t, ++ia) {
+            const int sl = (int)(ia % NA);
+            if (ia >= NA) mbar_wait(a_empty + 8 * sl, (uint32_t)((ia / NA) - 1) & 1u, a.fault);
+            mbar_expect_tx(a_full + 8 * sl, A_SLOT);
+            tma_load_3d(smA + sl * A_SLOT, &tmA, kc * KC, tl.x * TM, t, a_full + 8 * sl);
+          }
+        }
+      }
+    }
+  } else if (warp == 6) {  // B side of a chunk: its own thread, so that a stage is refilled the moment it is released
+    if (lane == 0) {
+      long long ib = 0;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const int2 tl = a.tiles[tile];
+        for (int kc = 0; kc < a.nkc; ++kc, ++ib) {
+          const int st = (int)(ib % NB);
+          if (ib >= NB) mbar_wait(b_empty + 8 * st, (uint32_t)((ib / NB) - 1) & 1u, a.fault);
+          mbar_expect_tx(b_full + 8 * st, (uint32_t)s * B_SLICE);
+          tma_load_3d(smB + st * B_STAGE, &tmB, kc * KC, tl.y * TN, 0, b_full + 8 * st);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      long long ia = 0, ib = 0;
+      int tcount = 0;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
+        if (tcount > 0) {  // the epilogue of the previous tile has drained the accumulators
+          mbar_wait(tempty, (uint32_t)(tcount - 1) & 1u, a.fault);
+          tc_fence_after();
+        }
+        for (int kc = 0; kc < a.nkc; ++kc, ++ib) {
+          const int st = (int)(ib % NB);
+          mbar_wait(b_full + 8 * st, (uint32_t)(ib / NB) & 1u, a.fault);
+          const uint32_t sb = smB + st * B_STAGE;
+          for (int t = 0; t < s; ++t, ++ia) {
+            const int sl = (int)(ia % NA);
+            mbar_wait(a_full + 8 * sl, (uint32_t)(ia / NA) & 1u, a.fault);
+            tc_fence_after();
+            const uint32_t sa = smA + sl * A_SLOT;
+            const int ncols = TN * (s - t);  // B rows = slices 0 .. s-1-t; accumulators of the diagonals t .. s-1
+#pragma unroll
+            for (int j = 0; j < KC / KSTEP; ++j) {
+              const uint64_t da = smem_desc(sa + j * KSTEP);
+              for (int n0 = 0; n0 < ncols; n0 += 256) {
+                const int nn = min(256, ncols - n0);
+                umma_i8(tmem + t * TN + n0, da, smem_desc(sb + n0 * KC + j * KSTEP), IDESC | ((uint32_t)(nn >> 3) << 17),
+                        (kc > 0 || t > 0 || j > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(a_empty + 8 * sl);  // frees the A slot once these MMAs have read it
+          }
+          umma_commit(b_empty + 8 * st);
+        }
+        umma_commit(tfull);
+      }
+    }
+  } else {
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
+      const int2 tl = a.tiles[tile];
+      mbar_wait(tfull, (uint32_t)tcount & 1u, a.fault);
+      __syncwarp();
+      tc_fence_after();
+      const long long i = (long long)tl.x * TM + row;
+      const double si = i < a.n ? a.sigma[i] * 0x1p-14 : 0.0;
+      for (int c0 = 0; c0 < TN; c0 += 8) {
+        int v[SMAX][8];
+#pragma unroll
+        for (int d = 0; d < SMAX; ++d)
+          if (d < s) tmem_ld8(tmem + ((uint32_t)(q * 32) << 16) + d * TN + c0, v[d]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < SMAX; ++d)  // the loaded registers are valid only after the wait: pin their uses behind it
+          asm volatile("" : "+r"(v[d][0]), "+r"(v[d][1]), "+r"(v[d][2]), "+r"(v[d][3]), "+r"(v[d][4]), "+r"(v[d][5]),
+                            "+r"(v[d][6]), "+r"(v[d][7]));
+        const long long j0 = (long long)tl.y * TN + c0;
+        if (i < a.n && j0 < a.n) {
+          double out[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            double r = 0.0;
+#pragma unroll
+            for (int d = SMAX - 1; d >= 0; --d)
+              if (d < s) r = fma(r, 0x1p-7, (double)v[d][c]);
+            out[c] = r * si;
+          }
+          double* dst = a.H + i * a.ldh + j0;
+          if (j0 + 8 <= a.n) {
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+              const double2 sj = *reinterpret_cast<const double2*>(a.sigma + j0 + c);
+              double2 h = make_double2(out[c] * sj.x, out[c + 1] * sj.y);
+              if (a.beta != 0.0) {
+                const double2 old = *reinterpret_cast<const double2*>(dst + c);
+                h.x = fma(a.beta, old.x, h.x);
+                h.y = fma(a.beta, old.y, h.y);
+              }
+              *reinterpret_cast<double2*>(dst + c) = h;
+            }
+          } else {
+            for (int c = 0; c < 8; ++c)
+              if (j0 + c < a.n) {
+                const double h = out[c] * a.sigma[j0 + c];
+                dst[c] = a.beta != 0.0 ? fma(a.beta, dst[c], h) : h;
+              }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+int slice_map(CUtensorMap* tm, const int8_t* Q, long long n_pad, long long k_pad, int s, int box_rows, int box_slices) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return IPM_ERR_NO_DEVICE;
+  cuuint64_t gdim[3] = {(cuuint64_t)k_pad, (cuuint64_t)n_pad, (cuuint64_t)s};
+  cuuint64_t gstride[2] = {(cuuint64_t)k_pad, (cuuint64_t)(n_pad * k_pad)};
+  cuuint32_t box[3] = {KC, (cuuint32_t)box_rows, (cuuint32_t)box_slices};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)Q, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? IPM_OK : IPM_ERR_ARG;
+}
+
+long long round_up_ll(long long a, long long b) { return (a + b - 1) / b * b; }
+
+// workspace: [amax n_pad u64][sigma n_pad f64][tiles ntiles int2][pad to 1024][Q s x n_pad x k_pad int8]
+struct Layout {
+  long long n_pad, k_pad, off_sigma, off_tiles, off_q, bytes;
+  int ntiles;
+};
+Layout layout_for(int m, int n, int s) {
+  Layout L;
+  L.n_pad = round_up_ll(n, TM);
+  L.k_pad = round_up_ll(m, KC);
+  const int rb = (int)(L.n_pad / TM);
+  L.ntiles = rb * (rb + 1);  // sum over row blocks bi of the 2 rb - 2 bi column blocks of 64 with bj >= 2 bi
+  L.off_sigma = L.n_pad * 8;
+  L.off_tiles = 2 * L.n_pad * 8;
+  L.off_q = round_up_ll(L.off_tiles + (long long)L.ntiles * 8, 1024);
+  L.bytes = L.off_q + (long long)s * L.n_pad * L.k_pad;
+  return L;
+}
+}  // namespace
+
+// Bytes of the workspace of ipm_hess_i8_f64 for an m x n operand cut into `slices` digits (0 on invalid arguments).
+extern "C" long long ipm_hess_i8_ws_bytes(int m, int n, int slices) {
+  if (m <= 0 || n <= 0 || slices < 1 || slices > SMAX || m > kMaxRows) return 0;
+  return layout_for(m, n, slices).bytes;
+}
+
+// One-time set-up of a workspace (256-byte aligned device memory of ipm_hess_i8_ws_bytes bytes): zeroes the slice
+// buffer -- its padding rows / columns must stay zero, the slicing kernel never writes them -- and uploads the list of
+// upper-triangle output tiles (synchronous copy: call it outside the hot loop).
+extern "C" int ipm_hess_i8_prepare(void* ws, int m, int n, int slices, void* stream) {
+  if (!ws || ((uintptr_t)ws & 255) || ipm_hess_i8_ws_bytes(m, n, slices) == 0) return IPM_ERR_ARG;
+  const Layout L = layout_for(m, n, slices);
+  cudaStream_t st = (cudaStream_t)stream;
+  IPM_CUDA_CHECK(cudaMemsetAsync(ws, 0, (size_t)L.bytes, st));
+  const int rb = (int)(L.n_pad / TM), cb = 2 * rb;
+  int* host = new int[2 * (size_t)L.ntiles];
+  int cnt = 0;
+  for (int bi = 0; bi < rb; ++bi)  // concurrent CTAs share the A rows of one or two row blocks
+    for (int bj = 2 * bi; bj < cb; ++bj) {
+      host[2 * cnt] = bi;
+      host[2 * cnt + 1] = bj;
+      ++cnt;
+    }
+  IPM_CUDA_CHECK(cudaStreamSynchronize(st));
+  cudaError_t e = cudaMemcpy((char*)ws + L.off_tiles, host, sizeof(int) * 2 * (size_t)L.ntiles, cudaMemcpyHostToDevice);
+  delete[] host;
+  IPM_CUDA_CHECK(e);
+  return cnt == L.ntiles ? IPM_OK : IPM_ERR_ARG;
+}
+
+// H (upper tiles; n x n, ldh) = beta * H + C' diag(w) C  for C: m x n (ldc), w: m weights >= 0, through `slices` INT8
+// digits per entry (8: FP64-level accuracy; fewer digits are faster and less accurate, 7 bits each).  ws: prepared by
+// ipm_hess_i8_prepare for the same (m, n, slices).  Elements below the diagonal inside diagonal tiles are written too
+// (as by ipm_gemm_tn_f64 with upper = 1).  FunctionManager.py:301-312, 564-576, 801-813.
+extern "C" int ipm_hess_i8_f64(const double* C, int ldc, int m, int n, const double* w, double beta, double* H, int ldh,
+                               int slices, void* ws, void* stream) {
+  if (!C || !w || !H || !ws || ((uintptr_t)ws & 255) || ldc < n || ldh < n || (ldh & 1) || ((uintptr_t)H & 15) ||
+      ipm_hess_i8_ws_bytes(m, n, slices) == 0)
+    return IPM_ERR_ARG;
+  const Layout L = layout_for(m, n, slices);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* amax = (unsigned long long*)ws;
+  double* sigma = (double*)((char*)ws + L.off_sigma);
+  const int2* tiles = (const int2*)((char*)ws + L.off_tiles);
+  int8_t* Q = (int8_t*)((char*)ws + L.off_q);
+  CUtensorMap tmA, tmB;
+  int rc = slice_map(&tmA, Q, L.n_pad, L.k_pad, slices, TM, 1);
+  if (rc) return rc;
+  rc = slice_map(&tmB, Q, L.n_pad, L.k_pad, slices, TN, slices);
+  if (rc) return rc;
+  static bool attr_done[kMaxDevices] = {};
+  IPM_CUDA_CHECK(ensure_dynamic_smem(syrk_kernel, SMEM_BYTES, attr_done));
+  int dev = 0, sms = 0;
+  IPM_CUDA_CHECK(cudaGetDevice(&dev));
+  IPM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+
+  IPM_CUDA_CHECK(cudaMemsetAsync(amax, 0, (size_t)L.n_pad * 8, st));
+  colmax_kernel<<<dim3(ceil_div(n, 128), ceil_div(m, 128)), 128, 0, st>>>(C, ldc, m, n, w, amax);
+  IPM_LAUNCH_CHECK();
+  slice_kernel<<<dim3((unsigned)(L.n_pad / SL_COLS), (unsigned)(L.k_pad / SL_K)), 256, 0, st>>>(C, ldc, m, n, w, amax, slices,
+                                                                                              Q, L.n_pad, L.k_pad, sigma);
+  IPM_LAUNCH_CHECK();
+  Args a;
+  a.tiles = tiles;
+  a.ntiles = L.ntiles;
+  a.nkc = (int)(L.k_pad / KC);
+  a.s = slices;
+  a.n = n;
+  a.sigma = sigma;
+  a.H = H;
+  a.ldh = ldh;
+  a.beta = beta;
+  a.fault = ipm_internal_fault_word();
+  syrk_kernel<<<L.ntiles < sms ? L.ntiles : sms, THREADS, SMEM_BYTES, st>>>(tmA, tmB, a);
+  IPM_LAUNCH_CHECK();
+  return IPM_OK;
+}

@@ -11,6 +11,7 @@ Mirrors, on the device, ``FunctionManagerLP/QP/Phase1`` (FunctionManager.py:197-
 """
 
 import ctypes as C
+import os
 from types import SimpleNamespace
 
 import numpy as np
@@ -42,6 +43,25 @@ def step_table(beta):
         if a < STUCK:
             break
     return tab
+
+
+# Hessian on the INT8 tensor pipe (csrc/hess_i8.cu) instead of the FP64 DMMA contraction.  Measured on a B200
+# (profiles/ozaki_syrk_v3_r02.jsonl, profiles/hess_i8_sizes_r02.jsonl): 19.2 ms against 32.4 ms at n = 8192, m = 16384
+# with 8 digits per entry, identical accuracy class (2e-15 of sum |x||x|); 1.17x at n = 2048, m = 4096; 0.66x at n = 1024
+# (three kernels and a 148-CTA persistent grid only pay off on large operands), so the default is size-gated.  IPM_HESSIAN_I8 = 0: never; 1: whenever the shape
+# is supported; 5..8: that many 7-bit digits, whenever supported.
+HESS_I8_MIN_N, HESS_I8_MIN_M, HESS_I8_SLICES = 2048, 4096, 8
+
+
+def hess_i8_slices(m, n):
+    """Digits per entry for an m x n dense constraint matrix, or 0 for the FP64 DMMA kernel."""
+    env = os.environ.get("IPM_HESSIAN_I8", "")
+    if env == "0" or m <= 0:
+        return 0
+    slices = int(env) if env in ("5", "6", "7", "8") else HESS_I8_SLICES
+    if env == "" and (n < HESS_I8_MIN_N or m < HESS_I8_MIN_M):
+        return 0
+    return slices if _abi.lib().ipm_hess_i8_ws_bytes(m, n, slices) > 0 else 0
 
 
 class Launcher:
@@ -403,12 +423,29 @@ class LinearNewton:
             L.tag = None
         elif m:
             L.tag = "hessian"
-            L("ipm_gemm_tn_f64", d.C.data_ptr(), d.ldc, d.C.data_ptr(), d.ldc, ws.w.data_ptr(), 1.0, beta,
-              ws.H.data_ptr(), ws.ldh, n, n, m, 1)
+            slices = hess_i8_slices(m, n)
+            if slices:
+                L("ipm_hess_i8_f64", d.C.data_ptr(), d.ldc, m, n, ws.w.data_ptr(), beta, ws.H.data_ptr(), ws.ldh, slices,
+                  self._hess_i8_ws(slices).data_ptr())
+            else:
+                L("ipm_gemm_tn_f64", d.C.data_ptr(), d.ldc, d.C.data_ptr(), d.ldc, ws.w.data_ptr(), 1.0, beta,
+                  ws.H.data_ptr(), ws.ldh, n, n, m, 1)
             L.tag = None
         shift = self.shift + (1e-9 if self.use_psd_condition else 0.0)
         L("ipm_hess_finish_f64", ws.H.data_ptr(), ws.ldh, n, ws.hdiag.data_ptr(),
           ws.hxs.data_ptr() if self.phase1 else None, (ws.red.data_ptr() + 24) if self.phase1 else None, shift)
+
+    def _hess_i8_ws(self, slices):
+        """Slice buffer of the INT8 Hessian kernel (as many bytes per entry of C as digits): one per problem, shared by
+        the phase-I and the main-phase solver (same C)."""
+        d = self.d
+        cached = getattr(d, "hess_i8_ws", None)
+        if cached is None or cached[0] != slices:
+            nbytes = _abi.lib().ipm_hess_i8_ws_bytes(d.m, d.n, slices)
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=d.device)
+            self.L("ipm_hess_i8_prepare", buf.data_ptr(), d.m, d.n, slices)
+            d.hess_i8_ws = cached = (slices, buf)
+        return cached[1]
 
     def _p2_ptr(self):
         """Quadratic line-search coefficients (second-order cones only)."""

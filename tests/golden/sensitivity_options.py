@@ -90,9 +90,35 @@ def large_qp(out):
         print(name, out["cases"][name])
 
 
+# barrier_cases.json entries with a centering step whose count the reference itself does not reproduce under the
+# perturbation (qp_seed1_n100_0: the step after a 21-iteration centering moves over 9..11); the INT8 tensor-core Hessian
+# (different rounding than the FP64 kernel) is held to this envelope there
+SENSITIVE_BARRIER = ["qp_seed1_n100_0"]
+
+
+def barrier_cases(out):
+    with open(os.path.join(HERE, "barrier_cases.json")) as f:
+        cases = {c["name"]: c for c in json.load(f)}
+    for name in SENSITIVE_BARRIER:
+        case = cases[name]
+        runs = [run(case, None)] + [run(case, sd) for sd in range(SEEDS)]
+        assert runs[0]["inner_iters"] == case["inner_iters"], "oracle no longer reproduces the golden"
+        out["cases"][name] = dict(inner_iters=envelope(runs, "inner_iters"),
+                                  phase1_inner_iters=envelope(runs, "phase1_inner_iters"),
+                                  value_spread=float(max(abs(r["value"] - runs[0]["value"]) for r in runs)))
+        print(name, out["cases"][name])
+
+
 def main():
     out = {"relative_perturbation": REL, "perturbed_runs": SEEDS, "cases": {}}
     path = os.path.join(HERE, "sensitivity.json")
+    if "--barrier-only" in sys.argv:  # keep everything else as it is
+        with open(path) as f:
+            out = json.load(f)
+        barrier_cases(out)
+        with open(path, "w") as f:
+            json.dump(out, f, indent=1)
+        return
     if "--large" in sys.argv:
         large_qp(out)
     elif os.path.exists(path):
@@ -124,6 +150,7 @@ def main():
                                        for r in runs[1:])
         out["cases"][case["name"]] = rec
         print(case["name"], rec)
+    barrier_cases(out)
     with open(os.path.join(HERE, "sensitivity.json"), "w") as f:
         json.dump(out, f, indent=1)
 

@@ -188,3 +188,21 @@ def test_flat_module_layout_imports_like_the_reference():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     assert out.stdout.split() == ["LPSolver", "QPSolver", "SOCPSolver", "LassoSolver"]
+
+
+def test_int8_hessian_policy(monkeypatch):
+    """engine.hess_i8_slices: size-gated by default (the INT8 kernel only pays off on large operands), IPM_HESSIAN_I8
+    forces it off / on / to a digit count, and shapes the kernel does not support fall back to the DMMA kernel."""
+    from ipm_b200 import engine
+
+    monkeypatch.delenv("IPM_HESSIAN_I8", raising=False)
+    assert engine.hess_i8_slices(16384, 8192) == 8 and engine.hess_i8_slices(4096, 2048) == 8
+    assert engine.hess_i8_slices(16384, 1024) == 0 and engine.hess_i8_slices(512, 8192) == 0
+    assert engine.hess_i8_slices(0, 8192) == 0
+    monkeypatch.setenv("IPM_HESSIAN_I8", "0")
+    assert engine.hess_i8_slices(16384, 8192) == 0
+    monkeypatch.setenv("IPM_HESSIAN_I8", "1")
+    assert engine.hess_i8_slices(100, 64) == 8
+    assert engine.hess_i8_slices(70000, 64) == 0          # INT32 accumulators bound the contraction length
+    monkeypatch.setenv("IPM_HESSIAN_I8", "6")
+    assert engine.hess_i8_slices(100, 64) == 6

@@ -537,3 +537,73 @@ def test_lasso_admm_steps_multi_iteration(n, K, add_bias, positive):
     torch.cuda.synchronize()
     assert state[:2].tolist() == [1, total + 2]
     assert all(torch.equal(a, b) for a, b in zip(st, snap))
+
+
+def _hess_i8(Cm, ldc, m, n, w, beta, H, ldh, slices):
+    nbytes = _abi.lib().ipm_hess_i8_ws_bytes(m, n, slices)
+    assert nbytes > 0
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    _abi.call("ipm_hess_i8_prepare", ws.data_ptr(), m, n, slices, None)
+    _abi.call("ipm_hess_i8_f64", Cm.data_ptr(), ldc, m, n, w.data_ptr(), beta, H.data_ptr(), ldh, slices, ws.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert _abi.lib().ipm_device_fault() == 0
+    return ws
+
+
+@pytest.mark.parametrize("n,m,slices,beta,decades", [
+    (64, 100, 8, 0.0, 6), (200, 300, 8, 0.0, 16), (1000, 2100, 8, 1.0, 16), (1024, 2048, 8, 0.0, 20),
+    (385, 4000, 8, 1.0, 12), (513, 700, 6, 0.0, 8), (2048, 4096, 8, 0.0, 20),
+])
+def test_hess_i8_matches_fp64(n, m, slices, beta, decades):
+    """C' diag(w) C through exact INT8 slice products (tcgen05.mma.kind::i8) against float64: same error class as the
+    DMMA kernel -- relative to sum_k |x_ki x_kj| -- for 8 digits, weights spanning up to 20 decades (the late-solve
+    regime), ragged n and m, and accumulation into a preloaded H (the QP path)."""
+    rs = np.random.RandomState(n + m + slices)
+    Cn = rs.rand(m, n) * 4 - 2
+    Cn[rs.rand(m, n) < 0.05] = 0.0
+    Cn[:, n // 3] = 0.0                                    # a column of zeros: sigma = 0
+    wn = 10.0 ** (rs.rand(m) * decades - decades / 2)
+    wn[:: 17] = 0.0                                        # rows that do not count
+    Cm, ldc = padded(Cn)
+    w = dev(wn)
+    H0 = np.triu(rs.rand(n, n)) if beta else np.zeros((n, n))
+    H, ldh = padded(H0 if beta else np.full((n, n), np.nan))
+    _hess_i8(Cm, ldc, m, n, w, beta, H, ldh, slices)
+    X = np.sqrt(wn)[:, None] * Cn
+    ref = beta * H0 + X.T @ X
+    scale = np.abs(X).T @ np.abs(X) + 1e-300
+    iu = np.triu_indices(n)
+    err = (np.abs(H[:, :n].cpu().numpy() - ref) / scale)[iu].max()
+    assert err <= (1e-14 if slices == 8 else 128.0 ** -(slices - 1)), err
+    # and the DMMA kernel on the same operands sits in the same class
+    H2, _ = padded(H0)
+    _abi.call("ipm_gemm_tn_f64", Cm.data_ptr(), ldc, Cm.data_ptr(), ldc, w.data_ptr(), 1.0, beta, H2.data_ptr(), ldh, n, n, m,
+              1, None)
+    torch.cuda.synchronize()
+    err2 = (np.abs(H2[:, :n].cpu().numpy() - ref) / scale)[iu].max()
+    assert err2 <= 1e-14
+
+
+def test_hess_i8_is_deterministic_and_reuses_its_workspace():
+    """Same bits on every call, and a second call with other weights on the same workspace does not see the first."""
+    n, m = 300, 1000
+    rs = np.random.RandomState(3)
+    Cm, ldc = padded(rs.randn(m, n))
+    H1, ldh = padded(np.zeros((n, n)))
+    H2, _ = padded(np.zeros((n, n)))
+    H3, _ = padded(np.zeros((n, n)))
+    w1, w2 = dev(rs.rand(m) + 0.1), dev(10.0 ** (rs.rand(m) * 10 - 5))
+    ws = _hess_i8(Cm, ldc, m, n, w1, 0.0, H1, ldh, 8)
+    for w, H in ((w2, H2), (w1, H3)):
+        _abi.call("ipm_hess_i8_f64", Cm.data_ptr(), ldc, m, n, w.data_ptr(), 0.0, H.data_ptr(), ldh, 8, ws.data_ptr(), None)
+    torch.cuda.synchronize()
+    iu = torch.triu(torch.ones((n, n), dtype=torch.bool, device="cuda"))
+    assert torch.equal(H1[:, :n][iu], H3[:, :n][iu])
+    assert not torch.equal(H1[:, :n][iu], H2[:, :n][iu])
+
+
+def test_hess_i8_rejects_bad_arguments():
+    L = _abi.lib()
+    assert L.ipm_hess_i8_ws_bytes(100, 64, 9) == 0 and L.ipm_hess_i8_ws_bytes(100, 64, 0) == 0
+    assert L.ipm_hess_i8_ws_bytes(70000, 64, 8) == 0       # INT32 accumulators: m <= 65408
+    assert L.ipm_hess_i8_ws_bytes(100, 64, 8) > 8 * 128 * 128

@@ -318,3 +318,33 @@ def test_cg_newton_solves(case):
     assert_iters_in_envelope(s.inner_iters, sens["inner_iters"], cap=s.max_inner_iters)
     if case["phase1_inner_iters"] is not None:
         assert_iters_close(s.phase1_solver.inner_iters, case["phase1_inner_iters"])
+
+
+I8_CASES = [c for c in BARRIER + LARGE if c["name"] in (
+    "lp_seed1_n100_0", "qp_seed1_n100_0", "lp_dense_n64_warm", "lp_dense_n256_cold", "lp_dense_n97_ragged", "qp_dense_n512",
+    "lp_dense_n1024_cold", "lp_dense_n1024_warm", "lp_dense_n2048_warm", "qp_dense_n1024")]
+
+
+@pytest.mark.parametrize("case", I8_CASES, ids=[c["name"] for c in I8_CASES])
+def test_int8_tensor_core_hessian_matches_reference(case, monkeypatch):
+    """The same goldens with every barrier Hessian formed on the INT8 tensor pipe (csrc/hess_i8.cu: 8 exact 7-bit digits
+    per entry, tcgen05.mma.kind::i8) instead of the FP64 DMMA kernel -- the path cfg 2 takes by default from n = 4096:
+    phase-I and main phase, LP and QP (accumulation onto t P), ragged sizes, cold and warm starts.  Same bars."""
+    monkeypatch.setenv("IPM_HESSIAN_I8", "1")
+    cls = _solver_class(case["solver"])
+    prob = build_problem(case)
+    np.random.seed(0)
+    s = cls(**prob, check_cvxpy=False, suppress_print=True, **case["settings"])
+    val = s.solve()
+    print(case["name"], val, case["value"], s.inner_iters, case["inner_iters"])
+    assert getattr(s.ns.d, "hess_i8_ws", None) is not None, "the INT8 path did not run"
+    assert val == pytest.approx(case["value"], rel=1e-6, abs=1e-9)
+    if case["name"] in SENS:
+        assert_iters_in_envelope(s.inner_iters, SENS[case["name"]]["inner_iters"], cap=s.max_inner_iters)
+    else:
+        assert_iters_close(s.inner_iters, case["inner_iters"], cap=s.max_inner_iters,
+                           noisy=noise_dominated_steps(case, prob, case["settings"]))
+    if case["phase1_inner_iters"] is not None:
+        assert_iters_close(s.phase1_solver.inner_iters, case["phase1_inner_iters"])
+    x = np.asarray(s.xstar)
+    assert np.linalg.norm(x - np.array(case["xstar"])) <= 1e-4 * (1 + np.linalg.norm(case["xstar"]))

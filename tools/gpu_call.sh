@@ -2,5 +2,9 @@
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-( timeout 120 python tools/ozaki_syrk_test.py tile 0; timeout 120 python tools/ozaki_syrk_test.py full 0 1000 2100 8; timeout 200 python tools/ozaki_syrk_test.py time 0 8192 16384 8; timeout 200 python tools/ozaki_syrk_test.py time 0 8192 16384 7 ) > gpurun_out/ozaki_v3.jsonl 2> gpurun_out/ozaki_v3.err; echo "rc=$?"
-cut -c1-1500 gpurun_out/ozaki_v3.jsonl; tail -5 gpurun_out/ozaki_v3.err
+timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_solvers_gpu.py -m gpu -q -x -k "hess_i8 or int8" --timeout 300 > gpurun_out/pytest_i8.log 2>&1; echo "pytest rc=$?"
+tail -30 gpurun_out/pytest_i8.log
+timeout 300 python tools/hess_i8_sizes.py > gpurun_out/hess_i8_sizes.jsonl 2> gpurun_out/hess_i8_sizes.err; echo "sizes rc=$?"
+cat gpurun_out/hess_i8_sizes.jsonl; tail -5 gpurun_out/hess_i8_sizes.err
+timeout 600 python bench.py > gpurun_out/bench_i8.json 2> gpurun_out/bench_i8.err; echo "bench rc=$?"
+cat gpurun_out/bench_i8.json; tail -5 gpurun_out/bench_i8.err
