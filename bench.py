@@ -509,11 +509,12 @@ def socp_section(D, args, rows_mode):
                    shard_rows=rows_mode, **problems.SOCP_TEST_SETTINGS)
     del prob
     L = s.launcher
-    L.timed_ops = {"ipm_gemm_tn_f64": [], "ipm_syrk_scatter_f64": [], "range:hessian_formation": [],
+    L.timed_ops = {"ipm_gemm_tn_f64": [], "ipm_syrk_scatter_f64": [], "ipm_hess_i8_f64": [], "range:hessian_formation": [],
                    "ipm_potrf_upper_f64": [], "ipm_potrf_upper_peer_f64": []}
     ms, counts = D.timed(lambda: (s.solve(), sum(s.inner_iters))[1], 1)
-    hess = [a.elapsed_time(b) for key in ("ipm_gemm_tn_f64", "ipm_syrk_scatter_f64")
+    hess = [a.elapsed_time(b) for key in ("ipm_gemm_tn_f64", "ipm_syrk_scatter_f64", "ipm_hess_i8_f64")
             for a, b, tag in L.timed_ops[key] if tag == "hessian"]
+    hess_i8 = len(L.timed_ops["ipm_hess_i8_f64"]) > 0
     hform = [a.elapsed_time(b) for a, b, _ in L.timed_ops["range:hessian_formation"]]
     potrf = [a.elapsed_time(b) for key in ("ipm_potrf_upper_f64", "ipm_potrf_upper_peer_f64")
              for a, b, _ in L.timed_ops[key]]
@@ -526,7 +527,8 @@ def socp_section(D, args, rows_mode):
            "configs[3]); one SOCPSolver.solve()" + (", whole cones sharded over the GPUs" if rows_mode else ""),
            "time_to_solve_s": ms * 1e-3, "newton_steps": int(steps), "ms_per_newton_step": ms / steps,
            "value": steps / (ms * 1e-3), "unit": "Newton steps/s", "objective": s.value,
-           "roofline": {"bound": "tensor", "kernel": "gemm_tn_persistent_kernel (W' diag(w) W, rows of this rank)",
+           "roofline": int8_hessian_roofline(n, rows_local, hess_ms, len(hess)) if hess_i8 else
+                       {"bound": "tensor", "kernel": "gemm_tn_persistent_kernel (W' diag(w) W, rows of this rank)",
                         "achieved": flops / (hess_ms * 1e-3) / 1e12 if hess_ms else None, "peak": FP64_TENSOR_PEAK_TFLOPS,
                         "unit": "TFLOP/s per GPU",
                         "frac": flops / (hess_ms * 1e-3) / 1e12 / FP64_TENSOR_PEAK_TFLOPS if hess_ms else None,

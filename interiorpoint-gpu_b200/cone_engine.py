@@ -12,10 +12,10 @@ import torch
 
 try:
     from . import _abi
-    from .engine import F64, LinearNewton, _round_up, to_dev_matrix, to_dev_vector
+    from .engine import F64, LinearNewton, _round_up, hess_i8_slices, to_dev_matrix, to_dev_vector
 except ImportError:  # flat-module use
     import _abi
-    from engine import F64, LinearNewton, _round_up, to_dev_matrix, to_dev_vector
+    from engine import F64, LinearNewton, _round_up, hess_i8_slices, to_dev_matrix, to_dev_vector
 
 
 class ConeProblemData:
@@ -163,8 +163,13 @@ class ConeNewton(LinearNewton):
             L("ipm_scale_copy_upper_f64", ws.H.data_ptr(), ws.ldh, d.P.data_ptr(), d.ldp, n, t)
             beta = 1.0
         L.tag = "hessian"
-        L("ipm_gemm_tn_f64", d.W.data_ptr(), d.ldw, d.W.data_ptr(), d.ldw, ws.wts.data_ptr(), 1.0, beta, ws.H.data_ptr(),
-          ws.ldh, n, n, d.rows_w, 1)
+        slices = hess_i8_slices(d.rows_w, n)  # all SYRK weights are positive (2 / slack, 1): csrc/cone.cu
+        if slices:
+            L("ipm_hess_i8_f64", d.W.data_ptr(), d.ldw, d.rows_w, n, ws.wts.data_ptr(), beta, ws.H.data_ptr(), ws.ldh, slices,
+              self._hess_i8_ws(slices, d.rows_w).data_ptr())
+        else:
+            L("ipm_gemm_tn_f64", d.W.data_ptr(), d.ldw, d.W.data_ptr(), d.ldw, ws.wts.data_ptr(), 1.0, beta,
+              ws.H.data_ptr(), ws.ldh, n, n, d.rows_w, 1)
         L.tag = None
         shift = self.shift + (1e-9 if self.use_psd_condition else 0.0)
         L("ipm_hess_finish_f64", ws.H.data_ptr(), ws.ldh, n, ws.hdiag.data_ptr() if d.nbounds else None,

@@ -435,16 +435,17 @@ class LinearNewton:
         L("ipm_hess_finish_f64", ws.H.data_ptr(), ws.ldh, n, ws.hdiag.data_ptr(),
           ws.hxs.data_ptr() if self.phase1 else None, (ws.red.data_ptr() + 24) if self.phase1 else None, shift)
 
-    def _hess_i8_ws(self, slices):
-        """Slice buffer of the INT8 Hessian kernel (as many bytes per entry of C as digits): one per problem, shared by
-        the phase-I and the main-phase solver (same C)."""
+    def _hess_i8_ws(self, slices, rows=None):
+        """Slice buffer of the INT8 Hessian kernel (as many bytes per entry of the operand as digits): one per problem,
+        shared by the phase-I and the main-phase solver (same operand shape)."""
         d = self.d
+        rows = d.m if rows is None else rows
         cached = getattr(d, "hess_i8_ws", None)
-        if cached is None or cached[0] != slices:
-            nbytes = _abi.lib().ipm_hess_i8_ws_bytes(d.m, d.n, slices)
+        if cached is None or cached[0] != (slices, rows):
+            nbytes = _abi.lib().ipm_hess_i8_ws_bytes(rows, d.n, slices)
             buf = torch.empty(nbytes, dtype=torch.uint8, device=d.device)
-            self.L("ipm_hess_i8_prepare", buf.data_ptr(), d.m, d.n, slices)
-            d.hess_i8_ws = cached = (slices, buf)
+            self.L("ipm_hess_i8_prepare", buf.data_ptr(), rows, d.n, slices)
+            d.hess_i8_ws = cached = ((slices, rows), buf)
         return cached[1]
 
     def _p2_ptr(self):

@@ -322,14 +322,16 @@ def test_cg_newton_solves(case):
 
 I8_CASES = [c for c in BARRIER + LARGE if c["name"] in (
     "lp_seed1_n100_0", "qp_seed1_n100_0", "lp_dense_n64_warm", "lp_dense_n256_cold", "lp_dense_n97_ragged", "qp_dense_n512",
-    "lp_dense_n1024_cold", "lp_dense_n1024_warm", "lp_dense_n2048_warm", "qp_dense_n1024")]
+    "lp_dense_n1024_cold", "lp_dense_n1024_warm", "lp_dense_n2048_warm", "qp_dense_n1024", "socp_n48_warm", "socp_n48_cold",
+    "socp_n96_warm", "socp_n48_eq_warm")]
 
 
 @pytest.mark.parametrize("case", I8_CASES, ids=[c["name"] for c in I8_CASES])
 def test_int8_tensor_core_hessian_matches_reference(case, monkeypatch):
     """The same goldens with every barrier Hessian formed on the INT8 tensor pipe (csrc/hess_i8.cu: 8 exact 7-bit digits
     per entry, tcgen05.mma.kind::i8) instead of the FP64 DMMA kernel -- the path cfg 2 takes by default from n = 4096:
-    phase-I and main phase, LP and QP (accumulation onto t P), ragged sizes, cold and warm starts.  Same bars."""
+    phase-I and main phase, LP and QP (accumulation onto t P), second-order cones (the per-cone rows W), ragged sizes,
+    cold and warm starts.  Same bars."""
     monkeypatch.setenv("IPM_HESSIAN_I8", "1")
     cls = _solver_class(case["solver"])
     prob = build_problem(case)
