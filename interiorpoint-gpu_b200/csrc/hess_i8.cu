@@ -30,6 +30,8 @@
 #include <cuda.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tensormap.cuh"
 
@@ -129,13 +131,39 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
       "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
 }
+// COLLECT: 0 plain, 1 keep the A operand in the collector buffer for the next MMA, 2 reuse it (and release it)
+template <int COLLECT>
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (COLLECT == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8.collector::a::fill [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+  else if constexpr (COLLECT == 2)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8.collector::a::lastuse [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
-      : "memory");
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -160,6 +188,31 @@ struct Args {
   unsigned int* fault;
 };
 
+// all MMAs of one (chunk, slice t): 4 k-steps x the <= 2 pieces of the N = 64 (S - t) wide operand.  Everything but the
+// two operand base addresses is a compile-time constant, so one MMA costs one add per descriptor: the issuing warp runs
+// this with uniform control flow and only the instruction itself sits behind elect.sync (an `if (lane == 0)` around
+// the loop made every operand a per-thread value: ~200 clocks of uniform-datapath conversions per MMA, which starved
+// the tensor pipe -- tools/umma_probe.cu, profiles/umma_probe_r02.jsonl).
+template <int S, int T>
+__device__ __forceinline__ void issue_slice(uint32_t tmem, uint64_t da0, uint64_t db0, bool first_chunk, bool leader) {
+  constexpr int NCOLS = TN * (S - T);
+#pragma unroll
+  for (int j = 0; j < KC / KSTEP; ++j) {
+    const uint64_t da = da0 + (uint64_t)((j * KSTEP) >> 4);
+    const uint32_t acc = (T > 0 || j > 0) ? 1u : (first_chunk ? 0u : 1u);
+    if constexpr (NCOLS > 256) {
+      const uint64_t db = db0 + (uint64_t)((j * KSTEP) >> 4), db2 = db + (uint64_t)((256 * KC) >> 4);
+      if (leader) {
+        umma_i8<1>(tmem + T * TN, da, db, IDESC | ((uint32_t)(256 >> 3) << 17), acc);
+        umma_i8<2>(tmem + T * TN + 256, da, db2, IDESC | ((uint32_t)((NCOLS - 256) >> 3) << 17), acc);
+      }
+    } else {
+      if (leader) umma_i8<0>(tmem + T * TN, da, db0 + (uint64_t)((j * KSTEP) >> 4), IDESC | ((uint32_t)(NCOLS >> 3) << 17), acc);
+    }
+  }
+}
+
+template <int S>
 __global__ void __launch_bounds__(THREADS, 1)
 syrk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
   extern __shared__ uint8_t smem_raw[];
@@ -169,7 +222,7 @@ syrk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t a_full = bars, a_empty = bars + 8 * NA, b_full = bars + 16 * NA, b_empty = b_full + 8 * NB,
                  tfull = b_empty + 8 * NB, tempty = tfull + 8, tptr = tfull + 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int s = a.s;
+  constexpr int s = S;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NA; ++i) {
@@ -222,40 +275,43 @@ syrk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      long long ia = 0, ib = 0;
-      int tcount = 0;
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
-        if (tcount > 0) {  // the epilogue of the previous tile has drained the accumulators
-          mbar_wait(tempty, (uint32_t)(tcount - 1) & 1u, a.fault);
-          tc_fence_after();
-        }
-        for (int kc = 0; kc < a.nkc; ++kc, ++ib) {
-          const int st = (int)(ib % NB);
-          mbar_wait(b_full + 8 * st, (uint32_t)(ib / NB) & 1u, a.fault);
-          const uint32_t sb = smB + st * B_STAGE;
-          for (int t = 0; t < s; ++t, ++ia) {
+  } else if (warp == 1) {  // MMA issue: the whole warp walks the loop (uniform values), one elected lane issues
+    const bool leader = elect_one();
+    long long ia = 0, ib = 0;
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
+      if (tcount > 0) {  // the epilogue of the previous tile has drained the accumulators
+        mbar_wait(tempty, (uint32_t)(tcount - 1) & 1u, a.fault);
+        __syncwarp();
+        tc_fence_after();
+      }
+      for (int kc = 0; kc < a.nkc; ++kc, ++ib) {
+        const int st = (int)(ib % NB);
+        mbar_wait(b_full + 8 * st, (uint32_t)(ib / NB) & 1u, a.fault);
+        const uint64_t db0 = smem_desc(smB + st * B_STAGE);
+        auto slice = [&](auto tc) {
+          constexpr int T = decltype(tc)::value;
+          if constexpr (T < S) {
             const int sl = (int)(ia % NA);
             mbar_wait(a_full + 8 * sl, (uint32_t)(ia / NA) & 1u, a.fault);
+            __syncwarp();
             tc_fence_after();
-            const uint32_t sa = smA + sl * A_SLOT;
-            const int ncols = TN * (s - t);  // B rows = slices 0 .. s-1-t; accumulators of the diagonals t .. s-1
-#pragma unroll
-            for (int j = 0; j < KC / KSTEP; ++j) {
-              const uint64_t da = smem_desc(sa + j * KSTEP);
-              for (int n0 = 0; n0 < ncols; n0 += 256) {
-                const int nn = min(256, ncols - n0);
-                umma_i8(tmem + t * TN + n0, da, smem_desc(sb + n0 * KC + j * KSTEP), IDESC | ((uint32_t)(nn >> 3) << 17),
-                        (kc > 0 || t > 0 || j > 0) ? 1u : 0u);
-              }
-            }
-            umma_commit(a_empty + 8 * sl);  // frees the A slot once these MMAs have read it
+            issue_slice<S, T>(tmem, smem_desc(smA + sl * A_SLOT), db0, kc == 0, leader);
+            if (leader) umma_commit(a_empty + 8 * sl);  // frees the A slot once these MMAs have read it
+            ++ia;
           }
-          umma_commit(b_empty + 8 * st);
-        }
-        umma_commit(tfull);
+        };
+        slice(std::integral_constant<int, 0>{});
+        slice(std::integral_constant<int, 1>{});
+        slice(std::integral_constant<int, 2>{});
+        slice(std::integral_constant<int, 3>{});
+        slice(std::integral_constant<int, 4>{});
+        slice(std::integral_constant<int, 5>{});
+        slice(std::integral_constant<int, 6>{});
+        slice(std::integral_constant<int, 7>{});
+        if (leader) umma_commit(b_empty + 8 * st);
       }
+      if (leader) umma_commit(tfull);
     }
   } else {
     const int q = warp & 3;  // TMEM lane quarter this warp may read
@@ -334,6 +390,27 @@ int slice_map(CUtensorMap* tm, const int8_t* Q, long long n_pad, long long k_pad
   return r == CUDA_SUCCESS ? IPM_OK : IPM_ERR_ARG;
 }
 
+template <int S>
+int launch_syrk_s(int grid, cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& a) {
+  static bool attr_done[kMaxDevices] = {};
+  IPM_CUDA_CHECK(ensure_dynamic_smem(syrk_kernel<S>, SMEM_BYTES, attr_done));
+  syrk_kernel<S><<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmB, a);
+  IPM_LAUNCH_CHECK();
+  return IPM_OK;
+}
+int launch_syrk(int slices, int grid, cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& a) {
+  switch (slices) {
+    case 1: return launch_syrk_s<1>(grid, st, tmA, tmB, a);
+    case 2: return launch_syrk_s<2>(grid, st, tmA, tmB, a);
+    case 3: return launch_syrk_s<3>(grid, st, tmA, tmB, a);
+    case 4: return launch_syrk_s<4>(grid, st, tmA, tmB, a);
+    case 5: return launch_syrk_s<5>(grid, st, tmA, tmB, a);
+    case 6: return launch_syrk_s<6>(grid, st, tmA, tmB, a);
+    case 7: return launch_syrk_s<7>(grid, st, tmA, tmB, a);
+    default: return launch_syrk_s<8>(grid, st, tmA, tmB, a);
+  }
+}
+
 long long round_up_ll(long long a, long long b) { return (a + b - 1) / b * b; }
 
 // workspace: [amax n_pad u64][sigma n_pad f64][tiles ntiles int2][pad to 1024][Q s x n_pad x k_pad int8]
@@ -405,8 +482,7 @@ extern "C" int ipm_hess_i8_f64(const double* C, int ldc, int m, int n, const dou
   if (rc) return rc;
   rc = slice_map(&tmB, Q, L.n_pad, L.k_pad, slices, TN, slices);
   if (rc) return rc;
-  static bool attr_done[kMaxDevices] = {};
-  IPM_CUDA_CHECK(ensure_dynamic_smem(syrk_kernel, SMEM_BYTES, attr_done));
+
   int dev = 0, sms = 0;
   IPM_CUDA_CHECK(cudaGetDevice(&dev));
   IPM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -428,7 +504,5 @@ extern "C" int ipm_hess_i8_f64(const double* C, int ldc, int m, int n, const dou
   a.ldh = ldh;
   a.beta = beta;
   a.fault = ipm_internal_fault_word();
-  syrk_kernel<<<L.ntiles < sms ? L.ntiles : sms, THREADS, SMEM_BYTES, st>>>(tmA, tmB, a);
-  IPM_LAUNCH_CHECK();
-  return IPM_OK;
+  return launch_syrk(slices, L.ntiles < sms ? L.ntiles : sms, st, tmA, tmB, a);
 }

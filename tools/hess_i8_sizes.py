@@ -26,7 +26,11 @@ def timed(fn, reps=5):
 
 def main():
     _abi.require_device()
-    sizes = [(1024, 2048), (2048, 4096), (3072, 6144), (4096, 8192), (4096, 16384), (6144, 12288), (8192, 16384),
+    if len(sys.argv) > 2:
+        sizes_arg = [(int(sys.argv[1]), int(sys.argv[2]))]
+    else:
+        sizes_arg = None
+    sizes = sizes_arg or [(1024, 2048), (2048, 4096), (3072, 6144), (4096, 8192), (4096, 16384), (6144, 12288), (8192, 16384),
              (8192, 32768), (12288, 24576)]
     for n, m in sizes:
         g = torch.Generator(device="cuda").manual_seed(n)
