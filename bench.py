@@ -275,9 +275,11 @@ def int8_hessian_roofline(n, m, hess_ms, launches, slices=8):
     fp64_equiv = float(m) * n * (n + 1) / (hess_ms * 1e-3) / 1e12 if hess_ms else None
     return {"bound": "tensor", "achieved": achieved, "peak": INT8_TENSOR_PEAK_TOPS, "unit": "TOP/s (INT8)",
             "frac": achieved / INT8_TENSOR_PEAK_TOPS if achieved else None,
-            "traffic": 8.77e9 * (n_pad * n_pad * k_pad) / (8192.0 * 8192 * 16384) if (n, m) == (8192, 16384) else None,
-            "traffic_source": "profiles/ozaki_syrk_v2_ncu_r02.csv: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu "
-                              "--set full` capture of the SYRK kernel at this shape (not re-measured in this run)",
+            "traffic": 22.11e9 + 2.10e9 if (n, m) == (8192, 16384) else None,
+            "traffic_source": "profiles/hess_i8_syrk_ncu_r02.csv + hess_i8_slice_ncu_r02.csv: dram__bytes_read.sum + "
+                              "dram__bytes_write.sum of `ncu --set full` captures of the SYRK and the slicing kernel at this "
+                              "shape (not re-measured in this run; the SYRK re-reads the 1.07 GB of digits from L2, hit rate "
+                              "71 %, the rest spills to HBM at 1.9 TB/s)",
             "algorithmic_bytes": float(slices) * n_pad * k_pad + 8.0 * n * (n + 1) / 2,
             "kernel": "ipm_hess_i8_f64 = colmax_kernel + slice_kernel + syrk_kernel (tcgen05.mma.kind::i8, 8 x 7-bit digits "
                       "per entry, FP64-accurate)",
@@ -384,7 +386,7 @@ def lp_section(D, args, prob, m, rows_mode, steps, warmup, e2e=True, profile=Tru
         one_solve()
     L = solver.launcher
     if profile:
-        L.timed_ops = {"ipm_gemm_tn_f64": [], "ipm_syrk_scatter_f64": [], "ipm_hess_i8_f64": [],
+        L.timed_ops = {"ipm_gemm_tn_f64": [], "ipm_syrk_scatter_f64": [], "ipm_hess_i8_f64": [], "ipm_hess_i8_scatter_f64": [],
                        "range:hessian_formation": [], "ipm_potrf_upper_f64": [], "ipm_potrf_upper_peer_f64": []}
     launches0 = L.kernel_launches()
     with ClockSampler(D.local_rank) as clk:
@@ -393,9 +395,10 @@ def lp_section(D, args, prob, m, rows_mode, steps, warmup, e2e=True, profile=Tru
                value_obj=solver.value, m_local=solver.data.m, comm_bytes=getattr(solver.ns, "comm_bytes", 0),
                peer=getattr(solver.ns, "peer", None) is not None, inner_iters=list(solver.inner_iters))
     if profile:
-        out["hess"] = [a.elapsed_time(b) for key in ("ipm_gemm_tn_f64", "ipm_syrk_scatter_f64", "ipm_hess_i8_f64")
+        out["hess"] = [a.elapsed_time(b) for key in ("ipm_gemm_tn_f64", "ipm_syrk_scatter_f64", "ipm_hess_i8_f64",
+                                                      "ipm_hess_i8_scatter_f64")
                        for a, b, tag in L.timed_ops[key] if tag == "hessian"]
-        out["hess_i8"] = len(L.timed_ops["ipm_hess_i8_f64"]) > 0
+        out["hess_i8"] = len(L.timed_ops["ipm_hess_i8_f64"]) + len(L.timed_ops["ipm_hess_i8_scatter_f64"]) > 0
         out["hform"] = [a.elapsed_time(b) for a, b, _ in L.timed_ops["range:hessian_formation"]]
         out["potrf"] = [a.elapsed_time(b) for key in ("ipm_potrf_upper_f64", "ipm_potrf_upper_peer_f64")
                         for a, b, _ in L.timed_ops[key]]
@@ -451,7 +454,8 @@ def qp_section(D, args):
     s = QPSolver(**prob, check_cvxpy=False, suppress_print=True, **problems.QP_TEST_SETTINGS)
     del prob
     L = s.launcher
-    L.timed_ops = {"ipm_gemm_tn_f64": [], "ipm_potrf_upper_f64": [], "ipm_potrf_trsm_upper_f64": [], "ipm_trsv_upper_f64": [],
+    L.timed_ops = {"ipm_gemm_tn_f64": [], "ipm_hess_i8_f64": [], "ipm_potrf_upper_f64": [], "ipm_potrf_trsm_upper_f64": [],
+                   "ipm_trsv_upper_f64": [],
                    "ipm_gemv_n_f64": [], "ipm_gemv_t_f64": []}
     marks = {}
 
@@ -509,12 +513,13 @@ def socp_section(D, args, rows_mode):
                    shard_rows=rows_mode, **problems.SOCP_TEST_SETTINGS)
     del prob
     L = s.launcher
-    L.timed_ops = {"ipm_gemm_tn_f64": [], "ipm_syrk_scatter_f64": [], "ipm_hess_i8_f64": [], "range:hessian_formation": [],
-                   "ipm_potrf_upper_f64": [], "ipm_potrf_upper_peer_f64": []}
+    L.timed_ops = {"ipm_gemm_tn_f64": [], "ipm_syrk_scatter_f64": [], "ipm_hess_i8_f64": [], "ipm_hess_i8_scatter_f64": [],
+                   "range:hessian_formation": [], "ipm_potrf_upper_f64": [], "ipm_potrf_upper_peer_f64": []}
     ms, counts = D.timed(lambda: (s.solve(), sum(s.inner_iters))[1], 1)
-    hess = [a.elapsed_time(b) for key in ("ipm_gemm_tn_f64", "ipm_syrk_scatter_f64", "ipm_hess_i8_f64")
+    hess = [a.elapsed_time(b) for key in ("ipm_gemm_tn_f64", "ipm_syrk_scatter_f64", "ipm_hess_i8_f64",
+                                          "ipm_hess_i8_scatter_f64")
             for a, b, tag in L.timed_ops[key] if tag == "hessian"]
-    hess_i8 = len(L.timed_ops["ipm_hess_i8_f64"]) > 0
+    hess_i8 = len(L.timed_ops["ipm_hess_i8_f64"]) + len(L.timed_ops["ipm_hess_i8_scatter_f64"]) > 0
     hform = [a.elapsed_time(b) for a, b, _ in L.timed_ops["range:hessian_formation"]]
     potrf = [a.elapsed_time(b) for key in ("ipm_potrf_upper_f64", "ipm_potrf_upper_peer_f64")
              for a, b, _ in L.timed_ops[key]]
@@ -678,7 +683,7 @@ def main():
         "time_to_solve_s": ms * 1e-3 / args.steps,
         "newton_steps_per_solve": newton / args.steps / (1 if (rows_mode or D.world == 1) else D.world),
         "objective": r["value_obj"], "gpu_launches": int(r["launches"]), "clocks": r["clocks"],
-        "roofline": int8_hessian_roofline(n, m, hess_ms, len(r["hess"])) if r.get("hess_i8") else
+        "roofline": int8_hessian_roofline(n, int(r["m_local"]), hess_ms, len(r["hess"])) if r.get("hess_i8") else
                     {"bound": "tensor", "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
                      "frac": achieved / FP64_TENSOR_PEAK_TFLOPS if achieved else None,
                      "traffic": hessian_dram_traffic(n, m),

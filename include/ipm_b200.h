@@ -67,6 +67,12 @@ long long ipm_hess_i8_ws_bytes(int m, int n, int slices);
 int ipm_hess_i8_prepare(void* ws, int m, int n, int slices, void* stream);
 int ipm_hess_i8_f64(const double* C, int ldc, int m, int n, const double* w, double beta, double* H, int ldh, int slices,
                     void* ws, void* stream);
+/* Row-sharded variant: the partial C_r^T diag(w) C_r of this rank's m local rows, scattered tile by tile into the owners'
+ * inboxes; drop-in for ipm_syrk_scatter_f64 below (same peer arrays, slots and epoch; no local addend), to be followed
+ * by ipm_hess_reduce_bcast_f64. */
+int ipm_hess_i8_scatter_f64(const double* C, int ldc, int m, int n, const double* w, int slices, void* ws,
+                            void* const* peer_inbox, void* const* peer_flags, int me, int R, int slots,
+                            unsigned int epoch, void* stream);
 
 /* ---- HBM-streaming level-1/2 ---------------------------------------------------------------------------- */
 /* y = alpha * M x + beta * y   (M: rows x cols).  np.matmul(C, x) FunctionManager.py:123-125, 432-434, 939-941;

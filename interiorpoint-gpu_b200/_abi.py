@@ -30,6 +30,8 @@ SIGNATURES = {
     "ipm_hess_i8_ws_bytes": (_ll, [_i, _i, _i]),
     "ipm_hess_i8_prepare": (_i, [_dp, _i, _i, _i, _dp]),
     "ipm_hess_i8_f64": (_i, [_dp, _i, _i, _i, _dp, _d, _dp, _i, _i, _dp, _dp]),
+    "ipm_hess_i8_scatter_f64": (_i, [_dp, _i, _i, _i, _dp, _i, _dp, C.POINTER(_dp), C.POINTER(_dp), _i, _i, _i, C.c_uint,
+                                     _dp]),
     "ipm_gemv_n_f64": (_i, [_dp, _i, _i, _i, _dp, _dp, _d, _d, _dp]),
     "ipm_gemv_t_ws_doubles": (_ll, [_i, _i, _i]),
     "ipm_gemv_t_f64": (_i, [_dp, _i, _i, _i, _dp, _i, _i, _dp, _i, _d, _d, _dp, _ll, _dp]),

@@ -1,6 +1,6 @@
 // Barrier Hessian H = beta H + C' diag(w) C (w >= 0) in FP64 accuracy on the INT8 tensor pipe of sm_100a
 // (tcgen05.mma.kind::i8, accumulators in TMEM) -- the same contraction as ipm_gemm_tn_f64(upper = 1)
-// (FunctionManager.py:301-312, 564-576, 801-813), 1.7x faster at the cfg-2 shape (profiles/ozaki_syrk_v3_r02.jsonl).
+// (FunctionManager.py:301-312, 564-576, 801-813), 2.5x faster at the cfg-2 shape (profiles/hess_i8_sizes_r02.jsonl).
 //
 // Error-free slicing along the contraction index (Ozaki scheme).  X = diag(sqrt w) C (K x n, K = m rows).  Column i is
 // scaled by the power of two sigma_i = 2^(E_i + 2), 2^E_i <= max_k |X_ki| < 2^(E_i + 1), and cut into s signed digits
@@ -8,8 +8,9 @@
 //     X_ki = sigma_i sum_{t < s} q_t[k, i] 128^-(t+1)  +  O(sigma_i 128^-s)
 //     H_ij = sigma_i sigma_j sum_{d < s} 128^-(d+2) sum_{t + u = d} (Q_t' Q_u)_ij
 // Every Q_t' Q_u is an EXACT INT8 x INT8 -> INT32 product (|q q'| <= 2^12, K < 2^16 terms, <= 8 pairs per diagonal
-// d = t + u: below 2^31 in the worst case), so the only roundings are the slicing itself and the FP64 recombination of s integers per
-// entry.  s = 8 (56 bits) reproduces the DMMA kernel to 2e-15 of sum_k |x_ki x_kj| on weights spanning 20 decades.
+// d = t + u: below 2^31 in the worst case), so the only roundings are the slicing itself and the FP64 recombination of
+// s integers per entry.  s = 8 (56 bits) reproduces the DMMA kernel to 2e-15 of sum_k |x_ki x_kj| on weights spanning 20
+// decades.
 //
 // Kernels
 //   colmax_kernel   amax_i = max_k sqrt(w_k) |C_ki|                        HBM: reads C once
@@ -21,11 +22,15 @@
 //     * the B side of a chunk -- all s slices of the 64 rows, [s][64][128 B] = ONE contiguous K-major operand of 64 s
 //       rows -- sits in one of 2 stages; the A slices stream through a ring of 6 slots of 16 KB;
 //     * slice t of A meets slices 0..s-1-t of B, whose accumulators (diagonals t..s-1) are adjacent TMEM columns: one
-//       wide MMA (N = 64 (s - t), split at 256) instead of s - t narrow ones -- 12 instead of 36 A-operand reads per
-//       k-step at s = 8.  Measured limit (ncu, profiles/ozaki_syrk_v2_ncu_r02.csv): the tensor pipe is 49 % active, the
-//       rest of the time it waits for its shared-memory operand fetch (SS-mode UMMA of one CTA reads ~64 B/clk);
-//       A-from-TMEM or CTA pairs are the next step.
-//     * epilogue: tcgen05.ld of the s accumulators, Horner in FP64, scale by sigma_i sigma_j, [+ beta H], store.
+//       wide MMA (N = 64 (s - t), split at 256, the second piece reusing the A operand from the collector buffer)
+//       instead of s - t narrow ones -- 12 MMAs and 8 A-operand reads per k-step at s = 8 instead of 36;
+//     * the MMA warp runs its loop with warp-uniform control flow and compile-time descriptor offsets (issue_slice):
+//       one MMA costs a couple of uniform adds.  The first version issued from `if (lane == 0)`, where every operand
+//       is a per-thread value that has to be moved to the uniform datapath: ~200 clocks per MMA whatever its shape
+//       (tools/umma_probe.cu), tensor pipe 49 % active, 17.9 ms.  Now: pipe 86 % active, 11.6 ms at the cfg-2 shape
+//       (profiles/hess_i8_syrk_ncu_r02.csv) = 3.4 POP/s, 0.92 of the library INT8 GEMM rate on the same box;
+//     * epilogue: tcgen05.ld of the s accumulators, Horner in FP64, scale by sigma_i sigma_j, [+ beta H], store -- or,
+//       row-sharded (SCATTER), the half tile goes into the inbox of the rank that owns its 128 x 128 tile.
 // Every wait is bounded by the library's watchdog word (common.cuh).
 #include <cuda.h>
 #include <stdint.h>
@@ -186,6 +191,13 @@ struct Args {
   long long ldh;
   double beta;
   unsigned int* fault;
+  // row-sharded mode (SCATTER): the 128 x 64 partial tile goes into the inbox of the rank that owns the 128 x 128 tile
+  // it is one half of (same inbox / flag protocol as PeerScatterEpilogue in gemm_tn.cu)
+  double* inbox[8];
+  unsigned int* flags[8];
+  unsigned int* halves;  // per 128 x 128 tile: half tiles stored so far (the second one raises the owner's flag)
+  int me, R, slots;
+  unsigned int epoch;
 };
 
 // all MMAs of one (chunk, slice t): 4 k-steps x the <= 2 pieces of the N = 64 (S - t) wide operand.  Everything but the
@@ -212,7 +224,7 @@ __device__ __forceinline__ void issue_slice(uint32_t tmem, uint64_t da0, uint64_
   }
 }
 
-template <int S>
+template <int S, bool SCATTER>
 __global__ void __launch_bounds__(THREADS, 1)
 syrk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
   extern __shared__ uint8_t smem_raw[];
@@ -324,6 +336,13 @@ syrk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_after();
       const long long i = (long long)tl.x * TM + row;
       const double si = i < a.n ? a.sigma[i] * 0x1p-14 : 0.0;
+      int scatter_t = 0;
+      double* scatter_dst = nullptr;
+      if constexpr (SCATTER) {
+        const int T = (a.n + 127) / 128, ti = tl.x, tj = tl.y >> 1;
+        scatter_t = ti * T - ti * (ti - 1) / 2 + (tj - ti);  // upper_tile_index of gemm_tn.cu
+        scatter_dst = a.inbox[scatter_t % a.R] + ((size_t)a.me * a.slots + scatter_t / a.R) * (128 * 128) + 64 * (tl.y & 1);
+      }
       for (int c0 = 0; c0 < TN; c0 += 8) {
         int v[SMAX][8];
 #pragma unroll
@@ -335,7 +354,7 @@ syrk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           asm volatile("" : "+r"(v[d][0]), "+r"(v[d][1]), "+r"(v[d][2]), "+r"(v[d][3]), "+r"(v[d][4]), "+r"(v[d][5]),
                             "+r"(v[d][6]), "+r"(v[d][7]));
         const long long j0 = (long long)tl.y * TN + c0;
-        if (i < a.n && j0 < a.n) {
+        if (SCATTER || (i < a.n && j0 < a.n)) {
           double out[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -345,25 +364,45 @@ syrk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (d < s) r = fma(r, 0x1p-7, (double)v[d][c]);
             out[c] = r * si;
           }
-          double* dst = a.H + i * a.ldh + j0;
-          if (j0 + 8 <= a.n) {
+          if constexpr (SCATTER) {  // sigma is zero beyond n: the padding of the tile is stored as zeros
+            double* dst = scatter_dst + row * 128 + c0;
 #pragma unroll
             for (int c = 0; c < 8; c += 2) {
               const double2 sj = *reinterpret_cast<const double2*>(a.sigma + j0 + c);
-              double2 h = make_double2(out[c] * sj.x, out[c + 1] * sj.y);
-              if (a.beta != 0.0) {
-                const double2 old = *reinterpret_cast<const double2*>(dst + c);
-                h.x = fma(a.beta, old.x, h.x);
-                h.y = fma(a.beta, old.y, h.y);
-              }
-              *reinterpret_cast<double2*>(dst + c) = h;
+              *reinterpret_cast<double2*>(dst + c) = make_double2(out[c] * sj.x, out[c + 1] * sj.y);
             }
           } else {
-            for (int c = 0; c < 8; ++c)
-              if (j0 + c < a.n) {
-                const double h = out[c] * a.sigma[j0 + c];
-                dst[c] = a.beta != 0.0 ? fma(a.beta, dst[c], h) : h;
+            double* dst = a.H + i * a.ldh + j0;
+            if (j0 + 8 <= a.n) {
+#pragma unroll
+              for (int c = 0; c < 8; c += 2) {
+                const double2 sj = *reinterpret_cast<const double2*>(a.sigma + j0 + c);
+                double2 h = make_double2(out[c] * sj.x, out[c + 1] * sj.y);
+                if (a.beta != 0.0) {
+                  const double2 old = *reinterpret_cast<const double2*>(dst + c);
+                  h.x = fma(a.beta, old.x, h.x);
+                  h.y = fma(a.beta, old.y, h.y);
+                }
+                *reinterpret_cast<double2*>(dst + c) = h;
               }
+            } else {
+              for (int c = 0; c < 8; ++c)
+                if (j0 + c < a.n) {
+                  const double h = out[c] * a.sigma[j0 + c];
+                  dst[c] = a.beta != 0.0 ? fma(a.beta, dst[c], h) : h;
+                }
+            }
+          }
+        }
+      }
+      if constexpr (SCATTER) {  // publish: all 128 rows stored and visible system-wide, then count the half tile
+        __threadfence_system();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (row == 0) {
+          if (atomicAdd(a.halves + scatter_t, 1u) & 1u) {
+            __threadfence_system();
+            unsigned int* f = a.flags[scatter_t % a.R] + (size_t)(scatter_t / a.R) * a.R + a.me;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(a.epoch) : "memory");
           }
         }
       }
@@ -390,32 +429,33 @@ int slice_map(CUtensorMap* tm, const int8_t* Q, long long n_pad, long long k_pad
   return r == CUDA_SUCCESS ? IPM_OK : IPM_ERR_ARG;
 }
 
-template <int S>
+template <int S, bool SCATTER>
 int launch_syrk_s(int grid, cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& a) {
   static bool attr_done[kMaxDevices] = {};
-  IPM_CUDA_CHECK(ensure_dynamic_smem(syrk_kernel<S>, SMEM_BYTES, attr_done));
-  syrk_kernel<S><<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmB, a);
+  IPM_CUDA_CHECK(ensure_dynamic_smem(syrk_kernel<S, SCATTER>, SMEM_BYTES, attr_done));
+  syrk_kernel<S, SCATTER><<<grid, THREADS, SMEM_BYTES, st>>>(tmA, tmB, a);
   IPM_LAUNCH_CHECK();
   return IPM_OK;
 }
+template <bool SCATTER>
 int launch_syrk(int slices, int grid, cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB, const Args& a) {
   switch (slices) {
-    case 1: return launch_syrk_s<1>(grid, st, tmA, tmB, a);
-    case 2: return launch_syrk_s<2>(grid, st, tmA, tmB, a);
-    case 3: return launch_syrk_s<3>(grid, st, tmA, tmB, a);
-    case 4: return launch_syrk_s<4>(grid, st, tmA, tmB, a);
-    case 5: return launch_syrk_s<5>(grid, st, tmA, tmB, a);
-    case 6: return launch_syrk_s<6>(grid, st, tmA, tmB, a);
-    case 7: return launch_syrk_s<7>(grid, st, tmA, tmB, a);
-    default: return launch_syrk_s<8>(grid, st, tmA, tmB, a);
+    case 1: return launch_syrk_s<1, SCATTER>(grid, st, tmA, tmB, a);
+    case 2: return launch_syrk_s<2, SCATTER>(grid, st, tmA, tmB, a);
+    case 3: return launch_syrk_s<3, SCATTER>(grid, st, tmA, tmB, a);
+    case 4: return launch_syrk_s<4, SCATTER>(grid, st, tmA, tmB, a);
+    case 5: return launch_syrk_s<5, SCATTER>(grid, st, tmA, tmB, a);
+    case 6: return launch_syrk_s<6, SCATTER>(grid, st, tmA, tmB, a);
+    case 7: return launch_syrk_s<7, SCATTER>(grid, st, tmA, tmB, a);
+    default: return launch_syrk_s<8, SCATTER>(grid, st, tmA, tmB, a);
   }
 }
 
 long long round_up_ll(long long a, long long b) { return (a + b - 1) / b * b; }
 
-// workspace: [amax n_pad u64][sigma n_pad f64][tiles ntiles int2][pad to 1024][Q s x n_pad x k_pad int8]
+// workspace: [amax n_pad u64][sigma n_pad f64][tiles ntiles int2][half-tile counters][pad to 1024][Q s x n_pad x k_pad int8]
 struct Layout {
-  long long n_pad, k_pad, off_sigma, off_tiles, off_q, bytes;
+  long long n_pad, k_pad, off_sigma, off_tiles, off_halves, off_q, bytes;
   int ntiles;
 };
 Layout layout_for(int m, int n, int s) {
@@ -426,7 +466,8 @@ Layout layout_for(int m, int n, int s) {
   L.ntiles = rb * (rb + 1);  // sum over row blocks bi of the 2 rb - 2 bi column blocks of 64 with bj >= 2 bi
   L.off_sigma = L.n_pad * 8;
   L.off_tiles = 2 * L.n_pad * 8;
-  L.off_q = round_up_ll(L.off_tiles + (long long)L.ntiles * 8, 1024);
+  L.off_halves = L.off_tiles + (long long)L.ntiles * 8;
+  L.off_q = round_up_ll(L.off_halves + (long long)rb * (rb + 1) / 2 * 4, 1024);
   L.bytes = L.off_q + (long long)s * L.n_pad * L.k_pad;
   return L;
 }
@@ -462,15 +503,11 @@ extern "C" int ipm_hess_i8_prepare(void* ws, int m, int n, int slices, void* str
   return cnt == L.ntiles ? IPM_OK : IPM_ERR_ARG;
 }
 
-// H (upper tiles; n x n, ldh) = beta * H + C' diag(w) C  for C: m x n (ldc), w: m weights >= 0, through `slices` INT8
-// digits per entry (8: FP64-level accuracy; fewer digits are faster and less accurate, 7 bits each).  ws: prepared by
-// ipm_hess_i8_prepare for the same (m, n, slices).  Elements below the diagonal inside diagonal tiles are written too
-// (as by ipm_gemm_tn_f64 with upper = 1).  FunctionManager.py:301-312, 564-576, 801-813.
-extern "C" int ipm_hess_i8_f64(const double* C, int ldc, int m, int n, const double* w, double beta, double* H, int ldh,
-                               int slices, void* ws, void* stream) {
-  if (!C || !w || !H || !ws || ((uintptr_t)ws & 255) || ldc < n || ldh < n || (ldh & 1) || ((uintptr_t)H & 15) ||
-      ipm_hess_i8_ws_bytes(m, n, slices) == 0)
-    return IPM_ERR_ARG;
+namespace {
+// slicing + SYRK shared by the two entry points; H == nullptr: scatter mode
+int run_hess_i8(const double* C, int ldc, int m, int n, const double* w, double beta, double* H, int ldh, int slices,
+                void* ws, void* const* peer_inbox, void* const* peer_flags, int me, int R, int slots, unsigned int epoch,
+                void* stream) {
   const Layout L = layout_for(m, n, slices);
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* amax = (unsigned long long*)ws;
@@ -482,7 +519,6 @@ extern "C" int ipm_hess_i8_f64(const double* C, int ldc, int m, int n, const dou
   if (rc) return rc;
   rc = slice_map(&tmB, Q, L.n_pad, L.k_pad, slices, TN, slices);
   if (rc) return rc;
-
   int dev = 0, sms = 0;
   IPM_CUDA_CHECK(cudaGetDevice(&dev));
   IPM_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -493,7 +529,7 @@ extern "C" int ipm_hess_i8_f64(const double* C, int ldc, int m, int n, const dou
   slice_kernel<<<dim3((unsigned)(L.n_pad / SL_COLS), (unsigned)(L.k_pad / SL_K)), 256, 0, st>>>(C, ldc, m, n, w, amax, slices,
                                                                                               Q, L.n_pad, L.k_pad, sigma);
   IPM_LAUNCH_CHECK();
-  Args a;
+  Args a = {};
   a.tiles = tiles;
   a.ntiles = L.ntiles;
   a.nkc = (int)(L.k_pad / KC);
@@ -504,5 +540,39 @@ extern "C" int ipm_hess_i8_f64(const double* C, int ldc, int m, int n, const dou
   a.ldh = ldh;
   a.beta = beta;
   a.fault = ipm_internal_fault_word();
-  return launch_syrk(slices, L.ntiles < sms ? L.ntiles : sms, st, tmA, tmB, a);
+  const int grid = L.ntiles < sms ? L.ntiles : sms;
+  if (H) return launch_syrk<false>(slices, grid, st, tmA, tmB, a);
+  for (int r = 0; r < R; ++r) {
+    a.inbox[r] = (double*)peer_inbox[r];
+    a.flags[r] = (unsigned int*)peer_flags[r];
+  }
+  a.halves = (unsigned int*)((char*)ws + L.off_halves);
+  a.me = me, a.R = R, a.slots = slots, a.epoch = epoch;
+  return launch_syrk<true>(slices, grid, st, tmA, tmB, a);
+}
+}  // namespace
+
+// H (upper tiles; n x n, ldh) = beta * H + C' diag(w) C  for C: m x n (ldc), w: m weights >= 0, through `slices` INT8
+// digits per entry (8: FP64-level accuracy; fewer digits are faster and less accurate, 7 bits each).  ws: prepared by
+// ipm_hess_i8_prepare for the same (m, n, slices).  Elements below the diagonal inside diagonal tiles are written too
+// (as by ipm_gemm_tn_f64 with upper = 1).  FunctionManager.py:301-312, 564-576, 801-813.
+extern "C" int ipm_hess_i8_f64(const double* C, int ldc, int m, int n, const double* w, double beta, double* H, int ldh,
+                               int slices, void* ws, void* stream) {
+  if (!C || !w || !H || !ws || ((uintptr_t)ws & 255) || ldc < n || ldh < n || (ldh & 1) || ((uintptr_t)H & 15) ||
+      ipm_hess_i8_ws_bytes(m, n, slices) == 0)
+    return IPM_ERR_ARG;
+  return run_hess_i8(C, ldc, m, n, w, beta, H, ldh, slices, ws, nullptr, nullptr, 0, 1, 0, 0, stream);
+}
+
+// Row-sharded variant: the partial Hessian of this rank's m local rows, scattered tile by tile into the owners' inboxes
+// -- the drop-in for ipm_syrk_scatter_f64 (same inbox layout, flags, slots and epoch; no local addend), to be followed
+// by ipm_hess_reduce_bcast_f64.  A 128 x 128 tile arrives as two 128 x 64 halves from two CTAs; the one that stores
+// second raises the owner's flag.
+extern "C" int ipm_hess_i8_scatter_f64(const double* C, int ldc, int m, int n, const double* w, int slices, void* ws,
+                                       void* const* peer_inbox, void* const* peer_flags, int me, int R, int slots,
+                                       unsigned int epoch, void* stream) {
+  if (!C || !w || !ws || ((uintptr_t)ws & 255) || ldc < n || !peer_inbox || !peer_flags || R < 1 || R > 8 || me < 0 ||
+      me >= R || slots < 1 || epoch == 0 || ipm_hess_i8_ws_bytes(m, n, slices) == 0)
+    return IPM_ERR_ARG;
+  return run_hess_i8(C, ldc, m, n, w, 0.0, nullptr, 0, slices, ws, peer_inbox, peer_flags, me, R, slots, epoch, stream);
 }

@@ -46,11 +46,11 @@ def step_table(beta):
 
 
 # Hessian on the INT8 tensor pipe (csrc/hess_i8.cu) instead of the FP64 DMMA contraction.  Measured on a B200
-# (profiles/ozaki_syrk_v3_r02.jsonl, profiles/hess_i8_sizes_r02.jsonl): 19.2 ms against 32.4 ms at n = 8192, m = 16384
-# with 8 digits per entry, identical accuracy class (2e-15 of sum |x||x|); 1.17x at n = 2048, m = 4096; 0.66x at n = 1024
-# (three kernels and a 148-CTA persistent grid only pay off on large operands), so the default is size-gated.  IPM_HESSIAN_I8 = 0: never; 1: whenever the shape
+# (profiles/hess_i8_sizes_r02.jsonl): 12.8 ms against 32.5 ms at n = 8192, m = 16384 with 8 digits per entry, identical
+# accuracy class (2e-15 of sum |x||x|); 1.59x at n = 2048, m = 4096; 0.84x at n = 1024 (three kernels and a 148-CTA
+# persistent grid only pay off on large operands), so the default is size-gated.  IPM_HESSIAN_I8 = 0: never; 1: whenever the shape
 # is supported; 5..8: that many 7-bit digits, whenever supported.
-HESS_I8_MIN_N, HESS_I8_MIN_M, HESS_I8_SLICES = 2048, 4096, 8
+HESS_I8_MIN_N, HESS_I8_MIN_M, HESS_I8_SLICES = 2048, 1024, 8
 
 
 def hess_i8_slices(m, n):
@@ -448,6 +448,16 @@ class LinearNewton:
             d.hess_i8_ws = cached = ((slices, rows), buf)
         return cached[1]
 
+    def _schur_i8(self, slices):
+        """(unit weights, slice buffer) of the INT8 kernel for the Schur complement Y'Y (Y: n x p)."""
+        d = self.d
+        cached = getattr(d, "schur_i8_ws", None)
+        if cached is None or cached[0] != slices:
+            buf = torch.empty(_abi.lib().ipm_hess_i8_ws_bytes(d.n, d.p, slices), dtype=torch.uint8, device=d.device)
+            self.L("ipm_hess_i8_prepare", buf.data_ptr(), d.n, d.p, slices)
+            d.schur_i8_ws = cached = (slices, (torch.ones(d.n, dtype=F64, device=d.device), buf))
+        return cached[1]
+
     def _p2_ptr(self):
         """Quadratic line-search coefficients (second-order cones only)."""
         return None
@@ -681,8 +691,13 @@ class LinearNewton:
             ws.Y[:, p].copy_(ws.g)
             L("ipm_potrf_trsm_upper_f64", ws.H.data_ptr(), ws.ldh, n, ws.Y.data_ptr(), ws.ldy, p + 1, ws.info.data_ptr())
             ws.yv.copy_(ws.Y[:, p])  # f = U^{-T} g
-            L("ipm_gemm_tn_f64", ws.Y.data_ptr(), ws.ldy, ws.Y.data_ptr(), ws.ldy, None, 1.0, 0.0, ws.S.data_ptr(),
-              ws.lds, p, p, n, 1)
+            slices = hess_i8_slices(n, p)  # S = Y'Y is the same contraction as the Hessian (unit weights)
+            if slices:
+                L("ipm_hess_i8_f64", ws.Y.data_ptr(), ws.ldy, n, p, self._schur_i8(slices)[0].data_ptr(), 0.0,
+                  ws.S.data_ptr(), ws.lds, slices, self._schur_i8(slices)[1].data_ptr())
+            else:
+                L("ipm_gemm_tn_f64", ws.Y.data_ptr(), ws.ldy, ws.Y.data_ptr(), ws.ldy, None, 1.0, 0.0, ws.S.data_ptr(),
+                  ws.lds, p, p, n, 1)
         if self.shift:
             L("ipm_hess_finish_f64", ws.S.data_ptr(), ws.lds, p, None, None, None, self.shift)
         L("ipm_potrf_upper_f64", ws.S.data_ptr(), ws.lds, p, ws.info.data_ptr() + 4)

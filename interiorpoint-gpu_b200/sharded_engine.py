@@ -23,11 +23,11 @@ import torch.distributed as dist
 try:
     from . import _abi
     from .cone_engine import ConeNewton
-    from .engine import F64, LinearNewton
+    from .engine import F64, LinearNewton, hess_i8_slices
 except ImportError:  # flat-module use
     import _abi
     from cone_engine import ConeNewton
-    from engine import F64, LinearNewton
+    from engine import F64, LinearNewton, hess_i8_slices
 
 
 _PEER_CACHE = {}  # (H shape, world, group, device) -> peer-mapped buffers and their bookkeeping
@@ -131,8 +131,13 @@ class _RowSharded:
         pr["epoch"] += 1
         pr["target"] = (pr["target"] + pr["tiles"]) & 0xFFFFFFFF
         L.tag = "hessian"
-        L("ipm_syrk_scatter_f64", rows_ptr, ld, w_ptr, d.n, K, 1.0, None, 0, pr["p_inbox"], pr["p_flags"], self.rank,
-          self.world, pr["slots"], pr["epoch"])
+        slices = hess_i8_slices(K, d.n)  # this rank's rows on the INT8 tensor pipe (csrc/hess_i8.cu), same exchange
+        if slices:
+            L("ipm_hess_i8_scatter_f64", rows_ptr, ld, K, d.n, w_ptr, slices, self._hess_i8_ws(slices, K).data_ptr(),
+              pr["p_inbox"], pr["p_flags"], self.rank, self.world, pr["slots"], pr["epoch"])
+        else:
+            L("ipm_syrk_scatter_f64", rows_ptr, ld, w_ptr, d.n, K, 1.0, None, 0, pr["p_inbox"], pr["p_flags"], self.rank,
+              self.world, pr["slots"], pr["epoch"])
         L.tag = None
         L("ipm_hess_reduce_bcast_f64", pr["inbox"].data_ptr(), pr["sig"].data_ptr(), pr["p_H"], pr["p_done"], ws.ldh,
           d.n, self.rank, self.world, pr["slots"], pr["epoch"], pr["target"], _abi.ptr(P), ldp, tP)

@@ -198,6 +198,7 @@ def test_int8_hessian_policy(monkeypatch):
     monkeypatch.delenv("IPM_HESSIAN_I8", raising=False)
     assert engine.hess_i8_slices(16384, 8192) == 8 and engine.hess_i8_slices(4096, 2048) == 8
     assert engine.hess_i8_slices(16384, 1024) == 0 and engine.hess_i8_slices(512, 8192) == 0
+    assert engine.hess_i8_slices(2048, 8192) == 8      # an eighth of cfg 2's rows: the per-rank shard on 8 GPUs
     assert engine.hess_i8_slices(0, 8192) == 0
     monkeypatch.setenv("IPM_HESSIAN_I8", "0")
     assert engine.hess_i8_slices(16384, 8192) == 0

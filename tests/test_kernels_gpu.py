@@ -340,9 +340,11 @@ def test_sparse_rows_kernels():
     np.testing.assert_array_equal(got[:, n:], H0[:, n:])
 
 
+@pytest.mark.parametrize("int8", [False, True], ids=["dmma", "int8"])
 @pytest.mark.parametrize("n,m,R", [(300, 500, 2), (1100, 900, 3), (257, 64, 1)])
-def test_peer_hessian_kernels_emulated_ranks(n, m, R):
-    """ipm_syrk_scatter_f64 + ipm_hess_reduce_bcast_f64 (row-sharded Hessian over peer memory) with R ranks emulated
+def test_peer_hessian_kernels_emulated_ranks(n, m, R, int8):
+    """ipm_syrk_scatter_f64 (FP64 DMMA) or ipm_hess_i8_scatter_f64 (INT8 tensor pipe, two half tiles per 128 x 128 tile)
+    + ipm_hess_reduce_bcast_f64 (row-sharded Hessian over peer memory) with R ranks emulated
     on ONE device: every rank has its own inbox / flags / H / counter and its own stream, the "peer" pointers are
     simply the other ranks' buffers.  All R Hessians must equal C' diag(w) C + tP * P and be bit-identical."""
     rs = np.random.RandomState(n + m)
@@ -367,11 +369,22 @@ def test_peer_hessian_kernels_emulated_ranks(n, m, R):
     # Emulation on one device and ONE stream: all ranks scatter first, then every rank reduces its owned tiles (all the
     # flags it waits for are already raised) with done_target = 0, i.e. without parking the stream; the completion
     # counters are checked on the host instead.  (Real ranks run these concurrently on their own devices.)
+    i8ws = []
+    if int8:
+        for r in range(R):
+            rows = bounds[r + 1] - bounds[r]
+            buf = torch.empty(_abi.lib().ipm_hess_i8_ws_bytes(rows, n, 8), dtype=torch.uint8, device="cuda")
+            _abi.call("ipm_hess_i8_prepare", buf.data_ptr(), rows, n, 8, None)
+            i8ws.append(buf)
     for step in (1, 2):  # two consecutive "Newton steps": epochs and the running completion counters
         for r in range(R):
             Cr, ldc = Cd[r]
-            _abi.call("ipm_syrk_scatter_f64", Cr.data_ptr(), ldc, wd[r].data_ptr(), n, bounds[r + 1] - bounds[r], 1.0,
-                      None, 0, p_inbox, p_flags, r, R, slots, step, None)
+            if int8:
+                _abi.call("ipm_hess_i8_scatter_f64", Cr.data_ptr(), ldc, bounds[r + 1] - bounds[r], n, wd[r].data_ptr(), 8,
+                          i8ws[r].data_ptr(), p_inbox, p_flags, r, R, slots, step, None)
+            else:
+                _abi.call("ipm_syrk_scatter_f64", Cr.data_ptr(), ldc, wd[r].data_ptr(), n, bounds[r + 1] - bounds[r], 1.0,
+                          None, 0, p_inbox, p_flags, r, R, slots, step, None)
         for r in range(R):
             _abi.call("ipm_hess_reduce_bcast_f64", inbox[r].data_ptr(), sig[r].data_ptr(), p_H, p_done, ldh, n, r, R,
                       slots, step, 0, Pd.data_ptr(), ldp, tP, None)

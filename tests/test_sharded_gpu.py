@@ -18,9 +18,10 @@ pytestmark = pytest.mark.gpu
 CASES = {c["name"]: c for f in ("barrier_cases.json", "dual_cases.json", "large_cases.json") for c in load_golden(f)}
 
 
-def _worker(rank, world, port, name, q):
+def _worker(rank, world, port, name, q, env=None):
     import torch.distributed as dist
 
+    os.environ.update(env or {})
     # the distributed factorisation is off by default below n = 12288 (sharded_engine.PEER_POTRF_MIN_N): force it on so
     # that the n >= 512 cases here run ipm_potrf_upper_peer_f64
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), IPM_PEER_POTRF="1")
@@ -49,13 +50,13 @@ def _worker(rank, world, port, name, q):
     dist.destroy_process_group()
 
 
-def _run(name):
+def _run(name, env=None):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + os.getpid() % 1000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q, env)) for r in range(2)]
     import queue
     import time
 
@@ -89,6 +90,26 @@ def test_row_sharded_matches_reference(name):
     # n = 1024 cases also run the factorisation distributed over the two GPUs (ipm_potrf_upper_peer_f64)
     assert peer[0], peer_error
     assert peer[1] == (len(case["xstar"]) > 384), "distributed factorisation not exercised"
+    assert val == pytest.approx(case["value"], rel=1e-6, abs=1e-9)
+    prob = getattr(problems, case["generator"])(**case["generator_kwargs"])
+    if isinstance(prob, list):
+        prob = prob[case.get("index") or 0]
+    cap = case["settings"].get("max_inner_iters", 50)
+    assert_iters_close(iters, case["inner_iters"], cap=cap, noisy=noise_dominated_steps(case, prob, case["settings"]))
+    if p1 is not None:
+        assert_iters_close(p1, case["phase1_inner_iters"])
+    assert np.linalg.norm(x - np.array(case["xstar"])) <= 1e-4 * (1 + np.linalg.norm(case["xstar"]))
+
+
+@pytest.mark.parametrize("name", ["lp_dense_n1024_warm", "lp_dense_n97_ragged", "qp_dense_n512", "socp_n96_warm"])
+def test_row_sharded_int8_hessian(name):
+    """The same split with every rank's partial Hessian on the INT8 tensor pipe (ipm_hess_i8_scatter_f64: half tiles into the
+    owners' inboxes) -- what `bench.py --gpus N` runs at cfg-2 size."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    case = CASES[name]
+    val, iters, p1, x, peer, peer_error, _, _ = _run(name, {"IPM_HESSIAN_I8": "1"})
+    assert peer[0], peer_error
     assert val == pytest.approx(case["value"], rel=1e-6, abs=1e-9)
     prob = getattr(problems, case["generator"])(**case["generator_kwargs"])
     if isinstance(prob, list):
