@@ -387,7 +387,8 @@ def lp_section(D, args, prob, m, rows_mode, steps, warmup, e2e=True, profile=Tru
     L = solver.launcher
     if profile:
         L.timed_ops = {"ipm_gemm_tn_f64": [], "ipm_syrk_scatter_f64": [], "ipm_hess_i8_f64": [], "ipm_hess_i8_scatter_f64": [],
-                       "range:hessian_formation": [], "ipm_potrf_upper_f64": [], "ipm_potrf_upper_peer_f64": []}
+                       "range:hessian_formation": [], "ipm_potrf_upper_f64": [], "ipm_potrf_upper_peer_f64": [],
+                       "ipm_potrf_trsm_upper_f64": []}
     launches0 = L.kernel_launches()
     with ClockSampler(D.local_rank) as clk:
         ms, counts = D.timed(one_solve, steps)
@@ -400,8 +401,10 @@ def lp_section(D, args, prob, m, rows_mode, steps, warmup, e2e=True, profile=Tru
                        for a, b, tag in L.timed_ops[key] if tag == "hessian"]
         out["hess_i8"] = len(L.timed_ops["ipm_hess_i8_f64"]) + len(L.timed_ops["ipm_hess_i8_scatter_f64"]) > 0
         out["hform"] = [a.elapsed_time(b) for a, b, _ in L.timed_ops["range:hessian_formation"]]
-        out["potrf"] = [a.elapsed_time(b) for key in ("ipm_potrf_upper_f64", "ipm_potrf_upper_peer_f64")
+        out["potrf"] = [a.elapsed_time(b) for key in ("ipm_potrf_upper_f64", "ipm_potrf_upper_peer_f64",
+                                                       "ipm_potrf_trsm_upper_f64")
                         for a, b, _ in L.timed_ops[key]]
+        out["potrf_fused_rhs"] = len(L.timed_ops["ipm_potrf_trsm_upper_f64"]) > 0
         out["potrf_distributed"] = len(L.timed_ops["ipm_potrf_upper_peer_f64"]) > 0
         L.timed_ops = None
     del solver
@@ -514,14 +517,15 @@ def socp_section(D, args, rows_mode):
     del prob
     L = s.launcher
     L.timed_ops = {"ipm_gemm_tn_f64": [], "ipm_syrk_scatter_f64": [], "ipm_hess_i8_f64": [], "ipm_hess_i8_scatter_f64": [],
-                   "range:hessian_formation": [], "ipm_potrf_upper_f64": [], "ipm_potrf_upper_peer_f64": []}
+                   "range:hessian_formation": [], "ipm_potrf_upper_f64": [], "ipm_potrf_upper_peer_f64": [],
+                   "ipm_potrf_trsm_upper_f64": []}
     ms, counts = D.timed(lambda: (s.solve(), sum(s.inner_iters))[1], 1)
     hess = [a.elapsed_time(b) for key in ("ipm_gemm_tn_f64", "ipm_syrk_scatter_f64", "ipm_hess_i8_f64",
                                           "ipm_hess_i8_scatter_f64")
             for a, b, tag in L.timed_ops[key] if tag == "hessian"]
     hess_i8 = len(L.timed_ops["ipm_hess_i8_f64"]) + len(L.timed_ops["ipm_hess_i8_scatter_f64"]) > 0
     hform = [a.elapsed_time(b) for a, b, _ in L.timed_ops["range:hessian_formation"]]
-    potrf = [a.elapsed_time(b) for key in ("ipm_potrf_upper_f64", "ipm_potrf_upper_peer_f64")
+    potrf = [a.elapsed_time(b) for key in ("ipm_potrf_upper_f64", "ipm_potrf_upper_peer_f64", "ipm_potrf_trsm_upper_f64")
              for a, b, _ in L.timed_ops[key]]
     L.timed_ops = None
     steps = counts[0]
@@ -713,6 +717,9 @@ def main():
                                   "what": ("ipm_potrf_upper_peer_f64: tile-DAG Cholesky distributed over the GPUs (block "
                                            "columns dealt over the ranks, rows pushed over NVLink); aggregate rate over "
                                            "all GPUs" if r.get("potrf_distributed") else
+                                           "ipm_potrf_trsm_upper_f64 (pipelined tile-DAG kernel with the Newton right-hand "
+                                           "side as an extra block column: factorisation + forward solve in one launch)"
+                                           if r.get("potrf_fused_rhs") else
                                            "ipm_potrf_upper_f64 (pipelined tile-DAG kernel at this size)") +
                                           ", CUDA events around every call inside the timed solves; n^3/3 flop"}
     if hform_ms:

@@ -479,6 +479,17 @@ class LinearNewton:
         ws = self.ws
         self.L("ipm_potrf_upper_f64", ws.H.data_ptr(), ws.ldh, self.nz, ws.info.data_ptr())
 
+    def _fuse_forward(self):
+        """Forward solve of the Newton right-hand side inside the factorisation launch: from the size where the
+        single-launch tile-DAG Cholesky is the default (csrc/chol.cu, dag::kAutoMinN).  IPM_FUSE_FORWARD=0 switches it off."""
+        return self.nz >= 2048 and os.environ.get("IPM_FUSE_FORWARD", "1") != "0"
+
+    def _rhs_column(self):
+        ws = self.ws
+        if getattr(ws, "rhs1", None) is None:
+            ws.rhs1 = torch.zeros((self.nz, 16), dtype=F64, device=self.d.device)  # TMA: 16-byte row stride, even ld
+        return ws.rhs1
+
     def _chol_solve_vec(self, vec):
         """vec <- H^{-1} vec using the factor in ws.H."""
         ws, L = self.ws, self.L
@@ -571,9 +582,19 @@ class LinearNewton:
             self._cg_direction(z)
         else:
             self._hessian(t)
-            self._factor()
             L("ipm_lincomb3_f64", self.nz, -1.0, ws.g.data_ptr(), 0.0, None, 0.0, None, ws.dz.data_ptr())
-            self._chol_solve_vec(ws.dz)
+            if self._fuse_forward():
+                # ONE launch: H = U'U and f = U^{-T}(-g) -- the right-hand side rides along as an extra block column of
+                # the tile DAG (as [A' | g] does in the equality-constrained step); only the backward solve remains
+                rhs = self._rhs_column()
+                rhs[:, 0].copy_(ws.dz)
+                L("ipm_potrf_trsm_upper_f64", ws.H.data_ptr(), ws.ldh, self.nz, rhs.data_ptr(), rhs.stride(0), 1,
+                  ws.info.data_ptr())
+                ws.dz.copy_(rhs[:, 0])
+                L("ipm_trsv_upper_f64", ws.H.data_ptr(), ws.ldh, self.nz, ws.dz.data_ptr(), 0, ws.tr_ws.data_ptr())
+            else:
+                self._factor()
+                self._chol_solve_vec(ws.dz)
         self._feasibility(z)
         pairs = self._objective_pairs(z, lin) + [(ws.g, z, self.nz), (ws.g, ws.dz, self.nz)]
         self._dots(pairs)

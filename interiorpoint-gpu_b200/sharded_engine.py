@@ -143,6 +143,9 @@ class _RowSharded:
           d.n, self.rank, self.world, pr["slots"], pr["epoch"], pr["target"], _abi.ptr(P), ldp, tP)
         self.comm_bytes += 2 * pr["tiles"] * 128 * 128 * 8 * (self.world - 1) // self.world
 
+    def _fuse_forward(self):
+        return super()._fuse_forward() and not getattr(self, "peer_potrf", False)  # the distributed kernel has no RHS
+
     def _factor(self):
         """Distributed tile-DAG Cholesky over the ranks: block column j on rank j % R, finished rows pushed into every
         rank's copy of H over NVLink, so every rank ends with the whole factor (the triangular solves stay replicated)."""
