@@ -67,9 +67,10 @@ long long ipm_hess_i8_ws_bytes(int m, int n, int slices);
 int ipm_hess_i8_prepare(void* ws, int m, int n, int slices, void* stream);
 int ipm_hess_i8_f64(const double* C, int ldc, int m, int n, const double* w, double beta, double* H, int ldh, int slices,
                     void* ws, void* stream);
-/* Row-sharded variant: the partial C_r^T diag(w) C_r of this rank's m local rows, scattered tile by tile into the owners'
- * inboxes; drop-in for ipm_syrk_scatter_f64 below (same peer arrays, slots and epoch; no local addend), to be followed
- * by ipm_hess_reduce_bcast_f64. */
+/* Row-sharded variant: the partial C_r^T diag(w) C_r of this rank's m local rows, filed tile by tile under the owners in
+ * this rank's exchange buffer and announced through the owners' flags (same peer arrays, slots and epoch as
+ * ipm_syrk_scatter_f64 below; no local addend); to be followed by ipm_hess_reduce_bcast_pull_f64, in which the owners
+ * pull the tiles over NVLink. */
 int ipm_hess_i8_scatter_f64(const double* C, int ldc, int m, int n, const double* w, int slices, void* ws,
                             void* const* peer_inbox, void* const* peer_flags, int me, int R, int slots,
                             unsigned int epoch, void* stream);
@@ -99,6 +100,11 @@ int ipm_syrk_scatter_f64(const double* C, int ldc, const double* w, int n, int K
 int ipm_hess_reduce_bcast_f64(const double* inbox, const unsigned int* flags, void* const* peer_H,
                               void* const* peer_done, int ldh, int n, int me, int R, int slots, unsigned int epoch,
                               unsigned int done_target, const double* P, int ldp, double tP, void* stream);
+/* The same after ipm_hess_i8_scatter_f64: the partial tiles are read from the buffers of the ranks that computed them
+ * (peer_inbox: R device pointers, host array) with coalesced loads over NVLink instead of being pushed. */
+int ipm_hess_reduce_bcast_pull_f64(void* const* peer_inbox, const unsigned int* flags, void* const* peer_H,
+                                   void* const* peer_done, int ldh, int n, int me, int R, int slots, unsigned int epoch,
+                                   unsigned int done_target, const double* P, int ldp, double tP, void* stream);
 
 /* ---- L2 residency ----------------------------------------------------------------------------------------- */
 /* Mark [base, base + bytes) as persisting in L2 for kernels launched on `stream` (bytes == 0: clear).  *ratio_out

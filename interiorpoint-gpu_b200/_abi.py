@@ -39,6 +39,8 @@ SIGNATURES = {
                                   _dp]),
     "ipm_hess_reduce_bcast_f64": (_i, [_dp, _dp, C.POINTER(_dp), C.POINTER(_dp), _i, _i, _i, _i, _i, C.c_uint, C.c_uint,
                                        _dp, _i, _d, _dp]),
+    "ipm_hess_reduce_bcast_pull_f64": (_i, [C.POINTER(_dp), _dp, C.POINTER(_dp), C.POINTER(_dp), _i, _i, _i, _i, _i, C.c_uint,
+                                            C.c_uint, _dp, _i, _d, _dp]),
     "ipm_l2_persist": (_i, [_dp, C.c_ulonglong, C.POINTER(_d), _dp]),
     "ipm_csr_gemv_f64": (_i, [_dp, _dp, _dp, _i, _dp, _dp, _d, _d, _dp]),
     "ipm_sparse_syrk_f64": (_i, [_i, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp]),

@@ -281,7 +281,13 @@ struct PeerHs {
 
 // One CTA per owned tile (grid-stride): wait for the R partials, add them in rank order, write the final tile into
 // every rank's H (upper part only), count it as delivered there.
-__global__ void __launch_bounds__(256) hess_reduce_bcast_kernel(const double* __restrict__ inbox,
+// pull.inbox[0] != nullptr: the partials stay where they were computed (rank src keeps [owner][slot] tiles, written by
+// ipm_hess_i8_scatter_f64) and the owner reads them over NVLink with coalesced loads; otherwise they were pushed into this
+// rank's inbox ([src][slot], ipm_syrk_scatter_f64).
+struct PullSrc {
+  const double* inbox[kMaxPeers];
+};
+__global__ void __launch_bounds__(256) hess_reduce_bcast_kernel(const double* __restrict__ inbox, PullSrc pull,
                                                                 const unsigned int* __restrict__ flags, PeerHs out,
                                                                 long long ldh, int n, int T, int me, int R, int slots,
                                                                 unsigned int epoch, const double* __restrict__ P,
@@ -311,7 +317,9 @@ __global__ void __launch_bounds__(256) hess_reduce_bcast_kernel(const double* __
 #pragma unroll
     for (int q = 0; q < 32; ++q) sum[q] = make_double2(0.0, 0.0);
     for (int src = 0; src < R; ++src) {
-      const double2* p = reinterpret_cast<const double2*>(inbox + ((size_t)src * slots + slot) * kTileElems);
+      const double2* p = reinterpret_cast<const double2*>(
+          pull.inbox[0] ? pull.inbox[src] + ((size_t)me * slots + slot) * kTileElems
+                        : inbox + ((size_t)src * slots + slot) * kTileElems);
 #pragma unroll
       for (int q = 0; q < 32; ++q) {
         const double2 v = __ldcg(p + threadIdx.x + 256 * q);
@@ -416,14 +424,16 @@ extern "C" int ipm_syrk_scatter_f64(const double* Cm, int ldc, const double* w, 
 // Reduce the owned tiles and deliver them to every rank's H; then wait (on the stream) until this rank's H is complete.
 //   done_target: value this rank's completion counter reaches once all tiles of this step have arrived
 //   (callers add #tiles per step to a running target).  P (optional, n x ldp, replicated): t * P is added by the owner.
-extern "C" int ipm_hess_reduce_bcast_f64(const double* inbox, const unsigned int* flags, void* const* peer_H,
-                                         void* const* peer_done, int ldh, int n, int me, int R, int slots,
-                                         unsigned int epoch, unsigned int done_target, const double* P, int ldp,
-                                         double tP, void* stream) {
-  if (!inbox || !flags || !peer_H || !peer_done || n <= 0 || ldh < n || (ldh & 1) || R < 1 || R > kMaxPeers || me < 0 ||
-      me >= R)
+static int reduce_bcast(const double* inbox, void* const* peer_inbox, const unsigned int* flags, void* const* peer_H,
+                        void* const* peer_done, int ldh, int n, int me, int R, int slots, unsigned int epoch,
+                        unsigned int done_target, const double* P, int ldp, double tP, void* stream) {
+  if ((!inbox && !peer_inbox) || !flags || !peer_H || !peer_done || n <= 0 || ldh < n || (ldh & 1) || R < 1 ||
+      R > kMaxPeers || me < 0 || me >= R)
     return IPM_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+  PullSrc pull = {};
+  if (peer_inbox)
+    for (int r = 0; r < R; ++r) pull.inbox[r] = (const double*)peer_inbox[r];
   PeerHs out;
   for (int r = 0; r < kMaxPeers; ++r) {
     out.H[r] = r < R ? (double*)peer_H[r] : nullptr;
@@ -432,10 +442,31 @@ extern "C" int ipm_hess_reduce_bcast_f64(const double* inbox, const unsigned int
   const int T = ceil_div(n, gemm::BN);
   int grid = slots < 296 ? slots : 296;
   if (grid < 1) grid = 1;
-  hess_reduce_bcast_kernel<<<grid, 256, 0, st>>>(inbox, flags, out, ldh, n, T, me, R, slots, epoch, P, ldp, tP,
+  hess_reduce_bcast_kernel<<<grid, 256, 0, st>>>(inbox, pull, flags, out, ldh, n, T, me, R, slots, epoch, P, ldp, tP,
                                                  ipm_internal_fault_word());
   IPM_LAUNCH_CHECK();
   hess_wait_kernel<<<1, 1, 0, st>>>((const unsigned int*)peer_done[me], done_target, ipm_internal_fault_word());
   IPM_LAUNCH_CHECK();
   return IPM_OK;
+}
+
+extern "C" int ipm_hess_reduce_bcast_f64(const double* inbox, const unsigned int* flags, void* const* peer_H,
+                                         void* const* peer_done, int ldh, int n, int me, int R, int slots,
+                                         unsigned int epoch, unsigned int done_target, const double* P, int ldp,
+                                         double tP, void* stream) {
+  if (!inbox) return IPM_ERR_ARG;
+  return reduce_bcast(inbox, nullptr, flags, peer_H, peer_done, ldh, n, me, R, slots, epoch, done_target, P, ldp, tP,
+                      stream);
+}
+
+// The same reduction when the partial tiles were left in the producers' buffers (ipm_hess_i8_scatter_f64): rank src
+// keeps the tiles it computed for owner o at peer_inbox[src] + (o * slots + slot) tiles, and raised o's flag; the owner
+// pulls them over NVLink (512-byte coalesced loads) instead of receiving 16-byte remote stores from the epilogue.
+extern "C" int ipm_hess_reduce_bcast_pull_f64(void* const* peer_inbox, const unsigned int* flags, void* const* peer_H,
+                                              void* const* peer_done, int ldh, int n, int me, int R, int slots,
+                                              unsigned int epoch, unsigned int done_target, const double* P, int ldp,
+                                              double tP, void* stream) {
+  if (!peer_inbox) return IPM_ERR_ARG;
+  return reduce_bcast(nullptr, peer_inbox, flags, peer_H, peer_done, ldh, n, me, R, slots, epoch, done_target, P, ldp, tP,
+                      stream);
 }

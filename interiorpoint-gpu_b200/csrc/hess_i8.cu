@@ -191,8 +191,9 @@ struct Args {
   long long ldh;
   double beta;
   unsigned int* fault;
-  // row-sharded mode (SCATTER): the 128 x 64 partial tile goes into the inbox of the rank that owns the 128 x 128 tile
-  // it is one half of (same inbox / flag protocol as PeerScatterEpilogue in gemm_tn.cu)
+  // row-sharded mode (SCATTER): the 128 x 64 partial tile is filed in this rank's own exchange buffer under the rank
+  // that owns the 128 x 128 tile it is one half of, and that owner's flag is raised (flags as PeerScatterEpilogue in
+  // gemm_tn.cu; the owner then PULLS the tile: remote 16-byte stores from this epilogue cost 60 us per tile)
   double* inbox[8];
   unsigned int* flags[8];
   unsigned int* halves;  // per 128 x 128 tile: half tiles stored so far (the second one raises the owner's flag)
@@ -341,7 +342,8 @@ syrk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if constexpr (SCATTER) {
         const int T = (a.n + 127) / 128, ti = tl.x, tj = tl.y >> 1;
         scatter_t = ti * T - ti * (ti - 1) / 2 + (tj - ti);  // upper_tile_index of gemm_tn.cu
-        scatter_dst = a.inbox[scatter_t % a.R] + ((size_t)a.me * a.slots + scatter_t / a.R) * (128 * 128) + 64 * (tl.y & 1);
+        // the tile stays in THIS rank's buffer, filed under its owner: the owner pulls it (ipm_hess_reduce_bcast_pull_f64)
+        scatter_dst = a.inbox[a.me] + ((size_t)(scatter_t % a.R) * a.slots + scatter_t / a.R) * (128 * 128) + 64 * (tl.y & 1);
       }
       for (int c0 = 0; c0 < TN; c0 += 8) {
         int v[SMAX][8];
@@ -564,9 +566,10 @@ extern "C" int ipm_hess_i8_f64(const double* C, int ldc, int m, int n, const dou
   return run_hess_i8(C, ldc, m, n, w, beta, H, ldh, slices, ws, nullptr, nullptr, 0, 1, 0, 0, stream);
 }
 
-// Row-sharded variant: the partial Hessian of this rank's m local rows, scattered tile by tile into the owners' inboxes
-// -- the drop-in for ipm_syrk_scatter_f64 (same inbox layout, flags, slots and epoch; no local addend), to be followed
-// by ipm_hess_reduce_bcast_f64.  A 128 x 128 tile arrives as two 128 x 64 halves from two CTAs; the one that stores
+// Row-sharded variant: the partial Hessian of this rank's m local rows, filed tile by tile under the owners in this
+// rank's exchange buffer (peer_inbox[me] + (owner * slots + slot) tiles), the owners' flags raised as by
+// ipm_syrk_scatter_f64 (same buffers, slots and epoch; no local addend); to be followed by
+// ipm_hess_reduce_bcast_pull_f64.  A 128 x 128 tile is finished as two 128 x 64 halves by two CTAs; the one that stores
 // second raises the owner's flag.
 extern "C" int ipm_hess_i8_scatter_f64(const double* C, int ldc, int m, int n, const double* w, int slices, void* ws,
                                        void* const* peer_inbox, void* const* peer_flags, int me, int R, int slots,

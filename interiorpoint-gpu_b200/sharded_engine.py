@@ -131,17 +131,32 @@ class _RowSharded:
         pr["epoch"] += 1
         pr["target"] = (pr["target"] + pr["tiles"]) & 0xFFFFFFFF
         L.tag = "hessian"
-        slices = hess_i8_slices(K, d.n)  # this rank's rows on the INT8 tensor pipe (csrc/hess_i8.cu), same exchange
+        slices = self._shard_i8_slices(K)
         if slices:
+            # this rank's rows on the INT8 tensor pipe (csrc/hess_i8.cu): the partial tiles stay in this rank's exchange
+            # buffer, filed under their owners, who pull them over NVLink
             L("ipm_hess_i8_scatter_f64", rows_ptr, ld, K, d.n, w_ptr, slices, self._hess_i8_ws(slices, K).data_ptr(),
               pr["p_inbox"], pr["p_flags"], self.rank, self.world, pr["slots"], pr["epoch"])
+            L.tag = None
+            L("ipm_hess_reduce_bcast_pull_f64", pr["p_inbox"], pr["sig"].data_ptr(), pr["p_H"], pr["p_done"], ws.ldh, d.n,
+              self.rank, self.world, pr["slots"], pr["epoch"], pr["target"], _abi.ptr(P), ldp, tP)
         else:
             L("ipm_syrk_scatter_f64", rows_ptr, ld, w_ptr, d.n, K, 1.0, None, 0, pr["p_inbox"], pr["p_flags"], self.rank,
               self.world, pr["slots"], pr["epoch"])
-        L.tag = None
-        L("ipm_hess_reduce_bcast_f64", pr["inbox"].data_ptr(), pr["sig"].data_ptr(), pr["p_H"], pr["p_done"], ws.ldh,
-          d.n, self.rank, self.world, pr["slots"], pr["epoch"], pr["target"], _abi.ptr(P), ldp, tP)
+            L.tag = None
+            L("ipm_hess_reduce_bcast_f64", pr["inbox"].data_ptr(), pr["sig"].data_ptr(), pr["p_H"], pr["p_done"], ws.ldh,
+              d.n, self.rank, self.world, pr["slots"], pr["epoch"], pr["target"], _abi.ptr(P), ldp, tP)
         self.comm_bytes += 2 * pr["tiles"] * 128 * 128 * 8 * (self.world - 1) // self.world
+
+    def _shard_i8_slices(self, K):
+        """Digits of the INT8 Hessian kernel for this rank's K rows, or 0 -- agreed on by all ranks (push and pull
+        exchanges do not mix; the row blocks differ by one row at most, but a threshold may fall between them)."""
+        cache = self.__dict__.setdefault("_i8_agreed", {})
+        if K not in cache:
+            t = torch.tensor([hess_i8_slices(K, self.d.n)], dtype=torch.int32, device=self.d.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+            cache[K] = int(t.item())
+        return cache[K]
 
     def _fuse_forward(self):
         return super()._fuse_forward() and not getattr(self, "peer_potrf", False)  # the distributed kernel has no RHS

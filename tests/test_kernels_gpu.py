@@ -386,8 +386,12 @@ def test_peer_hessian_kernels_emulated_ranks(n, m, R, int8):
                 _abi.call("ipm_syrk_scatter_f64", Cr.data_ptr(), ldc, wd[r].data_ptr(), n, bounds[r + 1] - bounds[r], 1.0,
                           None, 0, p_inbox, p_flags, r, R, slots, step, None)
         for r in range(R):
-            _abi.call("ipm_hess_reduce_bcast_f64", inbox[r].data_ptr(), sig[r].data_ptr(), p_H, p_done, ldh, n, r, R,
-                      slots, step, 0, Pd.data_ptr(), ldp, tP, None)
+            if int8:  # the owners pull the partial tiles from the buffers of the ranks that computed them
+                _abi.call("ipm_hess_reduce_bcast_pull_f64", p_inbox, sig[r].data_ptr(), p_H, p_done, ldh, n, r, R, slots,
+                          step, 0, Pd.data_ptr(), ldp, tP, None)
+            else:
+                _abi.call("ipm_hess_reduce_bcast_f64", inbox[r].data_ptr(), sig[r].data_ptr(), p_H, p_done, ldh, n, r, R,
+                          slots, step, 0, Pd.data_ptr(), ldp, tP, None)
         torch.cuda.synchronize()
         for r in range(R):
             assert int(sig[r][slots * R].item()) == step * tiles   # every tile of this step was delivered to rank r
