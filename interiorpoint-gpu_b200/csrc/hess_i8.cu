@@ -62,36 +62,56 @@ __global__ void __launch_bounds__(128) colmax_kernel(const double* __restrict__ 
   const int k0 = blockIdx.y * 128, k1 = min(m, k0 + 128);
   if (i >= n) return;
   double mx = 0.0;
+  bool bad = false;  // NaN (negative or NaN weight, NaN entry) or inf: must reach H as it does in the FP64 kernel
 #pragma unroll 8
-  for (int k = k0; k < k1; ++k) mx = fmax(mx, sqrt(w[k]) * fabs(C[(long long)k * ldc + i]));
-  if (mx > 0.0) atomicMax(amax + i, (unsigned long long)__double_as_longlong(mx));  // non-negative doubles order as integers
+  for (int k = k0; k < k1; ++k) {
+    const double v = sqrt(w[k]) * fabs(C[(long long)k * ldc + i]);
+    bad |= !(v <= 1.7976931348623157e308);
+    mx = fmax(mx, v);
+  }
+  if (bad)  // non-negative doubles order as integers, the NaN pattern above all of them
+    atomicMax(amax + i, 0x7FF8000000000000ull);
+  else if (mx > 0.0)
+    atomicMax(amax + i, (unsigned long long)__double_as_longlong(mx));
 }
 
-constexpr int SL_COLS = 32, SL_K = 128, SL_PITCH = SL_K + 4;
+constexpr int SL_COLS = 32, SL_K = 128, SL_PITCHW = SL_K / 4 + 1;  // tile rows of 32 words (128 digits) + 1 word of padding
 __global__ void __launch_bounds__(256) slice_kernel(const double* __restrict__ C, long long ldc, int m, int n,
                                                     const double* __restrict__ w,
                                                     const unsigned long long* __restrict__ amax, int s,
                                                     int8_t* __restrict__ Q, long long n_pad, long long k_pad,
                                                     double* __restrict__ sigma) {
-  __shared__ __align__(16) int8_t tile[SMAX * SL_COLS * SL_PITCH];
-  const int ci = threadIdx.x & 31, kr = threadIdx.x >> 5;
+  __shared__ uint32_t tile[SMAX * SL_COLS * SL_PITCHW];  // [slice][column][4 consecutive k per word]
+  const int ci = threadIdx.x & 31, kq0 = threadIdx.x >> 5;
   const int i = blockIdx.x * SL_COLS + ci, k0 = blockIdx.y * SL_K;
   double inv = 0.0;
   if (i < n) {
     const unsigned long long ef = amax[i] >> 52;  // exponent field of amax (its sign bit is 0); 0: column of zeros
-    if (ef != 0) inv = __longlong_as_double((long long)(2044ull - ef) << 52);  // 2^-(E+2)
-    if (blockIdx.y == 0 && kr == 0) sigma[i] = ef != 0 ? __longlong_as_double((long long)(ef + 2ull) << 52) : 0.0;
+    const bool finite = ef < 0x7FDull;            // inf / NaN / about to overflow: the column of H becomes NaN
+    if (ef != 0 && finite) inv = __longlong_as_double((long long)(2044ull - ef) << 52);  // 2^-(E+2)
+    if (blockIdx.y == 0 && kq0 == 0)
+      sigma[i] = !finite ? __longlong_as_double(0x7FF8000000000000ll)
+                         : (ef != 0 ? __longlong_as_double((long long)(ef + 2ull) << 52) : 0.0);
   }
-  const double magic = 6755399441055744.0;  // 1.5 * 2^52: (r + magic) - magic = rint(r), low mantissa bits = the integer
-  for (int kk = kr; kk < SL_K; kk += 8) {
-    const int k = k0 + kk;
-    double r = 0.0;
-    if (i < n && k < m) r = sqrt(w[k]) * C[(long long)k * ldc + i] * inv;  // |r| <= 1/2
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52: r + magic has rint(r) in its low mantissa bits
+#pragma unroll
+  for (int g = 0; g < SL_K / 32; ++g) {     // 4 consecutive k per thread and pass: one packed word per slice
+    const int kq = kq0 + 8 * g;
+    double r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = k0 + 4 * kq + e;
+      r[e] = (i < n && k < m) ? sqrt(w[k]) * C[(long long)k * ldc + i] * inv : 0.0;  // |r| <= 1/2
+    }
     for (int t = 0; t < s; ++t) {
-      r *= 128.0;
-      const double tmp = r + magic;
-      r -= tmp - magic;  // exact; the remainder stays in [-1/2, 1/2]
-      tile[(t * SL_COLS + ci) * SL_PITCH + kk] = (int8_t)(int)__double2loint(tmp);
+      uint32_t word = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const double tmp = fma(r[e], 128.0, magic);  // r * 128 is exact: one rounding, to the nearest integer
+        r[e] = fma(r[e], 128.0, magic - tmp);        // exact; the remainder stays in [-1/2, 1/2]
+        word |= ((uint32_t)__double2loint(tmp) & 0xFFu) << (8 * e);
+      }
+      tile[(t * SL_COLS + ci) * SL_PITCHW + kq] = word;
     }
   }
   __syncthreads();
@@ -100,8 +120,7 @@ __global__ void __launch_bounds__(256) slice_kernel(const double* __restrict__ C
     const int t = row / SL_COLS, c = row % SL_COLS;
     const long long gi = (long long)blockIdx.x * SL_COLS + c;
     if (gi >= n) continue;
-    const uint32_t v = *reinterpret_cast<const uint32_t*>(&tile[row * SL_PITCH + lane * 4]);
-    *reinterpret_cast<uint32_t*>(Q + ((long long)t * n_pad + gi) * k_pad + k0 + lane * 4) = v;
+    *reinterpret_cast<uint32_t*>(Q + ((long long)t * n_pad + gi) * k_pad + k0 + lane * 4) = tile[row * SL_PITCHW + lane];
   }
 }
 

@@ -624,3 +624,17 @@ def test_hess_i8_rejects_bad_arguments():
     assert L.ipm_hess_i8_ws_bytes(100, 64, 9) == 0 and L.ipm_hess_i8_ws_bytes(100, 64, 0) == 0
     assert L.ipm_hess_i8_ws_bytes(70000, 64, 8) == 0       # INT32 accumulators: m <= 65408
     assert L.ipm_hess_i8_ws_bytes(100, 64, 8) > 8 * 128 * 128
+
+
+def test_hess_i8_propagates_nan_like_the_fp64_kernel():
+    """A NaN (or negative) weight must not turn into finite garbage: the affected entries of H are NaN, so the
+    factorisation reports the failure exactly as it does behind the FP64 kernel."""
+    n, m = 200, 300
+    rs = np.random.RandomState(5)
+    Cm, ldc = padded(rs.randn(m, n))
+    wn = rs.rand(m) + 0.1
+    wn[7] = np.nan
+    wn[11] = -1.0
+    H, ldh = padded(np.zeros((n, n)))
+    _hess_i8(Cm, ldc, m, n, dev(wn), 0.0, H, ldh, 8)
+    assert torch.isnan(torch.triu(H[:, :n])[torch.triu(torch.ones((n, n), dtype=torch.bool, device="cuda"))]).all()
