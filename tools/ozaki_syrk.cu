@@ -1,4 +1,5 @@
-// EXPERIMENT (tools/, not on the product path): the Hessian contraction H = C' diag(w) C in FP64 accuracy on the INT8
+// EXPERIMENT RECORD (tools/, not on the product path; the kernel that grew out of it is interiorpoint-gpu_b200/csrc/hess_i8.cu,
+// which has since replaced the issue loop below -- see its header): the Hessian contraction H = C' diag(w) C in FP64 accuracy on the INT8
 // tensor pipe of sm_100a (tcgen05.mma.kind::i8, accumulators in TMEM), by error-free slicing along the contraction index
 // (Ozaki scheme).  tools/ozaki_probe.py measured the idea with a library INT8 GEMM; this is the hand-written kernel.
 //
