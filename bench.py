@@ -284,6 +284,8 @@ def int8_hessian_roofline(n, m, hess_ms, launches, slices=8):
             "kernel": "ipm_hess_i8_f64 = colmax_kernel + slice_kernel + syrk_kernel (tcgen05.mma.kind::i8, 8 x 7-bit digits "
                       "per entry, FP64-accurate)",
             "int8_ops_per_launch": ops, "ms_per_launch": hess_ms, "launches_timed": launches,
+            "frac_of_nominal_dense_int8_peak": achieved / 4500.0 if achieved else None,  # NVIDIA dense INT8 figure, 4.5 POP/s
+            "frac_of_2x_measured_bf16_peak": achieved / (2 * 1642.0) if achieved else None,  # MEASURED_PEAKS.json bf16 burst x 2
             "fp64_equivalent_tflops": fp64_equiv,
             "fp64_equivalent_vs_dmma_peak": fp64_equiv / FP64_TENSOR_PEAK_TFLOPS if fp64_equiv else None,
             "peak_source": "library INT8 GEMM measured on this pool (see INT8_TENSOR_PEAK_TOPS in bench.py); the FP64-"
