@@ -399,10 +399,10 @@ syrk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int c = 0; c < 8; c += 2) {
                 const double2 sj = *reinterpret_cast<const double2*>(a.sigma + j0 + c);
                 double2 h = make_double2(out[c] * sj.x, out[c + 1] * sj.y);
-                if (a.beta != 0.0) {
+                if (a.beta != 0.0) {  // only the upper triangle of H is defined on entry
                   const double2 old = *reinterpret_cast<const double2*>(dst + c);
-                  h.x = fma(a.beta, old.x, h.x);
-                  h.y = fma(a.beta, old.y, h.y);
+                  if (j0 + c >= i) h.x = fma(a.beta, old.x, h.x);
+                  if (j0 + c + 1 >= i) h.y = fma(a.beta, old.y, h.y);
                 }
                 *reinterpret_cast<double2*>(dst + c) = h;
               }
@@ -410,7 +410,7 @@ syrk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int c = 0; c < 8; ++c)
                 if (j0 + c < a.n) {
                   const double h = out[c] * a.sigma[j0 + c];
-                  dst[c] = a.beta != 0.0 ? fma(a.beta, dst[c], h) : h;
+                  dst[c] = (a.beta != 0.0 && j0 + c >= i) ? fma(a.beta, dst[c], h) : h;
                 }
             }
           }

@@ -584,7 +584,8 @@ def test_hess_i8_matches_fp64(n, m, slices, beta, decades):
     Cm, ldc = padded(Cn)
     w = dev(wn)
     H0 = np.triu(rs.rand(n, n)) if beta else np.zeros((n, n))
-    H, ldh = padded(H0 if beta else np.full((n, n), np.nan))
+    # only the upper triangle of H is defined on entry (the engine never writes the lower one): NaN below the diagonal
+    H, ldh = padded(H0 + np.tril(np.full((n, n), np.nan), -1) if beta else np.full((n, n), np.nan))
     _hess_i8(Cm, ldc, m, n, w, beta, H, ldh, slices)
     X = np.sqrt(wn)[:, None] * Cn
     ref = beta * H0 + X.T @ X

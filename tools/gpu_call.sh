@@ -2,5 +2,5 @@
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 300 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/smoke31.log 2>&1; echo "smoke rc=$?"
-tail -6 gpurun_out/smoke31.log
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_gpu32.log 2>&1; echo "pytest rc=$?"
+tail -6 gpurun_out/pytest_gpu32.log
