@@ -207,3 +207,40 @@ def test_int8_hessian_policy(monkeypatch):
     assert engine.hess_i8_slices(70000, 64) == 0          # INT32 accumulators bound the contraction length
     monkeypatch.setenv("IPM_HESSIAN_I8", "6")
     assert engine.hess_i8_slices(100, 64) == 6
+
+
+def test_int8_hessian_scheme_on_the_cpu():
+    """The arithmetic of csrc/hess_i8.cu restated in NumPy (no GPU): digits by the same recurrence, exact integer slice-pair
+    products, FP64 recombination.  (1) 8 digits reach the FP64 kernel's error class on weights spanning 20 decades;
+    (2) every digit lies in [-64, 64]; (3) the INT32 accumulators cannot overflow for the longest contraction the library
+    accepts (ipm_hess_i8_ws_bytes refuses m > 65408)."""
+    rs = np.random.RandomState(0)
+    m, n, s = 300, 40, 8
+    Cm = rs.rand(m, n) * 4 - 2
+    w = 10.0 ** (rs.rand(m) * 20 - 10)
+    X = np.sqrt(w)[:, None] * Cm
+    amax = np.abs(X).max(axis=0)
+    e = np.frexp(amax)[1]                      # amax = f 2^e, f in [1/2, 1): sigma = 2^(e + 1) >= 2 amax
+    sigma = np.ldexp(1.0, e + 1)
+    r = X / sigma
+    Q = []
+    for _ in range(s):
+        r = r * 128.0
+        q = np.rint(r)
+        assert np.abs(q).max() <= 64
+        Q.append(q.astype(np.int64))
+        r = r - q
+        assert np.abs(r).max() <= 0.5
+    H = np.zeros((n, n))
+    for d in range(s - 1, -1, -1):             # Horner over the diagonals t + u = d, as the epilogue does
+        acc = sum(Q[t].T @ Q[d - t] for t in range(d + 1))
+        assert np.abs(acc).max() < 2 ** 31
+        H = H * 2.0 ** -7 + acc
+    H = H * 2.0 ** -14 * sigma[:, None] * sigma[None, :]
+    ref = X.T @ X
+    scale = np.abs(X).T @ np.abs(X)
+    assert (np.abs(H - ref) / scale).max() < 1e-14
+    # worst case: all digits +-64, 8 slice pairs on one diagonal, the longest padded contraction
+    assert 8 * 65408 * 64 * 64 < 2 ** 31
+    from ipm_b200 import _abi
+    assert _abi.lib().ipm_hess_i8_ws_bytes(65408, 128, 8) > 0 and _abi.lib().ipm_hess_i8_ws_bytes(65409, 128, 8) == 0
