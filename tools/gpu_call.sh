@@ -2,6 +2,10 @@
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-N=$(nvidia-smi -L | wc -l)
-IPM_PEER_POTRF=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 2 --warmup 1 --sections none --no-e2e > gpurun_out/bench_n${N}_peerpotrf.json 2> gpurun_out/bench_n${N}_peerpotrf.err; echo "bench n$N rc=$?"
-cat gpurun_out/bench_n${N}_peerpotrf.json | cut -c1-600; grep -v "^\s*$" gpurun_out/bench_n${N}_peerpotrf.err | grep -v Warning | tail -8
+timeout 200 python -c "
+import cProfile, pstats, sys, runpy
+sys.argv=['tools/socp_probe.py','16384']
+cProfile.run('runpy.run_path(\"tools/socp_probe.py\", run_name=\"__main__\")', 'gpurun_out/socp.prof')
+p=pstats.Stats('gpurun_out/socp.prof'); p.sort_stats('tottime').print_stats(22)
+" > gpurun_out/socp_cprofile.log 2>&1; echo "rc=$?"
+grep -A40 "tottime" gpurun_out/socp_cprofile.log | cut -c1-160 | head -45
