@@ -686,6 +686,9 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "strong" if rows_mode else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfg, "step": "one complete LPSolver.solve() (all centering steps of the barrier method)",
+        "arithmetic": ("FP64 throughout; the Hessian contraction runs on the INT8 tensor cores as exact products of 8 signed "
+                       "7-bit digits per FP64 entry, recombined in FP64 (2e-15 of sum |x||x|, the FP64 kernel's class)"
+                       if r.get("hess_i8") else "FP64 throughout (DMMA tensor cores)"),
         "time_to_solve_s": ms * 1e-3 / args.steps,
         "newton_steps_per_solve": newton / args.steps / (1 if (rows_mode or D.world == 1) else D.world),
         "objective": r["value_obj"], "gpu_launches": int(r["launches"]), "clocks": r["clocks"],
