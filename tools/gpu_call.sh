@@ -2,10 +2,5 @@
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 200 python -c "
-import cProfile, pstats, sys, runpy
-sys.argv=['tools/socp_probe.py','16384']
-cProfile.run('runpy.run_path(\"tools/socp_probe.py\", run_name=\"__main__\")', 'gpurun_out/socp.prof')
-p=pstats.Stats('gpurun_out/socp.prof'); p.sort_stats('tottime').print_stats(22)
-" > gpurun_out/socp_cprofile.log 2>&1; echo "rc=$?"
-grep -A40 "tottime" gpurun_out/socp_cprofile.log | cut -c1-160 | head -45
+timeout 900 python bench.py > gpurun_out/bench38.json 2> gpurun_out/bench38.err; echo "bench rc=$?"
+cat gpurun_out/bench38.json | cut -c1-900; tail -3 gpurun_out/bench38.err
