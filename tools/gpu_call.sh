@@ -1,6 +1,12 @@
 #!/bin/bash
+# Scratch driver for one gpurun call (rewritten per call during development).  This is the round's final check:
+#   gpurun --timeout 1700 -- 'bash tools/gpu_call.sh > gpurun_out/call.log 2>&1'
 set -x
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 900 python bench.py > gpurun_out/bench38.json 2> gpurun_out/bench38.err; echo "bench rc=$?"
-cat gpurun_out/bench38.json | cut -c1-900; tail -3 gpurun_out/bench38.err
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+tail -6 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"
+tail -4 gpurun_out/smoke.log
+timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
+cut -c1-600 gpurun_out/bench.json
